@@ -1,0 +1,178 @@
+/* slime_b200 C-ABI: the drop-in boundary of the B200-native SliME prefill path.
+ *
+ * The reference (yfzhang114/SliME) has no FFI of its own - its seam is the Python module API of
+ * llava/model.  The Python shims in slime_b200/ keep that API and forward
+ * every stage to the entry points below through ctypes.  Each entry point names the reference
+ * function it replaces (paths relative to the reference repo; "HF:" = transformers).
+ *
+ * Conventions
+ *   - every tensor pointer is a DEVICE pointer owned by the caller (PyTorch); bf16 unless stated;
+ *     row-major, 16-byte aligned.  The library never frees or retains activation pointers; weight
+ *     pointers registered with slime_ctx_set_weight are borrowed until slime_ctx_destroy.
+ *   - `ws`/`ws_bytes` is caller-provided scratch; size it with the matching *_workspace_bytes().
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); only
+ *     slime_splice_plan synchronises (it must hand sequence lengths to the host).
+ *   - return value: 0 on success, negative SLIME_E* on failure; slime_last_error() gives the text.
+ *   - sm_100 only: slime_ctx_create fails with SLIME_EARCH on any other device.  No CPU fallback.
+ */
+#ifndef SLIME_B200_H_
+#define SLIME_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLIME_ABI_VERSION 1
+
+#define SLIME_OK 0
+#define SLIME_EINVAL (-1)
+#define SLIME_ECUDA (-2)
+#define SLIME_EARCH (-3)
+#define SLIME_EWORKSPACE (-4)
+#define SLIME_ESTATE (-5)
+
+#define SLIME_FLAG_LEFT_PAD 1u         /* config.tokenizer_padding_side == "left" */
+#define SLIME_FLAG_USE_GLOBAL_ONLY 2u  /* config.use_global_only */
+#define SLIME_FLAG_USE_LOCAL_ONLY 4u   /* config.use_local_only */
+
+typedef struct slime_ctx slime_ctx;
+
+/* Model description = the config attributes the reference reads on the hot path. */
+typedef struct slime_model_desc {
+  /* CLIP ViT (HF:models/clip/modeling_clip.py; mm_vision_tower) */
+  int32_t vit_hidden;       /* 1024 */
+  int32_t vit_layers_used;  /* layers executed = num_hidden_layers + 1 + mm_vision_select_layer (23) */
+  int32_t vit_heads;        /* 16 */
+  int32_t vit_mlp;          /* 4096 */
+  int32_t vit_image;        /* 336 */
+  int32_t vit_patch;        /* 14 */
+  float vit_ln_eps;         /* 1e-5 */
+  /* Resampler / projector (multimodal_resampler/sampler.py, multimodal_projector/builder.py) */
+  int32_t rs_local_queries;   /* mm_resampler_dim = 144 */
+  int32_t rs_global_queries;  /* GatedBlock.target_sequence_length = 576 */
+  float rs_ln_eps;            /* 1e-6 */
+  int32_t mm_learnable_gated; /* -1: gated mix, 0/1: that expert only */
+  /* Llama decoder (HF:models/llama/modeling_llama.py) */
+  int32_t hidden;
+  int32_t layers;
+  int32_t heads;
+  int32_t kv_heads;
+  int32_t head_dim;
+  int32_t mlp;
+  int32_t vocab;
+  float rope_theta;
+  float rms_eps;
+  int32_t max_pos; /* RoPE table length (>= longest spliced sequence) */
+  /* router / splice */
+  float top_p;           /* mm_resampler_topp */
+  float temp;            /* mm_resampler_temp */
+  int64_t image_token;   /* IMAGE_TOKEN_INDEX = -200 (llava/constants.py:9) */
+  int64_t sep_token;     /* config.seperator */
+  int32_t max_len;       /* tokenizer_model_max_length, 0 = no truncation */
+  uint32_t flags;        /* SLIME_FLAG_* */
+} slime_model_desc;
+
+int slime_version(void);
+const char* slime_last_error(void);
+
+int slime_ctx_create(slime_ctx** out, int device, const slime_model_desc* desc);
+void slime_ctx_destroy(slime_ctx* ctx);
+
+/* Register one weight tensor by canonical name (see slime_b200/weights.py for the mapping from the
+ * reference state-dict keys).  rows/cols are validated against the model description. */
+int slime_ctx_set_weight(slime_ctx* ctx, const char* name, const void* dev_ptr, int64_t rows, int64_t cols);
+/* Validates that every weight is present and pre-computes the input-independent tensors of the two
+ * Resamplers (projected queries, projected key position table) into the registered "*.derived_*"
+ * buffers.  Must be called once after the weights are registered (and again if they change). */
+size_t slime_finalize_workspace_bytes(const slime_ctx* ctx);
+int slime_ctx_finalize_weights(slime_ctx* ctx, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- stage 1: CLIPVisionTower.forward + feature_select  (multimodal_encoder/clip_encoder.py:36-58)
+ * pixels [Nc,3,S,S] -> feats [Nc, (S/P)^2, vit_hidden] = hidden_states[select_layer] without CLS. */
+size_t slime_vision_tower_workspace_bytes(const slime_ctx* ctx, int n_crops);
+int slime_vision_tower_fwd(slime_ctx* ctx, const void* pixels, int n_crops, void* feats, void* ws,
+                           size_t ws_bytes, void* stream);
+
+/* ---- stage 2: Resampler.forward  (multimodal_resampler/sampler.py:140-170)
+ * which = 0: sampler.post_qformer (local compression, 576 -> 144 tokens per crop)
+ * which = 1: mm_projector.attn    (global 576-query resampler)
+ * x [n, 576, vit_hidden] -> out [n, nq, vit_hidden]. */
+size_t slime_resampler_workspace_bytes(const slime_ctx* ctx, int which, int n);
+int slime_resampler_fwd(slime_ctx* ctx, int which, const void* x, int n, void* out, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* ---- stage 3a: GatedBlock.projection (multimodal_projector/builder.py:53-57,180-181)
+ * x [rows, vit_hidden] -> out[row_map ? row_map[r] : r, :hidden]; row_map folds the spatial merge
+ * (llava_arch.py:240-244) into the store. */
+size_t slime_projector_workspace_bytes(const slime_ctx* ctx, int rows);
+int slime_projector_fwd(slime_ctx* ctx, const void* x, int rows, const int32_t* row_map, void* out,
+                        void* ws, size_t ws_bytes, void* stream);
+/* ---- stage 3b: GatedBlock.forward on the global crop (multimodal_projector/builder.py:179-209)
+ * x [n*576, vit_hidden] -> out [n*576, hidden]. */
+size_t slime_gated_projector_workspace_bytes(const slime_ctx* ctx, int n);
+int slime_gated_projector_fwd(slime_ctx* ctx, const void* x, int n, void* out, void* ws, size_t ws_bytes,
+                              void* stream);
+
+/* ---- stage 4: TextGuidedSampler.forward (multimodal_resampler/builder.py:248-281) with the cosine
+ * selector (:189-201) and get_pure_text_embedding (llava_arch.py:162-210) folded in.
+ * local [B, n_per, hidden] (sample b uses its first n_valid[b] rows; n_valid may be NULL),
+ * ids [B,T] int64, mask [B,T] uint8 (may be NULL = all ones)
+ * -> sel_idx [B, n_per] int32 (ascending kept indices), sel_count [B] int32,
+ *    probs_out [B, n_per] fp32 (optional, the softmax the selection was made from). */
+size_t slime_router_workspace_bytes(const slime_ctx* ctx, int batch, int n_per, int prompt_len);
+int slime_router_fwd(slime_ctx* ctx, const void* local, int n_per, const int32_t* n_valid,
+                     const int64_t* ids, const uint8_t* mask, int batch, int prompt_len, float* probs_out,
+                     int32_t* sel_idx, int32_t* sel_count, void* ws, size_t ws_bytes, void* stream);
+/* Selection only, from given probabilities (bit-exact index parity test entry). */
+int slime_router_select(slime_ctx* ctx, const float* probs, int batch, int n_per, const int32_t* n_valid,
+                        int32_t* sel_idx, int32_t* sel_count, void* stream);
+
+/* ---- stage 5: the splice (llava_arch.py:249-255,361-459).
+ * plan: computes per-sample lengths and cu_seqlens, copies cu_seqlens[B+1] to host_cu (SYNCHRONISES).
+ *   plan_buf: device int32 scratch of slime_splice_plan_ints(B,T) ints, reused by gather/pad.
+ * gather: writes the packed rows out_embeds [cu[B], hidden] and pos_ids [cu[B]] (int32). */
+size_t slime_splice_plan_ints(int batch, int prompt_len);
+int slime_splice_plan(slime_ctx* ctx, const int64_t* ids, const uint8_t* mask, int batch, int prompt_len,
+                      int n_global, int has_sep, const int32_t* sel_count, int32_t* plan_buf,
+                      int32_t* host_cu, void* stream);
+int slime_splice_gather(slime_ctx* ctx, const int64_t* ids, int batch, int prompt_len,
+                        const int32_t* plan_buf, const void* global_feats, int n_global,
+                        int64_t global_sample_rows, const void* local_feats, int64_t local_sample_rows,
+                        const int32_t* sel_idx, int sel_stride, int has_sep, void* out_embeds,
+                        int32_t* pos_ids, int total_rows, void* stream);
+/* Padded views exactly as prepare_inputs_labels_for_multimodal returns them (any output may be NULL). */
+int slime_splice_pad(slime_ctx* ctx, const int32_t* plan_buf, const void* packed_embeds,
+                     const int64_t* labels_in, int batch, int prompt_len, int lmax, void* out_embeds,
+                     uint8_t* out_mask, int64_t* out_pos, int64_t* out_labels, void* stream);
+
+/* ---- stage 6: LlamaForCausalLM.forward(inputs_embeds=...) prefill (HF llama/modeling_llama.py:355-507)
+ * embeds [total, hidden] packed rows, cu_seqlens [B+1] int32 (device), pos_ids [total] int32
+ * -> logits_last [B, vocab] fp32 (last real token of every sequence; may be NULL)
+ *    logits_all  [total, vocab] bf16 (may be NULL)
+ *    hidden_out  [total, hidden] final-norm'ed hidden states (may be NULL) */
+size_t slime_decoder_workspace_bytes(const slime_ctx* ctx, int total_rows, int batch);
+int slime_decoder_prefill_fwd(slime_ctx* ctx, const void* embeds, const int32_t* cu_seqlens,
+                              const int32_t* pos_ids, int batch, int total_rows, int max_seqlen,
+                              float* logits_last, void* logits_all, void* hidden_out, void* ws,
+                              size_t ws_bytes, void* stream);
+
+/* ---- single-op entry points (unit parity tests of the kernels through the same ABI) ---- */
+int slime_op_gemm(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
+                  const void* residual, int res_ld, int res_period, const int32_t* row_map, int epilogue,
+                  void* out, float* out_f32, int out_ld, void* stream);
+int slime_op_attention(const void* q, const void* k, const void* v, void* o, int q_ld, int k_ld, int v_ld,
+                       int o_ld, const int32_t* cu_q, const int32_t* cu_k, int seqlen_q, int seqlen_k,
+                       int64_t q_batch_rows, int64_t k_batch_rows, int64_t o_batch_rows, int batch,
+                       int heads, int kv_heads, int head_dim, float scale, int causal, void* stream);
+int slime_op_layernorm(const void* x, const void* w, const void* b, void* y, int rows, int dim, float eps,
+                       void* stream);
+int slime_op_rmsnorm(const void* x, const void* w, void* y, int rows, int dim, float eps, void* stream);
+int slime_op_rope(slime_ctx* ctx, void* qkv, int ld, int rows, const int32_t* pos_ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLIME_B200_H_ */

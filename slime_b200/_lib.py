@@ -1,0 +1,135 @@
+"""ctypes binding of libslime_b200.so (include/slime_b200.h).
+
+The library is the product; there is no Python/PyTorch fallback.  Importing this module on a box
+where the library is missing raises immediately, and every wrapper raises RuntimeError with the
+library's own message when an entry point returns a negative code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libslime_b200.so"
+
+SLIME_FLAG_LEFT_PAD = 1
+SLIME_FLAG_USE_GLOBAL_ONLY = 2
+SLIME_FLAG_USE_LOCAL_ONLY = 4
+
+EPI_NONE, EPI_QUICK_GELU, EPI_GELU_ERF, EPI_SWIGLU = 0, 1, 2, 3
+
+
+class ModelDesc(C.Structure):
+    """Mirror of `slime_model_desc` (include/slime_b200.h)."""
+
+    _fields_ = [
+        ("vit_hidden", C.c_int32),
+        ("vit_layers_used", C.c_int32),
+        ("vit_heads", C.c_int32),
+        ("vit_mlp", C.c_int32),
+        ("vit_image", C.c_int32),
+        ("vit_patch", C.c_int32),
+        ("vit_ln_eps", C.c_float),
+        ("rs_local_queries", C.c_int32),
+        ("rs_global_queries", C.c_int32),
+        ("rs_ln_eps", C.c_float),
+        ("mm_learnable_gated", C.c_int32),
+        ("hidden", C.c_int32),
+        ("layers", C.c_int32),
+        ("heads", C.c_int32),
+        ("kv_heads", C.c_int32),
+        ("head_dim", C.c_int32),
+        ("mlp", C.c_int32),
+        ("vocab", C.c_int32),
+        ("rope_theta", C.c_float),
+        ("rms_eps", C.c_float),
+        ("max_pos", C.c_int32),
+        ("top_p", C.c_float),
+        ("temp", C.c_float),
+        ("image_token", C.c_int64),
+        ("sep_token", C.c_int64),
+        ("max_len", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); every symbol declared in include/slime_b200.h
+SIGNATURES = {
+    "slime_version": (_i, []),
+    "slime_last_error": (C.c_char_p, []),
+    "slime_ctx_create": (_i, [C.POINTER(_vp), _i, C.POINTER(ModelDesc)]),
+    "slime_ctx_destroy": (None, [_vp]),
+    "slime_ctx_set_weight": (_i, [_vp, C.c_char_p, _vp, _i64, _i64]),
+    "slime_finalize_workspace_bytes": (_sz, [_vp]),
+    "slime_ctx_finalize_weights": (_i, [_vp, _vp, _sz, _vp]),
+    "slime_vision_tower_workspace_bytes": (_sz, [_vp, _i]),
+    "slime_vision_tower_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "slime_resampler_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "slime_resampler_fwd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "slime_projector_workspace_bytes": (_sz, [_vp, _i]),
+    "slime_projector_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "slime_gated_projector_workspace_bytes": (_sz, [_vp, _i]),
+    "slime_gated_projector_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "slime_router_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "slime_router_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "slime_router_select": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "slime_splice_plan_ints": (_sz, [_i, _i]),
+    "slime_splice_plan": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "slime_splice_gather": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "slime_splice_pad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "slime_decoder_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "slime_decoder_prefill_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "slime_op_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    "slime_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i64, _i64, _i64, _i, _i, _i,
+                                _i, _f, _i, _vp]),
+    "slime_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "slime_op_rmsnorm": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
+    "slime_op_rope": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the library and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m slime_b200.build` "
+            "(slime_b200 has no PyTorch/CPU fallback path)")
+    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.slime_version() != 1:
+        raise RuntimeError(f"libslime_b200 ABI version {lib.slime_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().slime_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RuntimeError(f"slime_b200 {what} failed (code {rc}): {last_error()}")
+
+
+def ptr(t) -> C.c_void_p:
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> C.c_void_p:
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

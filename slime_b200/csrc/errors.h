@@ -1,0 +1,32 @@
+// Error codes + thread-local error message shared by every translation unit of libslime_b200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "slime_b200.h"  // SLIME_OK / SLIME_E* codes (include/slime_b200.h)
+
+void slime_set_error(const char* fmt, ...);
+const char* slime_get_error();
+
+#define SLIME_CHECK_CUDA(expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      slime_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,                 \
+                      cudaGetErrorString(_e));                                              \
+      return SLIME_ECUDA;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+#define SLIME_REQUIRE(cond, ...)       \
+  do {                                 \
+    if (!(cond)) {                     \
+      slime_set_error(__VA_ARGS__);    \
+      return SLIME_EINVAL;             \
+    }                                  \
+  } while (0)
+
+#define SLIME_PROPAGATE(expr)          \
+  do {                                 \
+    int _rc = (expr);                  \
+    if (_rc != SLIME_OK) return _rc;   \
+  } while (0)

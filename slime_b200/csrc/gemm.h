@@ -1,0 +1,26 @@
+// Host-side interface of the tcgen05 bf16 GEMM (gemm_sm100.cu).
+#pragma once
+#include "common.cuh"
+
+enum GemmEpilogue : int {
+  GEMM_EPI_NONE = 0,        // out = acc (+bias) (+residual)
+  GEMM_EPI_QUICK_GELU = 1,  // out = qgelu(acc + bias)          x*sigmoid(1.702x)  (CLIP MLP)
+  GEMM_EPI_GELU_ERF = 2,    // out = gelu(acc + bias)           exact erf GELU     (mm_projector)
+  GEMM_EPI_SWIGLU = 3,      // out[:, j] = silu(acc[:, 2j]) * acc[:, 2j+1]          (Llama MLP)
+};
+
+struct GemmParams {
+  int M, N, K;           // C[M,N] = A[M,K] * W[N,K]^T
+  const bf16* bias;      // [N] or nullptr
+  const bf16* residual;  // [*, res_ld] or nullptr; added after the activation
+  int res_ld;
+  int res_period;      // >0: residual row = row % res_period (row-periodic table), else row
+  const int* row_map;  // optional: output row = row_map[row]; negative = drop the row
+  bf16* out;           // bf16 output (may alias residual) or nullptr
+  float* out_f32;      // optional fp32 output (used for logits) or nullptr
+  int out_ld;          // leading dimension of the output (elements)
+};
+
+// Returns 0 on success; negative SLIME_E* otherwise (message via slime_set_error).
+int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
+                      int num_sms, cudaStream_t stream);

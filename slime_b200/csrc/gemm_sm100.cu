@@ -1,0 +1,426 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+//   * both operands K-major (activations row-major, nn.Linear weights [out,in] row-major), moved
+//     HBM -> shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle),
+//   * tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 in / fp32 accumulate) issued by ONE thread,
+//   * accumulators live in TMEM, double-buffered (2 x BLOCK_N columns) so the epilogue of tile i
+//     overlaps the main loop of tile i+1,
+//   * epilogue warps read TMEM with tcgen05.ld and apply bias / activation / residual / SwiGLU /
+//     row scatter before writing bf16 (or fp32) straight to HBM with 16-byte vector stores.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (warp w owns TMEM lane quadrant w % 4).
+//
+// This one kernel carries every dense contraction of the SliME prefill path: CLIP patch-embed /
+// QKV / out-proj / MLP (HF clip/modeling_clip.py:209,310-312,334,348-350), the Resampler K/V and
+// out projections (reference llava/model/multimodal_resampler/sampler.py:128), the mm_projector
+// MLP (reference llava/model/multimodal_projector/builder.py:53-57), and the Llama QKV / o-proj /
+// gate-up / down / lm_head projections (HF llama/modeling_llama.py:183,262-288,487).
+#include <mutex>
+#include <unordered_map>
+
+#include "errors.h"
+#include "gemm.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int GROUP_M = 8;  // m-blocks per rasterisation group (L2 reuse of the W tiles)
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : 6;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES;
+};
+
+struct TileCoord {
+  int m_blk, n_blk;
+};
+
+SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n) {
+  const int per_group = GROUP_M * num_n;
+  const int group = t / per_group;
+  const int first_m = group * GROUP_M;
+  const int gsize = min(GROUP_M, num_m - first_m);
+  const int in = t - group * per_group;
+  TileCoord c;
+  c.m_blk = first_m + in % gsize;
+  c.n_blk = in / gsize;
+  return c;
+}
+
+SLIME_DEVINL float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+SLIME_DEVINL float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+SLIME_DEVINL float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp_idx == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(t, num_m, num_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K,
+                      tc.m_blk * BLOCK_M);
+          tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K,
+                      tc.n_blk * BLOCK_N);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t desc_a = make_umma_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
+          const uint64_t desc_b = make_umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
+            umma_bf16_ss(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ============================ epilogue ================================
+    const int quad = warp_idx & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = tile_coord(t, num_m, num_n);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+
+      const int row = tc.m_blk * BLOCK_M + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      int out_row = row;
+      if (row_ok && p.row_map != nullptr) out_row = p.row_map[row];
+      const bool store_ok = row_ok && out_row >= 0;
+      int res_row = row;
+      if (p.res_period > 0) res_row = row % p.res_period;
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = tc.n_blk * BLOCK_N + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N +
+                               c * 32,
+                           r);
+        tmem_ld_wait();
+        if (!store_ok) continue;
+
+        if constexpr (EPI == GEMM_EPI_SWIGLU) {
+          // columns are (gate_j, up_j) interleaved -> 16 outputs per 32 accumulator columns
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int col = col0 + g * 16;
+            if (col >= p.N) break;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float gate = __uint_as_float(r[g * 16 + 2 * j]);
+              const float up = __uint_as_float(r[g * 16 + 2 * j + 1]);
+              o[j] = act_silu(gate) * up;
+            }
+            uint4 pk;
+            pk.x = pack_bf16x2(o[0], o[1]);
+            pk.y = pack_bf16x2(o[2], o[3]);
+            pk.z = pack_bf16x2(o[4], o[5]);
+            pk.w = pack_bf16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(out_row) * p.out_ld + (col >> 1)) =
+                pk;
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= p.N) break;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+            if (p.bias != nullptr) {
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+              const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y),
+                           b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
+              v[4] += b2.x; v[5] += b2.y; v[6] += b3.x; v[7] += b3.y;
+            }
+            if constexpr (EPI == GEMM_EPI_QUICK_GELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = act_quick_gelu(v[j]);
+            } else if constexpr (EPI == GEMM_EPI_GELU_ERF) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = act_gelu_erf(v[j]);
+            }
+            if (p.residual != nullptr) {
+              const uint4 q = *reinterpret_cast<const uint4*>(
+                  p.residual + static_cast<size_t>(res_row) * p.res_ld + col);
+              const float2 q0 = unpack_bf16x2(q.x), q1 = unpack_bf16x2(q.y),
+                           q2 = unpack_bf16x2(q.z), q3 = unpack_bf16x2(q.w);
+              v[0] += q0.x; v[1] += q0.y; v[2] += q1.x; v[3] += q1.y;
+              v[4] += q2.x; v[5] += q2.y; v[6] += q3.x; v[7] += q3.y;
+            }
+            if (p.out_f32 != nullptr) {
+              float4* dst =
+                  reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(out_row) * p.out_ld + col);
+              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              uint4 pk;
+              pk.x = pack_bf16x2(v[0], v[1]);
+              pk.y = pack_bf16x2(v[2], v[3]);
+              pk.z = pack_bf16x2(v[4], v[5]);
+              pk.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(out_row) * p.out_ld + col) = pk;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point fetched at run time, so the library
+// itself has no link-time dependency on libcuda and still loads on a GPU-less build box)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+    }
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int rows, cols, ld, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= (static_cast<size_t>(k.rows) * 0x9E3779B97F4A7C15ull) + (h << 6) + (h >> 2);
+    h ^= (static_cast<size_t>(k.cols) * 0xC2B2AE3D27D4EB4Full) + (h << 6) + (h >> 2);
+    h ^= (static_cast<size_t>(k.ld) * 0x165667B19E3779F9ull) + (h << 6) + (h >> 2);
+    h ^= static_cast<size_t>(k.box_rows) + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+int get_tmap(const bf16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return SLIME_OK;
+    }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    slime_set_error("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
+    return SLIME_ECUDA;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(bf16)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    slime_set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d",
+                    static_cast<int>(r), ptr, rows, cols, ld, box_rows);
+    return SLIME_ECUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+    g_tmap_cache[key] = m;
+  }
+  *out = m;
+  return SLIME_OK;
+}
+
+template <int BLOCK_N, int EPI>
+int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+               cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SLIME_CHECK_CUDA(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = num_m * num_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  SLIME_CHECK_CUDA(cudaGetLastError());
+  return SLIME_OK;
+}
+
+template <int BLOCK_N>
+int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi,
+               int num_sms, cudaStream_t stream) {
+  switch (epi) {
+    case GEMM_EPI_NONE:
+      return launch_cfg<BLOCK_N, GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_QUICK_GELU:
+      return launch_cfg<BLOCK_N, GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_GELU_ERF:
+      return launch_cfg<BLOCK_N, GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_SWIGLU:
+      return launch_cfg<BLOCK_N, GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
+    default:
+      slime_set_error("unknown GEMM epilogue %d", epi);
+      return SLIME_EINVAL;
+  }
+}
+
+}  // namespace
+
+int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
+                      int num_sms, cudaStream_t stream) {
+  SLIME_REQUIRE(A != nullptr && W != nullptr, "gemm: null operand");
+  SLIME_REQUIRE(p.out != nullptr || p.out_f32 != nullptr, "gemm: no output pointer");
+  SLIME_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  SLIME_REQUIRE(p.K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
+                "gemm: K/lda/ldw must be multiples of 8 (TMA 16-byte strides): K=%d lda=%d ldw=%d",
+                p.K, lda, ldw);
+  SLIME_REQUIRE(p.N % (epi == GEMM_EPI_SWIGLU ? 16 : 8) == 0, "gemm: N=%d not a multiple of %d", p.N,
+                epi == GEMM_EPI_SWIGLU ? 16 : 8);
+  SLIME_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                "gemm: operands must be 16-byte aligned");
+  const int out_align = p.out_f32 != nullptr ? 4 : 8;
+  SLIME_REQUIRE(p.out_ld % out_align == 0, "gemm: out_ld=%d must be a multiple of %d", p.out_ld,
+                out_align);
+  if (p.residual != nullptr)
+    SLIME_REQUIRE(p.res_ld % 8 == 0 && epi != GEMM_EPI_SWIGLU, "gemm: bad residual configuration");
+  if (epi == GEMM_EPI_SWIGLU)
+    SLIME_REQUIRE(p.bias == nullptr && p.out != nullptr, "gemm: SwiGLU epilogue takes no bias");
+
+  // BLOCK_N = 256 halves the A re-reads; fall back to 128 when the 256-wide grid cannot fill the GPU.
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles256 = num_m * ((p.N + 255) / 256);
+  const bool use256 = p.N >= 256 && tiles256 >= num_sms;
+  const int block_n = use256 ? 256 : 128;
+
+  CUtensorMap ta, tb;
+  SLIME_PROPAGATE(get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
+  SLIME_PROPAGATE(get_tmap(W, p.N, p.K, ldw, block_n, &tb));
+  if (use256) return launch_epi<256>(ta, tb, p, epi, num_sms, stream);
+  return launch_epi<128>(ta, tb, p, epi, num_sms, stream);
+}

@@ -1,0 +1,299 @@
+// Text-guided router (reference llava/model/multimodal_resampler/builder.py:177-201 cosine selector,
+// :248-281 top-p selection) and the text-side reduction it needs.
+//
+// The reference materialises cos(x_i, e_t) for every (local token, text token) pair - an N x T x H
+// broadcast - and then sums over t.  Algebraically
+//     score_i = sum_t m_t * <x_i, e_t> / (max(|x_i|,eps) * max(|e_t|,eps))
+//             = <x_i, tvec> / max(|x_i|, eps),      tvec = sum_t m_t * e_t / max(|e_t|, eps)
+// so the router is one reduction over the prompt (text_inv_norm + text_dir) and one GEMV-like pass
+// over the local tokens (router_score), followed by a per-sample single-CTA softmax / stable
+// descending sort / prefix-sum / compaction (router_select) that reproduces the reference's
+// selection rule exactly:  count = #(cumsum(sorted p) <= top_p);  keep the first count+1 sorted
+// entries (all of them if count == N);  return their indices in ascending order.
+#include "errors.h"
+#include "router.h"
+
+namespace {
+
+constexpr float COS_EPS = 1e-8f;  // torch.nn.functional.cosine_similarity default eps
+
+// inv_norm[b,t] = keep(b,t) / max(|E[id]|, eps);  keep = attention_mask != 0 and id is a real token
+__global__ void text_inv_norm_kernel(const long long* __restrict__ ids, const unsigned char* __restrict__ mask,
+                                     const bf16* __restrict__ embed, float* __restrict__ inv_norm, int B,
+                                     int T, int H, long long image_token, int vocab) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * T) return;
+  const long long id = ids[row];
+  const bool keep = (mask == nullptr || mask[row] != 0) && id != image_token && id >= 0 && id < vocab;
+  float r = 0.f;
+  if (keep) {
+    const bf16* e = embed + id * H;
+    float sq = 0.f;
+    for (int c = lane; c < (H >> 3); c += 32) {
+      const uint4 u = *reinterpret_cast<const uint4*>(e + c * 8);
+      float2 t;
+      t = unpack_bf16x2(u.x); sq += t.x * t.x + t.y * t.y;
+      t = unpack_bf16x2(u.y); sq += t.x * t.x + t.y * t.y;
+      t = unpack_bf16x2(u.z); sq += t.x * t.x + t.y * t.y;
+      t = unpack_bf16x2(u.w); sq += t.x * t.x + t.y * t.y;
+    }
+    sq = warp_sum(sq);
+    r = 1.0f / fmaxf(sqrtf(sq), COS_EPS);
+  }
+  if (lane == 0) inv_norm[row] = r;
+}
+
+// tvec[b, col] = sum_t inv_norm[b,t] * E[ids[b,t], col]     (thread per column pair, loop over t)
+__global__ void text_dir_kernel(const long long* __restrict__ ids, const float* __restrict__ inv_norm,
+                                const bf16* __restrict__ embed, float* __restrict__ tvec, int T, int H) {
+  const int b = blockIdx.y;
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (col >= H) return;
+  float a0 = 0.f, a1 = 0.f;
+  const long long* idr = ids + static_cast<long long>(b) * T;
+  const float* nr = inv_norm + static_cast<long long>(b) * T;
+  for (int t = 0; t < T; ++t) {
+    const float w = nr[t];
+    if (w != 0.f) {
+      const float2 e = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(embed + idr[t] * H + col));
+      a0 += w * e.x;
+      a1 += w * e.y;
+    }
+  }
+  tvec[static_cast<long long>(b) * H + col] = a0;
+  tvec[static_cast<long long>(b) * H + col + 1] = a1;
+}
+
+// score[i] = <x_i, tvec[b]> / max(|x_i|, eps)   (warp per local token; rows_per_sample tokens each)
+__global__ void router_score_kernel(const bf16* __restrict__ x, const float* __restrict__ tvec,
+                                    float* __restrict__ score, int rows, int rows_per_sample, int H) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / rows_per_sample;
+  const bf16* xr = x + static_cast<long long>(row) * H;
+  const float* tv = tvec + static_cast<long long>(b) * H;
+  float dot = 0.f, sq = 0.f;
+  for (int c = lane; c < (H >> 3); c += 32) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
+    const float4 t0 = *reinterpret_cast<const float4*>(tv + c * 8);
+    const float4 t1 = *reinterpret_cast<const float4*>(tv + c * 8 + 4);
+    float2 v;
+    v = unpack_bf16x2(u.x); dot += v.x * t0.x + v.y * t0.y; sq += v.x * v.x + v.y * v.y;
+    v = unpack_bf16x2(u.y); dot += v.x * t0.z + v.y * t0.w; sq += v.x * v.x + v.y * v.y;
+    v = unpack_bf16x2(u.z); dot += v.x * t1.x + v.y * t1.y; sq += v.x * v.x + v.y * v.y;
+    v = unpack_bf16x2(u.w); dot += v.x * t1.z + v.y * t1.w; sq += v.x * v.x + v.y * v.y;
+  }
+  dot = warp_sum(dot);
+  sq = warp_sum(sq);
+  if (lane == 0) score[row] = dot / fmaxf(sqrtf(sq), COS_EPS);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-sample selection: softmax (optional) -> stable descending sort -> cumsum -> top-p -> compaction
+// ------------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_MAX = 4096;  // max local tokens per sample (17 crops -> 16*144 = 2304)
+
+SLIME_DEVINL bool before(float pa, int ia, float pb, int ib) {
+  // descending by probability, ascending index among equal probabilities (stable order)
+  return pa > pb || (pa == pb && ia < ib);
+}
+
+template <typename T>
+SLIME_DEVINL T block_reduce(T v, T* red, bool is_max) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? (other > v ? other : v) : v + other;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    T w = lane < (SEL_THREADS / 32) ? red[lane] : (is_max ? red[0] : T(0));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T other = __shfl_xor_sync(0xffffffffu, w, o);
+      w = is_max ? (other > w ? other : w) : w + other;
+    }
+    if (lane == 0) red[0] = w;
+  }
+  __syncthreads();
+  const T out = red[0];
+  __syncthreads();
+  return out;
+}
+
+// in: score or prob [B, n_stride]; sample b uses its first n_valid[b] entries (all n_stride when
+// n_valid == nullptr).  from_probs: the input already holds probabilities, skip the softmax.
+__global__ void __launch_bounds__(SEL_THREADS) router_select_kernel(
+    const float* __restrict__ in, int n_stride, const int* __restrict__ n_valid, float temp, float top_p,
+    int from_probs, float* __restrict__ probs_out, int* __restrict__ sel_idx, int* __restrict__ sel_count) {
+  __shared__ float key[SEL_MAX];
+  __shared__ int idx[SEL_MAX];
+  __shared__ double scan[SEL_MAX / 4];  // per-thread partial sums (SEL_THREADS entries)
+  __shared__ float redf[32];
+  __shared__ int redi[32];
+  __shared__ int s_count;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n_per = n_valid != nullptr ? min(n_valid[b], n_stride) : n_stride;
+  const float* src = in + static_cast<long long>(b) * n_stride;
+  int* out_idx = sel_idx + static_cast<long long>(b) * n_stride;
+
+  if (n_per <= 0) {
+    if (tid == 0) sel_count[b] = 0;
+    return;
+  }
+
+  // ---- probabilities ----
+  if (!from_probs) {
+    float mx = -INFINITY;
+    for (int i = tid; i < n_per; i += SEL_THREADS) mx = fmaxf(mx, src[i] / temp);
+    mx = block_reduce<float>(mx, redf, true);
+    float sum = 0.f;
+    for (int i = tid; i < n_per; i += SEL_THREADS) {
+      const float e = expf(src[i] / temp - mx);
+      key[i] = e;
+      sum += e;
+    }
+    sum = block_reduce<float>(sum, redf, false);
+    for (int i = tid; i < n_per; i += SEL_THREADS) key[i] = key[i] / sum;
+  } else {
+    for (int i = tid; i < n_per; i += SEL_THREADS) key[i] = src[i];
+  }
+  __syncthreads();
+  if (probs_out != nullptr) {
+    for (int i = tid; i < n_per; i += SEL_THREADS) probs_out[static_cast<long long>(b) * n_stride + i] = key[i];
+  }
+  int npow = 1;
+  while (npow < n_per) npow <<= 1;
+  for (int i = tid; i < npow; i += SEL_THREADS) {
+    idx[i] = i;
+    if (i >= n_per) key[i] = -1.0f;  // padding sorts last (probabilities are >= 0)
+  }
+  __syncthreads();
+
+  // ---- bitonic sort, order: descending probability, ascending index on ties ----
+  for (int k = 2; k <= npow; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npow; i += SEL_THREADS) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float pa = key[i], pb = key[l];
+          const int ia = idx[i], ib = idx[l];
+          const bool up = (i & k) == 0;  // this subsequence should be in "before" order
+          const bool swap = up ? before(pb, ib, pa, ia) : before(pa, ia, pb, ib);
+          if (swap) {
+            key[i] = pb; key[l] = pa;
+            idx[i] = ib; idx[l] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- inclusive prefix sum in double (torch CPU cumsum accumulates float in double), then
+  //      count entries whose float(cumsum) <= top_p ----
+  const int per = (n_per + SEL_THREADS - 1) / SEL_THREADS;  // <= 4
+  const int lo = tid * per;
+  double local = 0.0;
+  for (int i = 0; i < per; ++i) {
+    const int p = lo + i;
+    if (p < n_per) local += static_cast<double>(key[p]);
+  }
+  scan[tid] = local;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over SEL_THREADS partials
+  for (int off = 1; off < SEL_THREADS; off <<= 1) {
+    double add = 0.0;
+    if (tid >= off) add = scan[tid - off];
+    __syncthreads();
+    scan[tid] += add;
+    __syncthreads();
+  }
+  double run = tid > 0 ? scan[tid - 1] : 0.0;
+  int cnt = 0;
+  for (int i = 0; i < per; ++i) {
+    const int p = lo + i;
+    if (p < n_per) {
+      run += static_cast<double>(key[p]);
+      if (static_cast<float>(run) <= top_p) cnt += 1;
+    }
+  }
+  cnt = block_reduce<int>(cnt, redi, false);
+  if (tid == 0) s_count = cnt < n_per ? cnt + 1 : n_per;
+  __syncthreads();
+  const int keep = s_count;
+
+  // ---- mark the kept original indices, compact them in ascending order ----
+  __syncthreads();
+  for (int i = tid; i < n_per; i += SEL_THREADS) key[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < keep; i += SEL_THREADS) key[idx[i]] = 1.f;
+  __syncthreads();
+  int mine = 0;
+  for (int i = 0; i < per; ++i) {
+    const int p = lo + i;
+    if (p < n_per && key[p] != 0.f) mine += 1;
+  }
+  int* iscan = reinterpret_cast<int*>(scan);
+  iscan[tid] = mine;
+  __syncthreads();
+  for (int off = 1; off < SEL_THREADS; off <<= 1) {
+    int add = 0;
+    if (tid >= off) add = iscan[tid - off];
+    __syncthreads();
+    iscan[tid] += add;
+    __syncthreads();
+  }
+  int pos = tid > 0 ? iscan[tid - 1] : 0;
+  for (int i = 0; i < per; ++i) {
+    const int p = lo + i;
+    if (p < n_per && key[p] != 0.f) out_idx[pos++] = p;
+  }
+  if (tid == 0) sel_count[b] = keep;
+}
+
+}  // namespace
+
+int slime_launch_text_dir(const long long* ids, const unsigned char* mask, const bf16* embed,
+                          float* inv_norm_ws, float* tvec, int B, int T, int H, long long image_token,
+                          int vocab, cudaStream_t stream) {
+  SLIME_REQUIRE(H % 8 == 0, "router: hidden size %d must be a multiple of 8", H);
+  if (B <= 0 || T <= 0) return SLIME_OK;
+  text_inv_norm_kernel<<<(B * T + 3) / 4, 128, 0, stream>>>(ids, mask, embed, inv_norm_ws, B, T, H,
+                                                            image_token, vocab);
+  SLIME_CHECK_CUDA(cudaGetLastError());
+  dim3 grid((H / 2 + 127) / 128, B);
+  text_dir_kernel<<<grid, 128, 0, stream>>>(ids, inv_norm_ws, embed, tvec, T, H);
+  SLIME_CHECK_CUDA(cudaGetLastError());
+  return SLIME_OK;
+}
+
+int slime_launch_router_score(const bf16* x, const float* tvec, float* score, int rows,
+                              int rows_per_sample, int H, cudaStream_t stream) {
+  SLIME_REQUIRE(H % 8 == 0, "router: hidden size %d must be a multiple of 8", H);
+  if (rows <= 0) return SLIME_OK;
+  router_score_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, tvec, score, rows, rows_per_sample, H);
+  SLIME_CHECK_CUDA(cudaGetLastError());
+  return SLIME_OK;
+}
+
+int slime_launch_router_select(const float* in, int B, int n_per, const int* n_valid, float temp,
+                               float top_p, int from_probs, float* probs_out, int* sel_idx,
+                               int* sel_count, cudaStream_t stream) {
+  SLIME_REQUIRE(n_per <= SEL_MAX, "router: %d local tokens per sample exceeds the supported %d", n_per,
+                SEL_MAX);
+  SLIME_REQUIRE(temp > 0.f, "router: temperature must be positive");
+  if (B <= 0) return SLIME_OK;
+  router_select_kernel<<<B, SEL_THREADS, 0, stream>>>(in, n_per, n_valid, temp, top_p, from_probs, probs_out,
+                                                      sel_idx, sel_count);
+  SLIME_CHECK_CUDA(cudaGetLastError());
+  return SLIME_OK;
+}

@@ -1,0 +1,253 @@
+"""Per-kernel parity tests on a B200, called through the C-ABI single-op entry points.
+
+The reference for each floating-point kernel is plain PyTorch fp32 math on the same bf16 inputs
+(the kernels accumulate in fp32 and round once to bf16, so they must agree with the fp32 result
+to within one bf16 rounding: rel-L2 <= 4e-3 and every element within 2 bf16 ulps of the largest
+magnitude).  Integer results (router selection) are compared exactly in test_stages_gpu.py.
+"""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_REL_L2 = 4e-3
+
+
+def _lib():
+    from slime_b200 import _lib as L
+
+    return L
+
+
+def rel_l2(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def assert_close_bf16(out, ref, what, tol=BF16_REL_L2):
+    ref = ref.float()
+    out = out.float()
+    assert out.shape == ref.shape, f"{what}: shape {tuple(out.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(out).all(), f"{what}: non-finite output"
+    err = rel_l2(out, ref)
+    max_abs = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol, f"{what}: rel-L2 {err:.3e} > {tol:.1e} (max abs err {max_abs:.3e}, ref max {scale:.3e})"
+    assert max_abs <= 2 ** -6 * scale + 1e-6, f"{what}: max abs err {max_abs:.3e} vs scale {scale:.3e}"
+
+
+def gemm(a, w, bias=None, residual=None, res_period=0, row_map=None, epi=0, out_rows=None, f32=False):
+    L = _lib()
+    lib = L.load()
+    M, K = a.shape
+    N = w.shape[0]
+    out_cols = N // 2 if epi == L.EPI_SWIGLU else N
+    rows = out_rows if out_rows is not None else M
+    if f32:
+        out = torch.zeros(rows, out_cols, device="cuda", dtype=torch.float32)
+    else:
+        out = torch.zeros(rows, out_cols, device="cuda", dtype=torch.bfloat16)
+    rc = lib.slime_op_gemm(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), M, N, K, L.ptr(bias), L.ptr(residual),
+                           residual.stride(0) if residual is not None else 0, res_period, L.ptr(row_map), epi,
+                           None if f32 else L.ptr(out), L.ptr(out) if f32 else None, out.stride(0), L.stream_ptr())
+    L.check(rc, "op_gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+def rnd(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 128, 64),       # one tile, one k-block
+    (128, 256, 128),
+    (256, 512, 256),
+    (100, 136, 72),       # ragged M, N % 128 != 0, K % 64 != 0 (TMA zero fill + store masks)
+    (577 * 5, 1024, 1024),   # CLIP out-proj at 5 crops
+    (577 * 5, 3072, 1024),   # CLIP QKV
+    (576 * 5, 1024, 640),    # patch embed (K padded 588 -> 640)
+    (1408 * 8, 6144, 4096),  # Llama-3 QKV, BLOCK_N = 256 path, many tiles per CTA
+    (1408, 4096, 14336),     # Llama-3 down proj (long K)
+    (8, 128256, 4096),       # lm_head on 8 last tokens
+])
+def test_gemm_plain(M, N, K):
+    torch.manual_seed(M + N + K)
+    a, w = rnd(M, K), rnd(N, K, scale=0.05)
+    bias = rnd(N)
+    out = gemm(a, w, bias=bias)
+    ref = a.float() @ w.float().t() + bias.float()
+    assert_close_bf16(out, ref, f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_fp32_out_and_no_bias():
+    torch.manual_seed(1)
+    a, w = rnd(300, 512), rnd(1000, 512, scale=0.05)
+    out = gemm(a, w, f32=True)
+    ref = a.float() @ w.float().t()
+    assert rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("epi", ["quick_gelu", "gelu_erf"])
+def test_gemm_activations(epi):
+    L = _lib()
+    torch.manual_seed(2)
+    a, w, bias = rnd(700, 1024), rnd(4096, 1024, scale=0.05), rnd(4096)
+    pre = a.float() @ w.float().t() + bias.float()
+    if epi == "quick_gelu":
+        ref = pre * torch.sigmoid(1.702 * pre)
+        out = gemm(a, w, bias=bias, epi=L.EPI_QUICK_GELU)
+    else:
+        ref = torch.nn.functional.gelu(pre)
+        out = gemm(a, w, bias=bias, epi=L.EPI_GELU_ERF)
+    assert_close_bf16(out, ref, f"gemm+{epi}")
+
+
+def test_gemm_residual_inplace_and_periodic():
+    torch.manual_seed(3)
+    a, w, bias = rnd(577 * 3, 1024), rnd(1024, 1024, scale=0.05), rnd(1024)
+    h = rnd(577 * 3, 1024)
+    ref = a.float() @ w.float().t() + bias.float() + h.float()
+    L = _lib()
+    lib = L.load()
+    out = h.clone()
+    rc = lib.slime_op_gemm(L.ptr(a), 1024, L.ptr(w), 1024, a.shape[0], 1024, 1024, L.ptr(bias), L.ptr(out), 1024, 0,
+                           None, 0, L.ptr(out), None, 1024, L.stream_ptr())
+    L.check(rc, "gemm residual in place")
+    torch.cuda.synchronize()
+    assert_close_bf16(out, ref, "gemm+residual (in place)")
+    # periodic residual table (Resampler key position term): row r uses table[r % 576]
+    a2, w2 = rnd(576 * 4, 1024), rnd(2048, 1024, scale=0.05)
+    table = rnd(576, 2048)
+    out2 = gemm(a2, w2, bias=None, residual=table, res_period=576)
+    ref2 = a2.float() @ w2.float().t() + table.float().repeat(4, 1)
+    assert_close_bf16(out2, ref2, "gemm+periodic residual")
+
+
+def test_gemm_row_map_scatter():
+    torch.manual_seed(4)
+    a, w = rnd(576, 1024), rnd(4096, 1024, scale=0.05)
+    perm = torch.randperm(576, device="cuda").to(torch.int32)
+    perm[5] = -1  # dropped row
+    out = gemm(a, w, row_map=perm)
+    ref = a.float() @ w.float().t()
+    expect = torch.zeros_like(ref)
+    keep = perm >= 0
+    expect[perm[keep].long()] = ref[keep]
+    assert_close_bf16(out, expect, "gemm+row_map")
+
+
+def test_gemm_swiglu():
+    L = _lib()
+    torch.manual_seed(5)
+    I, H, M = 1024, 512, 900
+    a = rnd(M, H)
+    gate, up = rnd(I, H, scale=0.05), rnd(I, H, scale=0.05)
+    inter = torch.stack([gate, up], dim=1).reshape(2 * I, H).contiguous()  # rows (g0,u0,g1,u1,...)
+    out = gemm(a, inter, epi=L.EPI_SWIGLU)
+    ref = torch.nn.functional.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+    assert_close_bf16(out, ref, "gemm+swiglu")
+
+
+def attention(q, k, v, o_rows, o_ld, **kw):
+    L = _lib()
+    lib = L.load()
+    o = torch.zeros(o_rows, o_ld, device="cuda", dtype=torch.bfloat16)
+    rc = lib.slime_op_attention(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), kw["q_ld"], kw["k_ld"], kw["v_ld"], o_ld,
+                                L.ptr(kw.get("cu_q")), L.ptr(kw.get("cu_k")), kw["seqlen_q"], kw["seqlen_k"],
+                                kw.get("q_batch_rows", 0), kw.get("k_batch_rows", 0), kw.get("o_batch_rows", 0),
+                                kw["batch"], kw["heads"], kw["kv_heads"], kw["head_dim"], kw["scale"],
+                                kw.get("causal", 0), L.stream_ptr())
+    L.check(rc, "op_attention")
+    torch.cuda.synchronize()
+    return o
+
+
+def ref_attention(q, k, v, scale, causal):
+    # q [B,h,Sq,d], k/v [B,h,Sk,d] fp32
+    s = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        Sq, Sk = q.shape[-2], k.shape[-2]
+        mask = torch.ones(Sq, Sk, device=q.device, dtype=torch.bool).tril(Sk - Sq)
+        s = s.masked_fill(~mask, float("-inf"))
+    return torch.softmax(s, dim=-1) @ v
+
+
+def test_attention_clip_shape():
+    """16 heads x 64, S = 577 (4*128+65: ragged tail tile), non-causal, packed qkv rows."""
+    torch.manual_seed(6)
+    B, h, d, S = 3, 16, 64, 577
+    D = h * d
+    qkv = rnd(B * S, 3 * D)
+    o = attention(qkv, qkv[:, D:], qkv[:, 2 * D:], B * S, D, q_ld=3 * D, k_ld=3 * D, v_ld=3 * D, seqlen_q=S,
+                  seqlen_k=S, q_batch_rows=S, k_batch_rows=S, o_batch_rows=S, batch=B, heads=h, kv_heads=h,
+                  head_dim=d, scale=d ** -0.5)
+    x = qkv.float().view(B, S, 3, h, d).permute(2, 0, 3, 1, 4)
+    ref = ref_attention(x[0], x[1], x[2], d ** -0.5, False).permute(0, 2, 1, 3).reshape(B * S, D)
+    assert_close_bf16(o, ref, "attention clip")
+
+
+@pytest.mark.parametrize("nq", [144, 576])
+def test_attention_resampler_shape(nq):
+    """8 heads x 128, shared learned queries (q_batch_rows = 0) against 576 keys per crop."""
+    torch.manual_seed(7)
+    n, h, d, NK = 4, 8, 128, 576
+    D = h * d
+    q = rnd(nq, D)
+    kv = rnd(n * NK, 2 * D)
+    o = attention(q, kv, kv[:, D:], n * nq, D, q_ld=D, k_ld=2 * D, v_ld=2 * D, seqlen_q=nq, seqlen_k=NK,
+                  q_batch_rows=0, k_batch_rows=NK, o_batch_rows=nq, batch=n, heads=h, kv_heads=h, head_dim=d,
+                  scale=d ** -0.5)
+    qf = q.float().view(1, nq, h, d).permute(0, 2, 1, 3).expand(n, h, nq, d)
+    kf = kv[:, :D].float().view(n, NK, h, d).permute(0, 2, 1, 3)
+    vf = kv[:, D:].float().view(n, NK, h, d).permute(0, 2, 1, 3)
+    ref = ref_attention(qf, kf, vf, d ** -0.5, False).permute(0, 2, 1, 3).reshape(n * nq, D)
+    assert_close_bf16(o, ref, f"attention resampler nq={nq}")
+
+
+def test_attention_decoder_causal_varlen_gqa():
+    """Packed variable-length causal attention with GQA 32/8 heads x 128 (Llama-3 layout)."""
+    torch.manual_seed(8)
+    h, kvh, d = 8, 2, 128
+    lens = [1, 63, 64, 65, 200, 333]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device="cuda", dtype=torch.int32)
+    total = sum(lens)
+    W = (h + 2 * kvh) * d
+    qkv = rnd(total, W)
+    o = attention(qkv, qkv[:, h * d:], qkv[:, (h + kvh) * d:], total, h * d, q_ld=W, k_ld=W, v_ld=W, cu_q=cu,
+                  cu_k=cu, seqlen_q=max(lens), seqlen_k=max(lens), batch=len(lens), heads=h, kv_heads=kvh,
+                  head_dim=d, scale=d ** -0.5, causal=1)
+    off = 0
+    for L_ in lens:
+        blk = qkv[off:off + L_].float()
+        q = blk[:, :h * d].view(L_, h, d).permute(1, 0, 2)[None]
+        k = blk[:, h * d:(h + kvh) * d].view(L_, kvh, d).permute(1, 0, 2)[None].repeat_interleave(h // kvh, dim=1)
+        v = blk[:, (h + kvh) * d:].view(L_, kvh, d).permute(1, 0, 2)[None].repeat_interleave(h // kvh, dim=1)
+        ref = ref_attention(q, k, v, d ** -0.5, True)[0].permute(1, 0, 2).reshape(L_, h * d)
+        assert_close_bf16(o[off:off + L_], ref, f"attention causal len={L_}")
+        off += L_
+
+
+@pytest.mark.parametrize("D", [128, 1024, 4096, 5120])
+def test_layernorm_rmsnorm(D):
+    L = _lib()
+    lib = L.load()
+    torch.manual_seed(9)
+    rows = 517
+    x, w, b = rnd(rows, D), rnd(D), rnd(D)
+    y = torch.empty_like(x)
+    L.check(lib.slime_op_layernorm(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), rows, D, 1e-5, L.stream_ptr()), "ln")
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-5)
+    torch.cuda.synchronize()
+    assert_close_bf16(y, ref, f"layernorm D={D}")
+    L.check(lib.slime_op_rmsnorm(L.ptr(x), L.ptr(w), L.ptr(y), rows, D, 1e-5, L.stream_ptr()), "rms")
+    torch.cuda.synchronize()
+    xf = x.float()
+    normed = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(torch.bfloat16)
+    ref = (w * normed).float()  # HF: weight * hidden_states.to(input_dtype), product in bf16
+    assert (y.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-6
+    assert rel_l2(y, ref) < 3e-3
