@@ -1,0 +1,384 @@
+"""SlimeEngine: the host side of the B200-native SliME prefill path.
+
+Owns a `slime_ctx` (include/slime_b200.h), the packed bf16 weights (borrowed by the library), one
+growable workspace tensor, and a small cache of spatial-merge row maps.  Every method is a thin
+ctypes call into libslime_b200.so - PyTorch is only the allocator / stream provider here.
+
+Stage methods mirror the reference functions they replace (file:line in each docstring); `prefill`
+chains them for a whole batch:  pixels + prompt ids -> last-token logits, with the samples PACKED
+(no padding rows ever reach a GEMM) and a single host synchronisation (the spliced lengths).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .config import IGNORE_INDEX, IMAGE_TOKEN_INDEX, SlimeConfig
+from .mm_utils import get_anyres_image_grid_shape
+from .weights import pack_weights
+
+
+def _locked(fn):
+    """Serialises every entry into the (non re-entrant) slime_ctx and its shared workspace."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self._lock, torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+
+    return wrapper
+
+
+@dataclass
+class PrefillResult:
+    logits_last: Optional[torch.Tensor]      # [B, V] fp32: logits of the last real token of each sample
+    logits_all: Optional[torch.Tensor]       # [total, V] bf16 packed rows (only if requested)
+    cu_seqlens: torch.Tensor                 # [B+1] int32 (device)
+    lengths: List[int]                       # spliced length of every sample (host)
+    sel_idx: Optional[torch.Tensor]          # [B, n_per] int32 kept local-token indices (ascending)
+    sel_count: Optional[torch.Tensor]        # [B] int32
+    probs: Optional[torch.Tensor]            # [B, n_per] fp32 router probabilities (if requested)
+    embeds: Optional[torch.Tensor]           # [total, H] bf16 packed spliced embeddings (if requested)
+    stages: Optional[dict] = None            # per-stage tensors (if requested)
+
+    @property
+    def total_tokens(self) -> int:
+        return int(sum(self.lengths))
+
+
+class SlimeEngine:
+    def __init__(self, cfg: SlimeConfig, device: int | str | torch.device = 0, max_pos: Optional[int] = None):
+        cfg.validate()
+        self.cfg = cfg
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if self.device.type != "cuda":
+            raise RuntimeError("SlimeEngine needs a CUDA (B200) device: there is no CPU path")
+        self.lib = L.load()
+        self._lock = threading.RLock()  # a slime_ctx is not re-entrant (serve/model_worker.py runs generate on threads)
+        self._ws: Optional[torch.Tensor] = None
+        self._row_maps: Dict[tuple, torch.Tensor] = {}
+        self.weights: Dict[str, torch.Tensor] = {}
+        d = L.ModelDesc()
+        d.vit_hidden, d.vit_layers_used, d.vit_heads, d.vit_mlp = cfg.vit_hidden, cfg.vit_layers_used, cfg.vit_heads, cfg.vit_mlp
+        d.vit_image, d.vit_patch, d.vit_ln_eps = cfg.vit_image, cfg.vit_patch, cfg.vit_ln_eps
+        d.rs_local_queries, d.rs_global_queries, d.rs_ln_eps = cfg.mm_resampler_dim, 576, 1e-6
+        d.mm_learnable_gated = cfg.mm_learnable_gated
+        d.hidden, d.layers, d.heads, d.kv_heads = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.num_key_value_heads
+        d.head_dim, d.mlp, d.vocab = cfg.head_dim, cfg.intermediate_size, cfg.vocab_size
+        d.rope_theta, d.rms_eps = cfg.rope_theta, cfg.rms_norm_eps
+        d.max_pos = int(max_pos or cfg.max_position_embeddings)
+        d.top_p, d.temp = cfg.mm_resampler_topp, cfg.mm_resampler_temp
+        d.image_token, d.sep_token = IMAGE_TOKEN_INDEX, cfg.seperator
+        d.max_len = int(cfg.tokenizer_model_max_length or 0)
+        d.flags = ((L.SLIME_FLAG_LEFT_PAD if cfg.tokenizer_padding_side == "left" else 0)
+                   | (L.SLIME_FLAG_USE_GLOBAL_ONLY if cfg.use_global_only else 0)
+                   | (L.SLIME_FLAG_USE_LOCAL_ONLY if cfg.use_local_only else 0))
+        self._desc = d
+        self._ctx = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.slime_ctx_create(C.byref(self._ctx), self.device.index or 0, C.byref(d)), "ctx_create")
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.lib.slime_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """Accepts the reference model's state-dict keys."""
+        self.load_weights(lambda name: state_dict[name])
+
+    def load_weights(self, get: Callable[[str], torch.Tensor]) -> None:
+        with self._lock, torch.cuda.device(self.device):
+            self.weights = pack_weights(self.cfg, get, self.device)
+            for name, t in self.weights.items():
+                L.check(self.lib.slime_ctx_set_weight(self._ctx, name.encode(), L.ptr(t), t.shape[0], t.shape[1]),
+                        f"set_weight({name})")
+            ws = self._workspace(self.lib.slime_finalize_workspace_bytes(self._ctx))
+            L.check(self.lib.slime_ctx_finalize_weights(self._ctx, L.ptr(ws), ws.numel(), L.stream_ptr()), "finalize")
+            torch.cuda.current_stream().synchronize()
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _bf16(self, *shape) -> torch.Tensor:
+        return torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+
+    # ------------------------------------------------------------------ stages
+    @_locked
+    def vision_tower(self, pixels: torch.Tensor) -> torch.Tensor:
+        """CLIPVisionTower.forward (reference multimodal_encoder/clip_encoder.py:46-58): [N,3,S,S] -> [N,576,D]."""
+        px = pixels.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        n = px.shape[0]
+        feats = self._bf16(n, self.cfg.vit_patches, self.cfg.vit_hidden)
+        if n == 0:
+            return feats
+        ws = self._workspace(self.lib.slime_vision_tower_workspace_bytes(self._ctx, n))
+        L.check(self.lib.slime_vision_tower_fwd(self._ctx, L.ptr(px), n, L.ptr(feats), L.ptr(ws), ws.numel(),
+                                                L.stream_ptr()), "vision_tower_fwd")
+        return feats
+
+    @_locked
+    def resampler(self, which: int, x: torch.Tensor) -> torch.Tensor:
+        """Resampler.forward (reference multimodal_resampler/sampler.py:140-170); which 0 = local 144-query
+        compression (sampler.post_qformer), 1 = the projector's 576-query resampler.  [n,576,D] -> [n,nq,D]."""
+        x = x.to(torch.bfloat16).contiguous()
+        n = x.shape[0]
+        nq = self.cfg.mm_resampler_dim if which == 0 else 576
+        out = self._bf16(n, nq, self.cfg.vit_hidden)
+        if n == 0:
+            return out
+        ws = self._workspace(self.lib.slime_resampler_workspace_bytes(self._ctx, which, n))
+        L.check(self.lib.slime_resampler_fwd(self._ctx, which, L.ptr(x), n, L.ptr(out), L.ptr(ws), ws.numel(),
+                                             L.stream_ptr()), "resampler_fwd")
+        return out
+
+    @_locked
+    def projector(self, x: torch.Tensor, row_map: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None
+                  ) -> torch.Tensor:
+        """GatedBlock.projection (reference multimodal_projector/builder.py:53-57,180-181): [rows,D] -> [rows,H];
+        row_map scatters output rows (the spatial merge of llava_arch.py:240-244 folded into the store)."""
+        x2 = x.to(torch.bfloat16).reshape(-1, self.cfg.vit_hidden).contiguous()
+        rows = x2.shape[0]
+        if out is None:
+            out = self._bf16(rows, self.cfg.hidden_size)
+        if rows == 0:
+            return out
+        ws = self._workspace(self.lib.slime_projector_workspace_bytes(self._ctx, rows))
+        L.check(self.lib.slime_projector_fwd(self._ctx, L.ptr(x2), rows, L.ptr(row_map), L.ptr(out), L.ptr(ws),
+                                             ws.numel(), L.stream_ptr()), "projector_fwd")
+        return out
+
+    @_locked
+    def gated_projector(self, x: torch.Tensor) -> torch.Tensor:
+        """GatedBlock.forward on global crops (reference multimodal_projector/builder.py:179-209): [n,576,D] -> [n,576,H]."""
+        x = x.to(torch.bfloat16).reshape(-1, 576, self.cfg.vit_hidden).contiguous()
+        n = x.shape[0]
+        out = self._bf16(n, 576, self.cfg.hidden_size)
+        if n == 0:
+            return out
+        ws = self._workspace(self.lib.slime_gated_projector_workspace_bytes(self._ctx, n))
+        L.check(self.lib.slime_gated_projector_fwd(self._ctx, L.ptr(x), n, L.ptr(out), L.ptr(ws), ws.numel(),
+                                                   L.stream_ptr()), "gated_projector_fwd")
+        return out
+
+    @_locked
+    def router(self, local: torch.Tensor, ids: torch.Tensor, mask: Optional[torch.Tensor],
+               n_valid: Optional[torch.Tensor] = None, want_probs: bool = False):
+        """TextGuidedSampler.forward + cosine selector + get_pure_text_embedding (reference
+        multimodal_resampler/builder.py:189-201,248-281; llava_arch.py:162-210).
+        local [B, n_per, H] -> (sel_idx [B,n_per] int32, sel_count [B] int32, probs or None)."""
+        B, n_per = local.shape[0], local.shape[1]
+        T = ids.shape[1]
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        m8 = None if mask is None else (mask != 0).to(device=self.device, dtype=torch.uint8).contiguous()
+        sel_idx = torch.zeros(B, max(n_per, 1), dtype=torch.int32, device=self.device)
+        sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
+        probs = torch.zeros(B, max(n_per, 1), dtype=torch.float32, device=self.device) if want_probs else None
+        ws = self._workspace(self.lib.slime_router_workspace_bytes(self._ctx, B, n_per, T))
+        L.check(self.lib.slime_router_fwd(self._ctx, L.ptr(local.contiguous()), n_per, L.ptr(n_valid), L.ptr(ids),
+                                          L.ptr(m8), B, T, L.ptr(probs), L.ptr(sel_idx), L.ptr(sel_count), L.ptr(ws),
+                                          ws.numel(), L.stream_ptr()), "router_fwd")
+        return sel_idx, sel_count, probs
+
+    @_locked
+    def router_select(self, probs: torch.Tensor, n_valid: Optional[torch.Tensor] = None):
+        """The top-p selection rule alone, from given probabilities (bit-exact index parity)."""
+        probs = probs.to(device=self.device, dtype=torch.float32).contiguous()
+        B, n_per = probs.shape
+        sel_idx = torch.zeros(B, n_per, dtype=torch.int32, device=self.device)
+        sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
+        L.check(self.lib.slime_router_select(self._ctx, L.ptr(probs), B, n_per, L.ptr(n_valid), L.ptr(sel_idx),
+                                             L.ptr(sel_count), L.stream_ptr()), "router_select")
+        return sel_idx, sel_count
+
+    @_locked
+    def splice(self, ids, mask, glob, local, sel_idx, sel_count, n_global: int, has_sep: bool,
+               labels: Optional[torch.Tensor] = None, padded: bool = False):
+        """prepare_inputs_labels_for_multimodal's splice (reference llava_arch.py:249-255,361-459).
+        Returns packed embeds [total,H], pos_ids [total] int32, cu_seqlens [B+1] int32 (device), lengths (host)
+        and, when `padded`, the reference's padded (inputs_embeds, attention_mask, position_ids, labels)."""
+        B, T = ids.shape
+        H = self.cfg.hidden_size
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        m8 = None if mask is None else (mask != 0).to(device=self.device, dtype=torch.uint8).contiguous()
+        plan = torch.empty(int(self.lib.slime_splice_plan_ints(B, T)), dtype=torch.int32, device=self.device)
+        host_cu = (C.c_int32 * (B + 1))()
+        L.check(self.lib.slime_splice_plan(self._ctx, L.ptr(ids), L.ptr(m8), B, T, n_global, int(has_sep),
+                                           L.ptr(sel_count), L.ptr(plan), host_cu, L.stream_ptr()), "splice_plan")
+        cu_host = list(host_cu)
+        lengths = [cu_host[i + 1] - cu_host[i] for i in range(B)]
+        total = cu_host[B]
+        embeds = self._bf16(total, H)
+        pos_ids = torch.empty(total, dtype=torch.int32, device=self.device)
+        g_rows = glob.shape[1] if glob is not None and glob.dim() == 3 else 0
+        l_rows = local.shape[1] if local is not None and local.dim() == 3 else 0
+        sel_stride = sel_idx.shape[1] if sel_idx is not None else 0
+        L.check(self.lib.slime_splice_gather(self._ctx, L.ptr(ids), B, T, L.ptr(plan), L.ptr(glob), n_global, g_rows,
+                                             L.ptr(local), l_rows, L.ptr(sel_idx), sel_stride, int(has_sep),
+                                             L.ptr(embeds), L.ptr(pos_ids), total, L.stream_ptr()), "splice_gather")
+        cu_dev = plan[B * T + B * 8: B * T + B * 8 + B + 1]
+        out = dict(embeds=embeds, pos_ids=pos_ids, cu_seqlens=cu_dev, lengths=lengths, plan=plan)
+        if padded:
+            lmax = max(lengths) if lengths else 0
+            pe = torch.empty(B, lmax, H, dtype=torch.bfloat16, device=self.device)
+            pm = torch.empty(B, lmax, dtype=torch.uint8, device=self.device)
+            pp = torch.empty(B, lmax, dtype=torch.int64, device=self.device)
+            pl = torch.empty(B, lmax, dtype=torch.int64, device=self.device)
+            lab = None if labels is None else labels.to(device=self.device, dtype=torch.int64).contiguous()
+            L.check(self.lib.slime_splice_pad(self._ctx, L.ptr(plan), L.ptr(embeds), L.ptr(lab), B, T, lmax, L.ptr(pe),
+                                              L.ptr(pm), L.ptr(pp), L.ptr(pl), L.stream_ptr()), "splice_pad")
+            out.update(inputs_embeds=pe, attention_mask=pm.bool(), position_ids=pp, labels=pl)
+        return out
+
+    @_locked
+    def decoder_prefill(self, embeds: torch.Tensor, cu_seqlens: torch.Tensor, pos_ids: torch.Tensor,
+                        lengths: Sequence[int], want_last: bool = True, want_all: bool = False,
+                        want_hidden: bool = False):
+        """LlamaForCausalLM.forward(inputs_embeds=...) (HF llama/modeling_llama.py:355-507) on packed rows."""
+        total, B = embeds.shape[0], len(lengths)
+        V = self.cfg.vocab_size
+        last = torch.empty(B, V, dtype=torch.float32, device=self.device) if want_last else None
+        allv = self._bf16(total, V) if want_all else None
+        hid = self._bf16(total, self.cfg.hidden_size) if want_hidden else None
+        ws = self._workspace(self.lib.slime_decoder_workspace_bytes(self._ctx, total, B))
+        L.check(self.lib.slime_decoder_prefill_fwd(self._ctx, L.ptr(embeds), L.ptr(cu_seqlens), L.ptr(pos_ids), B, total,
+                                                   max(lengths) if lengths else 0, L.ptr(last), L.ptr(allv), L.ptr(hid),
+                                                   L.ptr(ws), ws.numel(), L.stream_ptr()), "decoder_prefill_fwd")
+        return last, allv, hid
+
+    # ------------------------------------------------------------------ spatial merge addressing
+    def merge_row_map(self, n_local: Sequence[int], grids: Optional[Sequence[Tuple[int, int]]], n_per: int
+                      ) -> torch.Tensor:
+        """dst row (inside the [B, n_per, H] local buffer) of every compressed local token, in crop-major
+        source order.  'spatial': raster order over the whole image (reference llava_arch.py:240-244);
+        'flat': crop after crop (llava_arch.py:233-234)."""
+        g = self.cfg.resampler_grid
+        spatial = self.cfg.mm_patch_merge_type == "spatial"
+        key = (tuple(n_local), tuple(grids) if (grids is not None and spatial) else None, n_per, spatial)
+        hit = self._row_maps.get(key)
+        if hit is not None:
+            return hit
+        rows: List[torch.Tensor] = []
+        q = g * g
+        for b, nl in enumerate(n_local):
+            if nl == 0:
+                continue
+            if spatial:
+                w, h = grids[b]
+                if w * h != nl:
+                    raise ValueError(f"sample {b}: grid {w}x{h} does not match its {nl} local crops")
+                c = torch.arange(nl).view(nl, 1, 1)
+                gy = torch.arange(g).view(1, g, 1)
+                gx = torch.arange(g).view(1, 1, g)
+                dst = (((c // w) * g + gy) * w + (c % w)) * g + gx
+                rows.append(dst.reshape(-1) + b * n_per)
+            else:
+                rows.append(torch.arange(nl * q) + b * n_per)
+        out = (torch.cat(rows) if rows else torch.zeros(0, dtype=torch.long)).to(dtype=torch.int32, device=self.device)
+        if len(self._row_maps) > 256:
+            self._row_maps.clear()
+        self._row_maps[key] = out
+        return out
+
+    # ------------------------------------------------------------------ whole path
+    @torch.no_grad()
+    def prefill(self, pixels, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                image_sizes: Optional[Sequence[Tuple[int, int]]] = None, grids: Optional[Sequence[Tuple[int, int]]] = None,
+                labels: Optional[torch.Tensor] = None, forced_selection: Optional[Sequence[torch.Tensor]] = None,
+                want_last: bool = True, want_all_logits: bool = False, want_probs: bool = False,
+                keep_stages: bool = False) -> PrefillResult:
+        """LlavaLlamaForCausalLM.forward(images=...) (reference llava_llama.py:57-104 -> llava_arch.py:274-459).
+
+        pixels: [B, n, 3, S, S] tensor or list of per-sample [n_b, 3, S, S] tensors (crop 0 = global view).
+        forced_selection: optional per-sample index tensors that replace the router's choice (teacher forcing
+        for logits parity)."""
+        cfg = self.cfg
+        with self._lock, torch.cuda.device(self.device):
+            if isinstance(pixels, (list, tuple)):
+                per = [p.unsqueeze(0) if p.dim() == 3 else p for p in pixels]
+                counts = [p.shape[0] for p in per]
+                px = torch.cat(per, 0)
+            else:
+                counts = [pixels.shape[1]] * pixels.shape[0]
+                px = pixels.reshape(-1, *pixels.shape[2:])
+            B = len(counts)
+            assert input_ids.shape[0] == B, "one image (stack of crops) per sample"
+            px = px.to(device=self.device, dtype=torch.bfloat16, non_blocking=True)
+            ids = input_ids.to(device=self.device, dtype=torch.int64, non_blocking=True)
+            mask = None if attention_mask is None else attention_mask.to(device=self.device, non_blocking=True)
+            stages = {} if keep_stages else None
+
+            feats = self.vision_tower(px)                                   # [Nc, 576, D]
+            starts = [0]
+            for c in counts:
+                starts.append(starts[-1] + c)
+            uniform = len(set(counts)) == 1
+            n_local = [c - 1 for c in counts]
+            if uniform:
+                fv = feats.view(B, counts[0], cfg.vit_patches, cfg.vit_hidden)
+                xg = fv[:, 0]
+                xl = fv[:, 1:].reshape(-1, cfg.vit_patches, cfg.vit_hidden)
+            else:
+                gi = torch.tensor(starts[:-1], device=self.device)
+                li = torch.tensor([i for b in range(B) for i in range(starts[b] + 1, starts[b + 1])], device=self.device,
+                                  dtype=torch.long)
+                xg, xl = feats.index_select(0, gi), feats.index_select(0, li)
+
+            glob = local = sel_idx = sel_count = probs = None
+            n_global, has_sep = 0, False
+            if not cfg.use_local_only:
+                glob = self.gated_projector(xg)                              # [B, 576, H]
+                n_global = 576
+                has_sep = not cfg.use_global_only
+            q = cfg.mm_resampler_dim
+            n_per = max(n_local) * q if n_local else 0
+            if not cfg.use_global_only:
+                local = torch.zeros(B, max(n_per, 1), cfg.hidden_size, dtype=torch.bfloat16, device=self.device) \
+                    if not uniform else self._bf16(B, max(n_per, 1), cfg.hidden_size)
+                if n_per > 0:
+                    if grids is None and cfg.mm_patch_merge_type == "spatial":
+                        if image_sizes is None:
+                            raise ValueError("spatial merge needs image_sizes or grids")
+                        grids = [get_anyres_image_grid_shape(s, None, cfg.vit_image) for s in image_sizes]
+                    lc = self.resampler(0, xl)                               # [Nl, 144, D]
+                    rmap = self.merge_row_map(n_local, grids, n_per)
+                    self.projector(lc, row_map=rmap, out=local.view(-1, cfg.hidden_size))
+                    n_valid = None if uniform else torch.tensor([n * q for n in n_local], dtype=torch.int32,
+                                                                device=self.device)
+                    sel_idx, sel_count, probs = self.router(local, ids, mask, n_valid, want_probs)
+                    if forced_selection is not None:
+                        sel_idx = torch.zeros_like(sel_idx)
+                        for b, s in enumerate(forced_selection):
+                            sel_idx[b, : s.numel()] = s.to(device=self.device, dtype=torch.int32)
+                        sel_count = torch.tensor([s.numel() for s in forced_selection], dtype=torch.int32,
+                                                 device=self.device)
+                    if stages is not None:
+                        stages.update(local_c=lc)
+                else:
+                    sel_idx = torch.zeros(B, 1, dtype=torch.int32, device=self.device)
+                    sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
+            sp = self.splice(ids, mask, glob, local, sel_idx, sel_count, n_global, has_sep, labels=labels,
+                             padded=keep_stages)
+            last, allv, _ = self.decoder_prefill(sp["embeds"], sp["cu_seqlens"], sp["pos_ids"], sp["lengths"],
+                                                 want_last=want_last, want_all=want_all_logits)
+            if stages is not None:
+                stages.update(vit=feats, glob=glob, local_m=local, splice=sp)
+            return PrefillResult(logits_last=last, logits_all=allv, cu_seqlens=sp["cu_seqlens"], lengths=sp["lengths"],
+                                 sel_idx=sel_idx, sel_count=sel_count, probs=probs,
+                                 embeds=sp["embeds"] if keep_stages else None, stages=stages)
