@@ -172,6 +172,12 @@ int slime_op_layernorm(const void* x, const void* w, const void* b, void* y, int
 int slime_op_rmsnorm(const void* x, const void* w, void* y, int rows, int dim, float eps, void* stream);
 int slime_op_rope(slime_ctx* ctx, void* qkv, int ld, int rows, const int32_t* pos_ids, void* stream);
 
+/* ---- accounting: kernels launched by the library since load; optional CUDA-event profiling of the
+ * library's own launches (class 0 = tcgen05 GEMM [work = FLOPs], 1 = attention, 2 = other) ---- */
+long long slime_launch_count(void);
+int slime_profile_enable(int on);
+int slime_profile_collect(double* ms3, double* work3, long long* launches3);
+
 #ifdef __cplusplus
 }
 #endif

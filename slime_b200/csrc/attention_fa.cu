@@ -288,8 +288,14 @@ int launch(const AttnParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((p.seqlen_q + BM - 1) / BM, p.num_heads, p.batch);
+  // FLOPs are only known exactly for fixed-length batches (4*Sq*Sk*hd per head, halved when causal)
+  double flops = 0.0;
+  if (p.cu_q == nullptr)
+    flops = 4.0 * p.seqlen_q * static_cast<double>(p.seqlen_k) * HD * p.num_heads * p.batch * (CAUSAL ? 0.5 : 1.0);
+  slime_prof_begin(1, flops, stream);
   kern<<<grid, NTHREADS, SMEM, stream>>>(p);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  slime_prof_end(stream);
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 

@@ -411,7 +411,7 @@ int slime_launch_layernorm(const bf16* x, int x_ld, const bf16* w, const bf16* b
     layernorm_kernel<128, 8><<<rows, NT, 0, stream>>>(x, x_ld, w, b, y, y_ld, rows, D, eps, in_group,
                                                       in_group_stride, in_offset);
   }
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -426,7 +426,7 @@ int slime_launch_rmsnorm(const bf16* x, int x_ld, const bf16* w, bf16* y, int y_
   } else {
     rmsnorm_kernel<128, 8><<<rows, NT, 0, stream>>>(x, x_ld, w, y, y_ld, rows, D, eps, src_rows);
   }
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -436,7 +436,7 @@ int slime_launch_im2col(const bf16* pixels, bf16* patches, int Nc, int image, in
   if (Nc <= 0) return SLIME_OK;
   const long long total = static_cast<long long>(Nc) * (image / patch) * (image / patch) * Kpad;
   im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(pixels, patches, Nc, image, patch, Kpad);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -451,7 +451,7 @@ int slime_launch_clip_embed_ln(const bf16* patch_out, const bf16* cls, const bf1
   } else {
     clip_embed_ln_kernel<8><<<(rows + 3) / 4, NT, 0, stream>>>(patch_out, cls, pos, w, b, h, Nc, tokens, D, eps);
   }
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -461,7 +461,7 @@ int slime_launch_copy_rows(const bf16* src, int src_ld, bf16* dst, int dst_ld, i
   if (rows <= 0) return SLIME_OK;
   copy_rows_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0, stream>>>(
       src, src_ld, dst, dst_ld, rows, D, group, group_stride, offset, nullptr);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -471,7 +471,7 @@ int slime_launch_scatter_rows(const bf16* src, int src_ld, bf16* dst, int dst_ld
   if (rows <= 0) return SLIME_OK;
   copy_rows_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0, stream>>>(
       src, src_ld, dst, dst_ld, rows, D, 0, 0, 0, dst_rows);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -481,7 +481,7 @@ int slime_launch_add_rows(const bf16* a, const bf16* b, bf16* y, int rows, int D
   if (rows <= 0) return SLIME_OK;
   add_rows_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0, stream>>>(a, b, y, rows,
                                                                                            D, period);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -490,7 +490,7 @@ int slime_launch_rope_table(float* table, int max_pos, int head_dim, float theta
   const int total = max_pos * half;
   rope_table_kernel<<<(total + 255) / 256, 256, 0, stream>>>(reinterpret_cast<float2*>(table), max_pos, half,
                                                              theta);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -503,7 +503,7 @@ int slime_launch_rope(bf16* qkv, int ld, int rows, int n_q_heads, int n_k_heads,
   rope_kernel<<<grid_for(total, 256), 256, 0, stream>>>(qkv, ld, rows, heads, head_dim, pos_ids,
                                                         reinterpret_cast<const float2*>(cos_sin_table),
                                                         max_pos);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -512,6 +512,6 @@ int slime_launch_gate_mix(const bf16* x, const bf16* w_gate, const bf16* e0, con
   SLIME_REQUIRE(Dm % 2 == 0 && H % 8 == 0, "gate_mix: bad dims Dm=%d H=%d", Dm, H);
   if (rows <= 0) return SLIME_OK;
   gate_mix_kernel<<<rows, NT, 0, stream>>>(x, w_gate, e0, e1, out, rows, Dm, H);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

@@ -1,6 +1,9 @@
-// Thread-local error message storage for the C-ABI.
+// Thread-local error message storage, launch accounting and the optional event profiler.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "errors.h"
 
@@ -13,3 +16,78 @@ void slime_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* slime_get_error() { return g_err; }
+
+namespace {
+std::atomic<long long> g_launches{0};
+std::atomic<bool> g_prof_on{false};
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cls;
+  double work;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_recs;
+ProfRec g_open;
+bool g_has_open = false;
+}  // namespace
+
+void slime_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool slime_prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+
+void slime_prof_begin(int cls, double work, cudaStream_t stream) {
+  if (!slime_prof_enabled()) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.cls = cls;
+  r.work = work;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, stream);
+  g_open = r;
+  g_has_open = true;
+}
+void slime_prof_end(cudaStream_t stream) {
+  if (!slime_prof_enabled()) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_has_open) return;
+  cudaEventRecord(g_open.b, stream);
+  g_recs.push_back(g_open);
+  g_has_open = false;
+}
+
+extern "C" {
+
+long long slime_launch_count(void) { return g_launches.load(); }
+
+int slime_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_recs.clear();
+  g_has_open = false;
+  g_prof_on.store(on != 0);
+  return SLIME_OK;
+}
+
+// Sums per class: ms[3], work[3], launches[3].  Synchronises on the recorded events.
+int slime_profile_collect(double* ms, double* work, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < 3; ++i) {
+    ms[i] = 0.0;
+    work[i] = 0.0;
+    launches[i] = 0;
+  }
+  for (auto& r : g_recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+    const int c = r.cls < 0 || r.cls > 2 ? 2 : r.cls;
+    ms[c] += t;
+    work[c] += r.work;
+    launches[c] += 1;
+  }
+  return SLIME_OK;
+}
+
+}  // extern "C"

@@ -7,6 +7,19 @@
 void slime_set_error(const char* fmt, ...);
 const char* slime_get_error();
 
+// Launch accounting / optional CUDA-event profiling of the library's own kernels (errors.cu).
+// class: 0 = tcgen05 GEMM, 1 = attention, 2 = everything else (HBM-bound kernels)
+void slime_note_launch();
+bool slime_prof_enabled();
+void slime_prof_begin(int cls, double work, cudaStream_t stream);  // work = FLOPs (cls 0/1) or bytes (cls 2)
+void slime_prof_end(cudaStream_t stream);
+
+#define SLIME_AFTER_LAUNCH()                 \
+  do {                                       \
+    slime_note_launch();                     \
+    SLIME_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
+
 #define SLIME_CHECK_CUDA(expr)                                                              \
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \

@@ -367,8 +367,10 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
+  slime_prof_begin(0, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
   kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  slime_prof_end(stream);
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 

@@ -269,10 +269,10 @@ int slime_launch_text_dir(const long long* ids, const unsigned char* mask, const
   if (B <= 0 || T <= 0) return SLIME_OK;
   text_inv_norm_kernel<<<(B * T + 3) / 4, 128, 0, stream>>>(ids, mask, embed, inv_norm_ws, B, T, H,
                                                             image_token, vocab);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   dim3 grid((H / 2 + 127) / 128, B);
   text_dir_kernel<<<grid, 128, 0, stream>>>(ids, inv_norm_ws, embed, tvec, T, H);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -281,7 +281,7 @@ int slime_launch_router_score(const bf16* x, const float* tvec, float* score, in
   SLIME_REQUIRE(H % 8 == 0, "router: hidden size %d must be a multiple of 8", H);
   if (rows <= 0) return SLIME_OK;
   router_score_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, tvec, score, rows, rows_per_sample, H);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -294,6 +294,6 @@ int slime_launch_router_select(const float* in, int B, int n_per, const int* n_v
   if (B <= 0) return SLIME_OK;
   router_select_kernel<<<B, SEL_THREADS, 0, stream>>>(in, n_per, n_valid, temp, top_p, from_probs, probs_out,
                                                       sel_idx, sel_count);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

@@ -187,7 +187,7 @@ int slime_launch_splice_plan(const long long* ids, const unsigned char* mask, in
   SLIME_REQUIRE(B > 0 && T > 0, "splice: empty batch");
   splice_plan_kernel<<<1, 1024, 0, stream>>>(ids, mask, B, T, image_token, n_global, has_sep, sel_count,
                                              max_len, valid_pos, plan, cu_seqlens, err_flag);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -202,7 +202,7 @@ int slime_launch_splice_gather(const long long* ids, int T, const int* valid_pos
   splice_gather_kernel<<<(total_rows + 3) / 4, 128, 0, stream>>>(
       ids, T, valid_pos, plan, cu_seqlens, B, embed, H, sep_token, has_sep, glob, n_global,
       glob_sample_rows, local, local_sample_rows, sel_idx, sel_stride, out, pos_ids, total_rows);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -216,7 +216,7 @@ int slime_launch_splice_pad_meta(const int* plan, const int* valid_pos, const lo
   if (grid > 148 * 16) grid = 148 * 16;
   splice_pad_meta_kernel<<<grid, 256, 0, stream>>>(plan, valid_pos, labels_in, T, B, Lmax, left_pad,
                                                    ignore_index, out_mask, out_pos, out_labels);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
@@ -226,13 +226,13 @@ int slime_launch_splice_pad_embeds(const bf16* packed, const int* cu_seqlens, in
   const long long rows = static_cast<long long>(B) * Lmax;
   splice_pad_embeds_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, stream>>>(packed, cu_seqlens, B,
                                                                                       Lmax, H, left_pad, out);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
 int slime_launch_last_rows(const int* cu_seqlens, int B, int* rows, cudaStream_t stream) {
   if (B <= 0) return SLIME_OK;
   last_rows_kernel<<<(B + 127) / 128, 128, 0, stream>>>(cu_seqlens, B, rows);
-  SLIME_CHECK_CUDA(cudaGetLastError());
+  SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

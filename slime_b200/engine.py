@@ -137,7 +137,7 @@ class SlimeEngine:
     def resampler(self, which: int, x: torch.Tensor) -> torch.Tensor:
         """Resampler.forward (reference multimodal_resampler/sampler.py:140-170); which 0 = local 144-query
         compression (sampler.post_qformer), 1 = the projector's 576-query resampler.  [n,576,D] -> [n,nq,D]."""
-        x = x.to(torch.bfloat16).contiguous()
+        x = x.to(device=self.device, dtype=torch.bfloat16).contiguous()
         n = x.shape[0]
         nq = self.cfg.mm_resampler_dim if which == 0 else 576
         out = self._bf16(n, nq, self.cfg.vit_hidden)
@@ -153,7 +153,7 @@ class SlimeEngine:
                   ) -> torch.Tensor:
         """GatedBlock.projection (reference multimodal_projector/builder.py:53-57,180-181): [rows,D] -> [rows,H];
         row_map scatters output rows (the spatial merge of llava_arch.py:240-244 folded into the store)."""
-        x2 = x.to(torch.bfloat16).reshape(-1, self.cfg.vit_hidden).contiguous()
+        x2 = x.to(device=self.device, dtype=torch.bfloat16).reshape(-1, self.cfg.vit_hidden).contiguous()
         rows = x2.shape[0]
         if out is None:
             out = self._bf16(rows, self.cfg.hidden_size)
@@ -167,7 +167,7 @@ class SlimeEngine:
     @_locked
     def gated_projector(self, x: torch.Tensor) -> torch.Tensor:
         """GatedBlock.forward on global crops (reference multimodal_projector/builder.py:179-209): [n,576,D] -> [n,576,H]."""
-        x = x.to(torch.bfloat16).reshape(-1, 576, self.cfg.vit_hidden).contiguous()
+        x = x.to(device=self.device, dtype=torch.bfloat16).reshape(-1, 576, self.cfg.vit_hidden).contiguous()
         n = x.shape[0]
         out = self._bf16(n, 576, self.cfg.hidden_size)
         if n == 0:
@@ -183,6 +183,7 @@ class SlimeEngine:
         """TextGuidedSampler.forward + cosine selector + get_pure_text_embedding (reference
         multimodal_resampler/builder.py:189-201,248-281; llava_arch.py:162-210).
         local [B, n_per, H] -> (sel_idx [B,n_per] int32, sel_count [B] int32, probs or None)."""
+        local = local.to(device=self.device, dtype=torch.bfloat16).contiguous()
         B, n_per = local.shape[0], local.shape[1]
         T = ids.shape[1]
         ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
@@ -191,7 +192,7 @@ class SlimeEngine:
         sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
         probs = torch.zeros(B, max(n_per, 1), dtype=torch.float32, device=self.device) if want_probs else None
         ws = self._workspace(self.lib.slime_router_workspace_bytes(self._ctx, B, n_per, T))
-        L.check(self.lib.slime_router_fwd(self._ctx, L.ptr(local.contiguous()), n_per, L.ptr(n_valid), L.ptr(ids),
+        L.check(self.lib.slime_router_fwd(self._ctx, L.ptr(local), n_per, L.ptr(n_valid), L.ptr(ids),
                                           L.ptr(m8), B, T, L.ptr(probs), L.ptr(sel_idx), L.ptr(sel_count), L.ptr(ws),
                                           ws.numel(), L.stream_ptr()), "router_fwd")
         return sel_idx, sel_count, probs

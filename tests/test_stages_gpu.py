@@ -6,9 +6,9 @@ Tolerances (north_star: "within 1e-3 relative bf16 tolerance, bit-exact for the 
   * integer results - selected indices given the probabilities, lengths, cu_seqlens, attention_mask,
     position_ids, labels, and the spliced rows as a gather of the stage outputs - are compared EXACTLY;
   * floating-point stages are bf16 pipelines compared with the fp32 oracle: one bf16 rounding is
-    already 1.7e-3 rel-L2, so each stage must stay within STAGE_TOL = 2e-2 after its chain of
-    roundings, and the end-to-end logits (teacher-forced selection) within
-    E2E_TOL = 3e-2 - the unmodified reference's own bf16 run sits at 0.8e-2 on the same case
+    already 1.7e-3 rel-L2, so each stage must stay within STAGE_TOL = 1e-2 after its chain of
+    roundings (measured 3e-3..5e-3), and the end-to-end logits (teacher-forced selection, SURVEY.md 8a
+    row R) within E2E_TOL = 1.5e-2 (measured 5e-3..8e-3) - the unmodified reference's own bf16 run sits at 0.8e-2 on the same case
     (golden key ref_bf16_rel_err_last).  Measured values are printed (pytest -s) and recorded in DESIGN.md.
 """
 import os
@@ -20,8 +20,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-STAGE_TOL = 2e-2
-E2E_TOL = 3e-2
+STAGE_TOL = 1e-2
+E2E_TOL = 1.5e-2
 
 
 def rel(a, b):
