@@ -126,6 +126,12 @@ size_t slime_router_workspace_bytes(const slime_ctx* ctx, int batch, int n_per, 
 int slime_router_fwd(slime_ctx* ctx, const void* local, int n_per, const int32_t* n_valid,
                      const int64_t* ids, const uint8_t* mask, int batch, int prompt_len, float* probs_out,
                      int32_t* sel_idx, int32_t* sel_count, void* ws, size_t ws_bytes, void* stream);
+/* Same, with the prompt given as a dense [B, T, hidden] embedding tensor (the signature of the reference's
+ * TextGuidedSampler.forward(local_f, text_embedding, attn_mask), multimodal_resampler/builder.py:248). */
+int slime_router_fwd_embeds(slime_ctx* ctx, const void* local, int n_per, const int32_t* n_valid,
+                            const void* text_embeds, const uint8_t* mask, int batch, int prompt_len,
+                            float* probs_out, int32_t* sel_idx, int32_t* sel_count, void* ws, size_t ws_bytes,
+                            void* stream);
 /* Selection only, from given probabilities (bit-exact index parity test entry). */
 int slime_router_select(slime_ctx* ctx, const float* probs, int batch, int n_per, const int32_t* n_valid,
                         int32_t* sel_idx, int32_t* sel_count, void* stream);

@@ -75,6 +75,7 @@ SIGNATURES = {
     "slime_gated_projector_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "slime_router_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "slime_router_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "slime_router_fwd_embeds": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "slime_router_select": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "slime_splice_plan_ints": (_sz, [_i, _i]),
     "slime_splice_plan": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -104,14 +104,19 @@ class SlimeConfig:
 
     @classmethod
     def from_hf_config(cls, cfg, clip_cfg=None) -> "SlimeConfig":
-        g = lambda k, d=None: getattr(cfg, k, d)  # noqa: E731
+        def g(k, d=None):
+            v = getattr(cfg, k, d)
+            return d if v is None else v
+
+        heads = g("num_attention_heads", 32)
+        hidden = g("hidden_size", 4096)
         out = cls(
-            hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_hidden_layers,
-            num_attention_heads=cfg.num_attention_heads,
-            num_key_value_heads=g("num_key_value_heads", cfg.num_attention_heads),
-            head_dim=g("head_dim", None) or cfg.hidden_size // cfg.num_attention_heads,
-            intermediate_size=cfg.intermediate_size, vocab_size=cfg.vocab_size,
-            rope_theta=float(_rope_theta(cfg)), rms_norm_eps=cfg.rms_norm_eps,
+            hidden_size=hidden, num_hidden_layers=g("num_hidden_layers", 32),
+            num_attention_heads=heads,
+            num_key_value_heads=g("num_key_value_heads", heads),
+            head_dim=g("head_dim", None) or hidden // heads,
+            intermediate_size=g("intermediate_size", 11008), vocab_size=g("vocab_size", 32000),
+            rope_theta=float(_rope_theta(cfg)), rms_norm_eps=g("rms_norm_eps", 1e-5),
             max_position_embeddings=g("max_position_embeddings", 4096),
             mm_vision_select_layer=g("mm_vision_select_layer", -2),
             mm_vision_select_feature=g("mm_vision_select_feature", "patch"),

@@ -73,6 +73,7 @@ struct slime_ctx {
   float* rope_table = nullptr;  // [max_pos, head_dim/2] (cos, sin) fp32, owned
   int* err_flag = nullptr;      // device int, owned
   bool finalized = false;
+  bool has_vit = false, has_rs[2] = {false, false}, has_proj = false, has_llm = false;
   std::mutex mu;
   // resolved at finalize
   int vit_tokens = 0, vit_patches = 0, vit_kpad = 0;
@@ -247,9 +248,11 @@ int gated_body(slime_ctx* c, Arena& a, const bf16* x, int n, bf16* out, cudaStre
   return SLIME_OK;
 }
 
+// ids != nullptr: prompt given as token ids (rows gathered from the embedding table, placeholders skipped);
+// ids == nullptr: prompt given as a dense [B, T, H] embedding tensor `text` (the reference's module-level API).
 int router_body(slime_ctx* c, Arena& a, const bf16* local, int n_per, const int* n_valid, const long long* ids,
-                const unsigned char* mask, int B, int T, float* probs_out, int* sel_idx, int* sel_count,
-                cudaStream_t s) {
+                const bf16* text, const unsigned char* mask, int B, int T, float* probs_out, int* sel_idx,
+                int* sel_count, cudaStream_t s) {
   const int H = c->d.hidden;
   float* inv_norm = a.get<float>(static_cast<size_t>(B) * T);
   float* tvec = a.get<float>(static_cast<size_t>(B) * H);
@@ -260,8 +263,8 @@ int router_body(slime_ctx* c, Arena& a, const bf16* local, int n_per, const int*
     SLIME_CHECK_CUDA(cudaMemsetAsync(sel_count, 0, sizeof(int) * B, s));
     return SLIME_OK;
   }
-  SLIME_PROPAGATE(slime_launch_text_dir(ids, mask, c->llm_embed, inv_norm, tvec, B, T, H, c->d.image_token,
-                                        c->d.vocab, s));
+  SLIME_PROPAGATE(slime_launch_text_dir(ids, mask, ids != nullptr ? c->llm_embed : text, inv_norm, tvec, B, T, H,
+                                        c->d.image_token, c->d.vocab, s));
   SLIME_PROPAGATE(slime_launch_router_score(local, tvec, score, B * n_per, n_per, H, s));
   SLIME_PROPAGATE(slime_launch_router_select(score, B, n_per, n_valid, c->d.temp, c->d.top_p, 0, probs_out,
                                              sel_idx, sel_count, s));
@@ -327,12 +330,13 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
 int finalize_body(slime_ctx* c, Arena& a, cudaStream_t s) {
   const int D = c->d.vit_hidden;
   const int NK = c->vit_patches;
-  const int nq_max = c->rs[0].nq > c->rs[1].nq ? c->rs[0].nq : c->rs[1].nq;
+  const int nq_max = c->d.rs_local_queries > c->d.rs_global_queries ? c->d.rs_local_queries : c->d.rs_global_queries;
   bf16* t1 = a.get<bf16>(static_cast<size_t>(nq_max) * D);
   bf16* t2 = a.get<bf16>(static_cast<size_t>(nq_max) * D);
   ARENA_CHECK(a, "finalize_weights");
   if (a.dry) return SLIME_OK;
   for (int which = 0; which < 2; ++which) {
+    if (!c->has_rs[which]) continue;
     Resampler& R = c->rs[which];
     // Q = (ln_q(query) + pos_q) Wq^T + bq   -- input independent (sampler.py:159-161)
     SLIME_PROPAGATE(slime_launch_layernorm(R.query, D, R.ln_q_w, R.ln_q_b, t1, D, R.nq, D, c->d.rs_ln_eps, 0, 0, 0, s));
@@ -347,13 +351,22 @@ int finalize_body(slime_ctx* c, Arena& a, cudaStream_t s) {
   return SLIME_OK;
 }
 
-int check_ready(slime_ctx* c) {
+enum Group { G_VIT = 1, G_RS_LOCAL = 2, G_RS_GLOBAL = 4, G_PROJ = 8, G_LLM = 16 };
+
+int check_ready(slime_ctx* c, int groups) {
   if (c == nullptr) {
     slime_set_error("null context");
     return SLIME_EINVAL;
   }
   if (!c->finalized) {
     slime_set_error("weights not finalized: call slime_ctx_finalize_weights first");
+    return SLIME_ESTATE;
+  }
+  const int have = (c->has_vit ? G_VIT : 0) | (c->has_rs[0] ? G_RS_LOCAL : 0) | (c->has_rs[1] ? G_RS_GLOBAL : 0) |
+                   (c->has_proj ? G_PROJ : 0) | (c->has_llm ? G_LLM : 0);
+  if ((have & groups) != groups) {
+    slime_set_error("stage needs weight groups 0x%x but only 0x%x are registered (1 vit, 2 rs_local, 4 rs_global, "
+                    "8 proj, 16 llm)", groups, have);
     return SLIME_ESTATE;
   }
   return SLIME_OK;
@@ -444,6 +457,14 @@ int slime_ctx_finalize_weights(slime_ctx* c, void* ws, size_t ws_bytes, void* st
   const slime_model_desc& d = c->d;
   const int D = d.vit_hidden, I = d.vit_mlp, H = d.hidden;
 #define W(name, r, cc, dst) SLIME_PROPAGATE(find_weight(c, name, r, cc, &(dst)))
+  c->has_vit = c->w.count("vit.patch_w") > 0;
+  c->has_rs[0] = c->w.count("rs_local.query") > 0;
+  c->has_rs[1] = c->w.count("rs_global.query") > 0;
+  c->has_proj = c->w.count("proj.fc1_w") > 0;
+  c->has_llm = c->w.count("llm.embed") > 0;
+  SLIME_REQUIRE(c->has_vit || c->has_rs[0] || c->has_rs[1] || c->has_proj || c->has_llm,
+                "finalize: no weight group registered");
+  if (c->has_vit) {
   W("vit.patch_w", D, c->vit_kpad, c->vit_patch_w);
   W("vit.cls", 1, D, c->vit_cls);
   W("vit.pos", c->vit_tokens, D, c->vit_pos);
@@ -466,7 +487,9 @@ int slime_ctx_finalize_weights(slime_ctx* c, void* ws, size_t ws_bytes, void* st
     W(p + "fc2_w", D, I, L.fc2_w);
     W(p + "fc2_b", 1, D, L.fc2_b);
   }
+  }  // has_vit
   for (int which = 0; which < 2; ++which) {
+    if (!c->has_rs[which]) continue;
     const std::string p = which == 0 ? "rs_local." : "rs_global.";
     Resampler& R = c->rs[which];
     R.nq = which == 0 ? d.rs_local_queries : d.rs_global_queries;
@@ -489,12 +512,15 @@ int slime_ctx_finalize_weights(slime_ctx* c, void* ws, size_t ws_bytes, void* st
     R.derived_q = const_cast<bf16*>(dq);
     R.derived_kvbias = const_cast<bf16*>(dk);
   }
+  if (c->has_proj) {
   W("proj.fc1_w", H, D, c->proj_fc1_w);
   W("proj.fc1_b", 1, H, c->proj_fc1_b);
   W("proj.fc2_w", H, H, c->proj_fc2_w);
   W("proj.fc2_b", 1, H, c->proj_fc2_b);
   W("proj.w_gate", D, 2, c->proj_w_gate);
+  }  // has_proj
   const int QKV = (d.heads + 2 * d.kv_heads) * d.head_dim;
+  if (c->has_llm) {
   W("llm.embed", d.vocab, H, c->llm_embed);
   W("llm.norm_w", 1, H, c->llm_norm_w);
   W("llm.lm_head", d.vocab, H, c->llm_lm_head);
@@ -509,6 +535,7 @@ int slime_ctx_finalize_weights(slime_ctx* c, void* ws, size_t ws_bytes, void* st
     W(p + "gate_up_w", 2 * d.mlp, H, L.gate_up_w);
     W(p + "down_w", H, d.mlp, L.down_w);
   }
+  }  // has_llm
 #undef W
   SLIME_REQUIRE(D % 128 == 0, "Resampler needs mm_hidden_size %% 128 == 0 (heads = D/128)");
   Arena a(ws, ws_bytes);
@@ -526,7 +553,7 @@ size_t slime_vision_tower_workspace_bytes(const slime_ctx* ctx, int n_crops) {
 }
 int slime_vision_tower_fwd(slime_ctx* ctx, const void* pixels, int n_crops, void* feats, void* ws,
                            size_t ws_bytes, void* stream) {
-  SLIME_PROPAGATE(check_ready(ctx));
+  SLIME_PROPAGATE(check_ready(ctx, G_VIT));
   SLIME_REQUIRE(pixels && feats && ws, "vision_tower: null pointer");
   if (n_crops <= 0) return SLIME_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -543,8 +570,8 @@ size_t slime_resampler_workspace_bytes(const slime_ctx* ctx, int which, int n) {
 }
 int slime_resampler_fwd(slime_ctx* ctx, int which, const void* x, int n, void* out, void* ws, size_t ws_bytes,
                         void* stream) {
-  SLIME_PROPAGATE(check_ready(ctx));
   SLIME_REQUIRE(which == 0 || which == 1, "resampler: which must be 0 (local) or 1 (global)");
+  SLIME_PROPAGATE(check_ready(ctx, which == 0 ? G_RS_LOCAL : G_RS_GLOBAL));
   if (n <= 0) return SLIME_OK;
   SLIME_REQUIRE(x && out && ws, "resampler: null pointer");
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -561,7 +588,7 @@ size_t slime_projector_workspace_bytes(const slime_ctx* ctx, int rows) {
 }
 int slime_projector_fwd(slime_ctx* ctx, const void* x, int rows, const int32_t* row_map, void* out, void* ws,
                         size_t ws_bytes, void* stream) {
-  SLIME_PROPAGATE(check_ready(ctx));
+  SLIME_PROPAGATE(check_ready(ctx, G_PROJ));
   if (rows <= 0) return SLIME_OK;
   SLIME_REQUIRE(x && out && ws, "projector: null pointer");
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -576,7 +603,7 @@ size_t slime_gated_projector_workspace_bytes(const slime_ctx* ctx, int n) {
 }
 int slime_gated_projector_fwd(slime_ctx* ctx, const void* x, int n, void* out, void* ws, size_t ws_bytes,
                               void* stream) {
-  SLIME_PROPAGATE(check_ready(ctx));
+  SLIME_PROPAGATE(check_ready(ctx, G_PROJ | (ctx != nullptr && ctx->d.mm_learnable_gated == 0 ? 0 : G_RS_GLOBAL)));
   if (n <= 0) return SLIME_OK;
   SLIME_REQUIRE(x && out && ws, "gated_projector: null pointer");
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -588,21 +615,32 @@ int slime_gated_projector_fwd(slime_ctx* ctx, const void* x, int n, void* out, v
 // ---- router ----
 size_t slime_router_workspace_bytes(const slime_ctx* ctx, int batch, int n_per, int prompt_len) {
   Arena a(nullptr, 0);
-  router_body(const_cast<slime_ctx*>(ctx), a, nullptr, n_per, nullptr, nullptr, nullptr, batch > 0 ? batch : 1,
+  router_body(const_cast<slime_ctx*>(ctx), a, nullptr, n_per, nullptr, nullptr, nullptr, nullptr, batch > 0 ? batch : 1,
               prompt_len > 0 ? prompt_len : 1, nullptr, nullptr, nullptr, nullptr);
   return a.off + 256;
 }
 int slime_router_fwd(slime_ctx* ctx, const void* local, int n_per, const int32_t* n_valid, const int64_t* ids,
                      const uint8_t* mask, int batch, int prompt_len, float* probs_out, int32_t* sel_idx,
                      int32_t* sel_count, void* ws, size_t ws_bytes, void* stream) {
-  SLIME_PROPAGATE(check_ready(ctx));
+  SLIME_PROPAGATE(check_ready(ctx, G_LLM));
   SLIME_REQUIRE(ids && sel_idx && sel_count && ws, "router: null pointer");
   SLIME_REQUIRE(n_per <= 0 || local != nullptr, "router: null local features");
   std::lock_guard<std::mutex> lk(ctx->mu);
   Arena a(ws, ws_bytes);
   return router_body(ctx, a, static_cast<const bf16*>(local), n_per, n_valid,
-                     reinterpret_cast<const long long*>(ids), mask, batch, prompt_len, probs_out, sel_idx,
+                     reinterpret_cast<const long long*>(ids), nullptr, mask, batch, prompt_len, probs_out, sel_idx,
                      sel_count, static_cast<cudaStream_t>(stream));
+}
+int slime_router_fwd_embeds(slime_ctx* ctx, const void* local, int n_per, const int32_t* n_valid,
+                            const void* text_embeds, const uint8_t* mask, int batch, int prompt_len, float* probs_out,
+                            int32_t* sel_idx, int32_t* sel_count, void* ws, size_t ws_bytes, void* stream) {
+  SLIME_REQUIRE(ctx != nullptr && text_embeds && sel_idx && sel_count && ws, "router_embeds: null pointer");
+  SLIME_REQUIRE(n_per <= 0 || local != nullptr, "router_embeds: null local features");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Arena a(ws, ws_bytes);
+  return router_body(ctx, a, static_cast<const bf16*>(local), n_per, n_valid, nullptr,
+                     static_cast<const bf16*>(text_embeds), mask, batch, prompt_len, probs_out, sel_idx, sel_count,
+                     static_cast<cudaStream_t>(stream));
 }
 int slime_router_select(slime_ctx* ctx, const float* probs, int batch, int n_per, const int32_t* n_valid,
                         int32_t* sel_idx, int32_t* sel_count, void* stream) {
@@ -651,7 +689,7 @@ int slime_splice_gather(slime_ctx* ctx, const int64_t* ids, int batch, int promp
                         const void* local_feats, int64_t local_sample_rows, const int32_t* sel_idx,
                         int sel_stride, int has_sep, void* out_embeds, int32_t* pos_ids, int total_rows,
                         void* stream) {
-  SLIME_PROPAGATE(check_ready(ctx));
+  SLIME_PROPAGATE(check_ready(ctx, G_LLM));
   SLIME_REQUIRE(ids && plan_buf && out_embeds, "splice_gather: null pointer");
   int32_t* pb = const_cast<int32_t*>(plan_buf);
   return slime_launch_splice_gather(reinterpret_cast<const long long*>(ids), prompt_len, plan_valid(pb),
@@ -695,7 +733,7 @@ size_t slime_decoder_workspace_bytes(const slime_ctx* ctx, int total_rows, int b
 int slime_decoder_prefill_fwd(slime_ctx* ctx, const void* embeds, const int32_t* cu_seqlens, const int32_t* pos_ids,
                               int batch, int total_rows, int max_seqlen, float* logits_last, void* logits_all,
                               void* hidden_out, void* ws, size_t ws_bytes, void* stream) {
-  SLIME_PROPAGATE(check_ready(ctx));
+  SLIME_PROPAGATE(check_ready(ctx, G_LLM));
   SLIME_REQUIRE(embeds && cu_seqlens && pos_ids && ws, "decoder: null pointer");
   SLIME_REQUIRE(max_seqlen <= ctx->d.max_pos, "decoder: sequence length %d exceeds max_pos %d", max_seqlen,
                 ctx->d.max_pos);

@@ -24,8 +24,10 @@ __global__ void text_inv_norm_kernel(const long long* __restrict__ ids, const un
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * T) return;
-  const long long id = ids[row];
-  const bool keep = (mask == nullptr || mask[row] != 0) && id != image_token && id >= 0 && id < vocab;
+  // ids == nullptr: `embed` is a dense [B*T, H] tensor and row t is its own embedding
+  const long long id = ids != nullptr ? ids[row] : row;
+  const bool keep = (mask == nullptr || mask[row] != 0) &&
+                    (ids == nullptr || (id != image_token && id >= 0 && id < vocab));
   float r = 0.f;
   if (keep) {
     const bf16* e = embed + id * H;
@@ -56,7 +58,8 @@ __global__ void text_dir_kernel(const long long* __restrict__ ids, const float* 
   for (int t = 0; t < T; ++t) {
     const float w = nr[t];
     if (w != 0.f) {
-      const float2 e = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(embed + idr[t] * H + col));
+      const long long er = ids != nullptr ? idr[t] : static_cast<long long>(b) * T + t;
+      const float2 e = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(embed + er * H + col));
       a0 += w * e.x;
       a1 += w * e.y;
     }

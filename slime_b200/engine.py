@@ -20,7 +20,7 @@ import torch
 from . import _lib as L
 from .config import IGNORE_INDEX, IMAGE_TOKEN_INDEX, SlimeConfig
 from .mm_utils import get_anyres_image_grid_shape
-from .weights import pack_weights
+from .weights import ALL_GROUPS, pack_weights
 
 
 def _locked(fn):
@@ -96,13 +96,15 @@ class SlimeEngine:
         except Exception:
             pass
 
-    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], groups=ALL_GROUPS) -> None:
         """Accepts the reference model's state-dict keys."""
-        self.load_weights(lambda name: state_dict[name])
+        self.load_weights(lambda name: state_dict[name], groups)
 
-    def load_weights(self, get: Callable[[str], torch.Tensor]) -> None:
+    def load_weights(self, get: Callable[[str], torch.Tensor], groups=ALL_GROUPS) -> None:
+        """groups: which weight groups to register ("vit", "rs_local", "rs_global", "proj", "llm"); a stage
+        whose group is absent fails loudly (used by the stand-alone module shims of slime_b200/model)."""
         with self._lock, torch.cuda.device(self.device):
-            self.weights = pack_weights(self.cfg, get, self.device)
+            self.weights = pack_weights(self.cfg, get, self.device, groups)
             for name, t in self.weights.items():
                 L.check(self.lib.slime_ctx_set_weight(self._ctx, name.encode(), L.ptr(t), t.shape[0], t.shape[1]),
                         f"set_weight({name})")
@@ -195,6 +197,25 @@ class SlimeEngine:
         L.check(self.lib.slime_router_fwd(self._ctx, L.ptr(local), n_per, L.ptr(n_valid), L.ptr(ids),
                                           L.ptr(m8), B, T, L.ptr(probs), L.ptr(sel_idx), L.ptr(sel_count), L.ptr(ws),
                                           ws.numel(), L.stream_ptr()), "router_fwd")
+        return sel_idx, sel_count, probs
+
+    @_locked
+    def router_embeds(self, local: torch.Tensor, text_embeds: torch.Tensor, mask: Optional[torch.Tensor],
+                      want_probs: bool = False):
+        """The reference's module-level signature TextGuidedSampler.forward(local_f, text_embedding, attn_mask)
+        (multimodal_resampler/builder.py:248): the prompt arrives as embeddings [B,T,H], not ids."""
+        local = local.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        text = text_embeds.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        B, n_per = local.shape[0], local.shape[1]
+        T = text.shape[1]
+        m8 = None if mask is None else (mask != 0).to(device=self.device, dtype=torch.uint8).contiguous()
+        sel_idx = torch.zeros(B, max(n_per, 1), dtype=torch.int32, device=self.device)
+        sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
+        probs = torch.zeros(B, max(n_per, 1), dtype=torch.float32, device=self.device) if want_probs else None
+        ws = self._workspace(self.lib.slime_router_workspace_bytes(self._ctx, B, n_per, T))
+        L.check(self.lib.slime_router_fwd_embeds(self._ctx, L.ptr(local), n_per, None, L.ptr(text), L.ptr(m8), B, T,
+                                                 L.ptr(probs), L.ptr(sel_idx), L.ptr(sel_count), L.ptr(ws), ws.numel(),
+                                                 L.stream_ptr()), "router_fwd_embeds")
         return sel_idx, sel_count, probs
 
     @_locked
@@ -297,13 +318,47 @@ class SlimeEngine:
         self._row_maps[key] = out
         return out
 
+    # ------------------------------------------------------------------ module-API helpers (slime_b200/model)
+    @torch.no_grad()
+    def prefill_splice(self, pixels, input_ids, attention_mask=None, grids=None, labels=None, padded=True,
+                       forced_selection=None) -> dict:
+        """encode_images + splice without the decoder: what prepare_inputs_labels_for_multimodal returns
+        (reference llava_arch.py:274-459).  Result: {'splice': {...padded + packed tensors...}, 'sel_idx', ...}."""
+        res = self.prefill(pixels, input_ids, attention_mask, grids=grids, labels=labels,
+                           forced_selection=forced_selection, want_last=False, keep_stages=True, run_decoder=False)
+        return dict(splice=res.stages["splice"], sel_idx=res.sel_idx, sel_count=res.sel_count, lengths=res.lengths,
+                    glob=res.stages.get("glob"), local=res.stages.get("local_m"))
+
+    @torch.no_grad()
+    def prefill_features(self, pixels, input_ids, attention_mask=None, grids=None) -> List[torch.Tensor]:
+        """Per-sample image feature blocks [1, 576 + 1 + K_b, H] exactly as the sampler branch of the reference's
+        encode_images returns them (llava_arch.py:249-255): global tokens, separator, kept local tokens."""
+        cfg = self.cfg
+        res = self.prefill(pixels, input_ids, attention_mask, grids=grids, want_last=False, keep_stages=True,
+                           run_decoder=False, run_splice=False)
+        st = res.stages
+        counts = res.sel_count.cpu().tolist() if res.sel_count is not None else None
+        sep = self.weights["llm.embed"][cfg.seperator][None]
+        out = []
+        B = input_ids.shape[0]
+        for b in range(B):
+            parts = []
+            if not cfg.use_local_only:
+                parts.append(st["glob"][b])
+                if not cfg.use_global_only:
+                    parts.append(sep)
+            if not cfg.use_global_only:
+                parts.append(st["local_m"][b][res.sel_idx[b, :counts[b]].long()])
+            out.append(torch.cat(parts, 0).unsqueeze(0))
+        return out
+
     # ------------------------------------------------------------------ whole path
     @torch.no_grad()
     def prefill(self, pixels, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 image_sizes: Optional[Sequence[Tuple[int, int]]] = None, grids: Optional[Sequence[Tuple[int, int]]] = None,
                 labels: Optional[torch.Tensor] = None, forced_selection: Optional[Sequence[torch.Tensor]] = None,
                 want_last: bool = True, want_all_logits: bool = False, want_probs: bool = False,
-                keep_stages: bool = False) -> PrefillResult:
+                keep_stages: bool = False, run_decoder: bool = True, run_splice: bool = True) -> PrefillResult:
         """LlavaLlamaForCausalLM.forward(images=...) (reference llava_llama.py:57-104 -> llava_arch.py:274-459).
 
         pixels: [B, n, 3, S, S] tensor or list of per-sample [n_b, 3, S, S] tensors (crop 0 = global view).
@@ -374,10 +429,17 @@ class SlimeEngine:
                 else:
                     sel_idx = torch.zeros(B, 1, dtype=torch.int32, device=self.device)
                     sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
+            if not run_splice:
+                if stages is not None:
+                    stages.update(vit=feats, glob=glob, local_m=local)
+                return PrefillResult(logits_last=None, logits_all=None, cu_seqlens=None, lengths=[], sel_idx=sel_idx,
+                                     sel_count=sel_count, probs=probs, embeds=None, stages=stages)
             sp = self.splice(ids, mask, glob, local, sel_idx, sel_count, n_global, has_sep, labels=labels,
                              padded=keep_stages)
-            last, allv, _ = self.decoder_prefill(sp["embeds"], sp["cu_seqlens"], sp["pos_ids"], sp["lengths"],
-                                                 want_last=want_last, want_all=want_all_logits)
+            last = allv = None
+            if run_decoder:
+                last, allv, _ = self.decoder_prefill(sp["embeds"], sp["cu_seqlens"], sp["pos_ids"], sp["lengths"],
+                                                     want_last=want_last, want_all=want_all_logits)
             if stages is not None:
                 stages.update(vit=feats, glob=glob, local_m=local, splice=sp)
             return PrefillResult(logits_last=last, logits_all=allv, cu_seqlens=sp["cu_seqlens"], lengths=sp["lengths"],

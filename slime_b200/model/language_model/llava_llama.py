@@ -1,0 +1,288 @@
+"""Drop-in for the reference's llava/model/language_model/llava_llama.py: LlavaConfig, LlavaLlamaModel and
+LlavaLlamaForCausalLM with the reference's forward / generate / prepare_inputs_for_generation signatures and
+state-dict keys (model.embed_tokens, model.layers.N.*, model.norm, lm_head, model.vision_tower.*,
+model.mm_projector.*, model.sampler.*).  The nn.Modules only HOLD the parameters; every FLOP of forward()
+runs in libslime_b200 (vision tower, adapter, router, splice, Llama prefill on packed rows).
+
+Not built (SURVEY.md section 8f "next"): the KV-cache decode step - generate() re-runs the packed prefill on the
+grown sequence for every new token (correct, O(n^2)); beam search; training (loss is provided for parity of
+the forward signature, computed from the returned logits with torch).
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from ...config import IGNORE_INDEX, SlimeConfig
+from .._runtime import EngineBinding, bind, binding_of
+from ..llava_arch import LlavaMetaForCausalLM, LlavaMetaModel
+
+
+class LlavaConfig:
+    """Attribute bag with LlamaConfig's defaults; `model_type` as registered by the reference (:30-31)."""
+
+    model_type = "llava_llama"
+    _defaults = dict(vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                     num_attention_heads=32, num_key_value_heads=None, rms_norm_eps=1e-5, rope_theta=10000.0,
+                     max_position_embeddings=4096, pad_token_id=0, bos_token_id=1, eos_token_id=2, pretraining_tp=1,
+                     tie_word_embeddings=False, torch_dtype="bfloat16")
+
+    def __init__(self, **kwargs):
+        for k, v in self._defaults.items():
+            setattr(self, k, v)
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+        if self.num_key_value_heads is None:
+            self.num_key_value_heads = self.num_attention_heads
+
+    @classmethod
+    def from_pretrained(cls, path: str, **kwargs):
+        with open(os.path.join(path, "config.json")) as f:
+            raw = json.load(f)
+        raw.update(kwargs)
+        return cls(**raw)
+
+    def to_dict(self):
+        return {k: v for k, v in self.__dict__.items() if not k.startswith("_")}
+
+
+@dataclass
+class CausalLMOutputWithPast:
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+    past_key_values: Optional[object] = None
+    hidden_states: Optional[Tuple[torch.Tensor]] = None
+    attentions: Optional[Tuple[torch.Tensor]] = None
+
+    def __getitem__(self, i):
+        return tuple(v for v in (self.loss, self.logits) if v is not None)[i]
+
+
+class _Norm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class _Bag(nn.Module):
+    pass
+
+
+class _LlamaParams(nn.Module):
+    """Parameter tree of HF LlamaModel (embed_tokens, layers.N.{self_attn,mlp,*layernorm}, norm)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H, I = config.hidden_size, config.intermediate_size
+        hd = getattr(config, "head_dim", None) or H // config.num_attention_heads
+        qd, kd = config.num_attention_heads * hd, config.num_key_value_heads * hd
+        self.embed_tokens = nn.Embedding(config.vocab_size, H)
+        layers = []
+        for _ in range(config.num_hidden_layers):
+            l = _Bag()
+            sa = _Bag()
+            sa.q_proj = nn.Linear(H, qd, bias=False)
+            sa.k_proj = nn.Linear(H, kd, bias=False)
+            sa.v_proj = nn.Linear(H, kd, bias=False)
+            sa.o_proj = nn.Linear(qd, H, bias=False)
+            l.self_attn = sa
+            mlp = _Bag()
+            mlp.gate_proj = nn.Linear(H, I, bias=False)
+            mlp.up_proj = nn.Linear(H, I, bias=False)
+            mlp.down_proj = nn.Linear(I, H, bias=False)
+            l.mlp = mlp
+            l.input_layernorm = _Norm(H)
+            l.post_attention_layernorm = _Norm(H)
+            layers.append(l)
+        self.layers = nn.ModuleList(layers)
+        self.norm = _Norm(H)
+
+
+class LlavaLlamaModel(LlavaMetaModel, _LlamaParams):
+    config_class = LlavaConfig
+
+    def __init__(self, config):
+        super(LlavaLlamaModel, self).__init__(config)
+
+
+class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
+    config_class = LlavaConfig
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.model = LlavaLlamaModel(config)
+        self.pretraining_tp = getattr(config, "pretraining_tp", 1)
+        self.vocab_size = config.vocab_size
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+
+    # ------------------------------------------------------------------ plumbing
+    def get_model(self):
+        return self.model
+
+    @property
+    def device(self):
+        return self.lm_head.weight.device
+
+    @property
+    def dtype(self):
+        return self.lm_head.weight.dtype
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def _slime_config(self) -> SlimeConfig:
+        vt = self.get_vision_tower()
+        return SlimeConfig.from_hf_config(self.config, vt.config if vt is not None else None)
+
+    def _engine(self, device=None):
+        vt = self.get_vision_tower()
+        if vt is None:
+            raise RuntimeError("config has no mm_vision_tower: nothing to run on the SliME path")
+        if not vt.is_loaded:
+            vt.load_model()
+            vt.to(device=self.device, dtype=self.dtype)
+        b = binding_of(self)
+        if b is None or b._owner() is not self:
+            b = EngineBinding(self, self._slime_config(), "", ("vit", "rs_local", "rs_global", "proj", "llm"))
+            bind(self, b)
+        return b.engine(device if device is not None and device.type == "cuda" else None)
+
+    # ------------------------------------------------------------------ forward (reference :57-104)
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, labels=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                images=None, images_mask=None, image_sizes=None, return_dict=None):
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("output_attentions / output_hidden_states are not produced by the fused path")
+        if past_key_values is not None:
+            raise NotImplementedError("KV-cache decode is the next scope item (SURVEY.md 8f.1)")
+        eng = self._engine(input_ids.device if input_ids is not None else inputs_embeds.device)
+        left = getattr(self.config, "tokenizer_padding_side", "right") == "left"
+        if inputs_embeds is None:
+            if images is None or input_ids.shape[1] == 1:
+                inputs_embeds = eng.weights["llm.embed"][input_ids.to(eng.device)]
+            else:
+                sp = self._spliced(input_ids, attention_mask, labels, images, image_sizes, images_mask,
+                                   padded=True)["splice"]
+                return self._decode_packed(eng, sp["embeds"], sp["cu_seqlens"], sp["pos_ids"], sp["lengths"], left,
+                                           sp["labels"] if labels is not None else None)
+        # caller-provided embeddings [B, L, H] (+ attention_mask): pack the real rows and run the decoder
+        B, Lm, _ = inputs_embeds.shape
+        am = torch.ones(B, Lm, dtype=torch.bool, device=inputs_embeds.device) if attention_mask is None \
+            else attention_mask.bool()
+        lengths = am.sum(1).tolist()
+        rows = inputs_embeds[am].to(device=eng.device, dtype=torch.bfloat16).contiguous()
+        cu = torch.tensor([0] + list(torch.tensor(lengths).cumsum(0)), dtype=torch.int32, device=eng.device)
+        pos = torch.cat([torch.arange(L) for L in lengths]).to(device=eng.device, dtype=torch.int32)
+        if position_ids is not None:
+            pos = position_ids.expand(B, Lm)[am].to(device=eng.device, dtype=torch.int32)
+        return self._decode_packed(eng, rows, cu, pos, lengths, left, labels)
+
+    def _decode_packed(self, eng, rows, cu, pos, lengths, left, labels):
+        _, allv, _ = eng.decoder_prefill(rows, cu, pos, lengths, want_last=False, want_all=True)
+        B, Lmax, V = len(lengths), max(lengths), self.vocab_size
+        logits = torch.zeros(B, Lmax, V, dtype=allv.dtype, device=allv.device)
+        off = 0
+        for b, L in enumerate(lengths):
+            if left:
+                logits[b, Lmax - L:] = allv[off:off + L]
+            else:
+                logits[b, :L] = allv[off:off + L]
+            off += L
+        loss = None
+        if labels is not None:
+            shift_logits = logits[:, :-1].float().reshape(-1, V)
+            shift_labels = labels[:, 1:].reshape(-1).to(logits.device)
+            loss = torch.nn.functional.cross_entropy(shift_logits, shift_labels, ignore_index=IGNORE_INDEX)
+        return CausalLMOutputWithPast(loss=loss, logits=logits)
+
+    # ------------------------------------------------------------------ generate (reference :106-144)
+    @torch.no_grad()
+    def generate(self, inputs=None, images=None, image_sizes=None, **kwargs):
+        position_ids = kwargs.pop("position_ids", None)
+        attention_mask = kwargs.pop("attention_mask", None)
+        if "inputs_embeds" in kwargs:
+            raise NotImplementedError("`inputs_embeds` is not supported")
+        max_new = int(kwargs.pop("max_new_tokens", 20))
+        do_sample = bool(kwargs.pop("do_sample", False))
+        temperature = float(kwargs.pop("temperature", 1.0) or 1.0)
+        top_p = kwargs.pop("top_p", None)
+        if int(kwargs.pop("num_beams", 1) or 1) != 1:
+            raise NotImplementedError("beam search is not built")
+        eos = kwargs.pop("eos_token_id", getattr(self.config, "eos_token_id", None))
+        eos = set(eos) if isinstance(eos, (list, tuple)) else ({eos} if eos is not None else set())
+        eng = self._engine(inputs.device)
+        table = eng.weights["llm.embed"]
+        if images is not None:
+            sp = self._spliced(inputs, attention_mask, None, images, image_sizes, None, padded=False)["splice"]
+            lengths = list(sp["lengths"])
+            cu = sp["cu_seqlens"].cpu().tolist()
+            seqs = [sp["embeds"][cu[b]:cu[b + 1]] for b in range(len(lengths))]
+        else:
+            am = torch.ones_like(inputs, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
+            seqs = [table[inputs[b][am[b]].to(table.device)] for b in range(inputs.shape[0])]
+        B = len(seqs)
+        out_tokens = [[] for _ in range(B)]
+        done = [False] * B
+        gen = torch.Generator(device=eng.device)
+        gen.manual_seed(int(kwargs.pop("seed", 0)))
+        for _ in range(max_new):
+            lengths = [s.shape[0] for s in seqs]
+            rows = torch.cat(seqs).contiguous()
+            cu_t = torch.tensor([0] + list(torch.tensor(lengths).cumsum(0)), dtype=torch.int32, device=eng.device)
+            pos = torch.cat([torch.arange(L) for L in lengths]).to(device=eng.device, dtype=torch.int32)
+            last, _, _ = eng.decoder_prefill(rows, cu_t, pos, lengths, want_last=True)
+            if do_sample:
+                probs = torch.softmax(last / max(temperature, 1e-5), dim=-1)
+                if top_p is not None and top_p < 1.0:
+                    sp_, si = torch.sort(probs, descending=True)
+                    keep = (torch.cumsum(sp_, -1) - sp_) < top_p
+                    sp_ = sp_ * keep
+                    probs = torch.zeros_like(probs).scatter(1, si, sp_ / sp_.sum(-1, keepdim=True))
+                nxt = torch.multinomial(probs, 1, generator=gen).squeeze(1)
+            else:
+                nxt = last.argmax(-1)
+            nxt_l = nxt.tolist()
+            for b in range(B):
+                if done[b]:
+                    continue
+                out_tokens[b].append(nxt_l[b])
+                if nxt_l[b] in eos:
+                    done[b] = True
+                seqs[b] = torch.cat([seqs[b], table[nxt[b]][None]])
+            if all(done):
+                break
+        width = max(len(t) for t in out_tokens)
+        pad = getattr(self.config, "pad_token_id", 0) or 0
+        return torch.tensor([t + [pad] * (width - len(t)) for t in out_tokens], dtype=torch.long, device=inputs.device)
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
+        images = kwargs.pop("images", None)
+        image_sizes = kwargs.pop("image_sizes", None)
+        inputs = dict(input_ids=input_ids, past_key_values=past_key_values, inputs_embeds=inputs_embeds, **kwargs)
+        if images is not None:
+            inputs["images"] = images
+        if image_sizes is not None:
+            inputs["image_sizes"] = image_sizes
+        return inputs
+
+
+def _register_with_transformers():
+    """AutoConfig / AutoModelForCausalLM registration as in the reference (:159-160), when transformers is
+    importable and the name is still free (the reference itself may already be registered)."""
+    try:
+        from transformers import AutoConfig
+
+        AutoConfig.register("llava_llama", LlavaConfig)  # type: ignore[arg-type]
+    except Exception:
+        pass

@@ -1,0 +1,52 @@
+"""Data-parallel plumbing for the SliME prefill path: samples are independent, so the batch is
+split into contiguous per-rank shards, weights are replicated, and the ONLY exchange step is the gather of the
+last-token logits.  torch.distributed does the plumbing (NCCL over NVLink on the GPUs; gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_samples: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of the batch owned by `rank`; block sizes differ by at most one."""
+    base, extra = divmod(n_samples, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def balanced_order(costs: Sequence[int], world: int) -> List[int]:
+    """Sample order that evens out per-rank work when crop counts differ (the reference's training-side
+    analogue is group_by_modality_length, llava/train/train.py:131): sort by cost descending and deal the
+    samples round-robin, then lay the ranks' lists out contiguously so shard_bounds() picks them up."""
+    idx = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    per_rank: List[List[int]] = [[] for _ in range(world)]
+    sizes = [shard_bounds(len(costs), r, world) for r in range(world)]
+    cap = [hi - lo for lo, hi in sizes]
+    r = 0
+    for i in idx:
+        while len(per_rank[r]) >= cap[r]:
+            r = (r + 1) % world
+        per_rank[r].append(i)
+        r = (r + 1) % world
+    return [i for lst in per_rank for i in sorted(lst)]
+
+
+def gather_logits(local_logits: torch.Tensor, n_samples: int, group=None) -> torch.Tensor:
+    """All-gather [B_local, V] logits into [n_samples, V] in global sample order.  Ranks may own blocks that
+    differ by one row: shorter blocks are zero-padded for the collective and trimmed afterwards."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local_logits
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [hi - lo for lo, hi in (shard_bounds(n_samples, r, world) for r in range(world))]
+    width = max(sizes)
+    assert local_logits.shape[0] == sizes[rank], (local_logits.shape, sizes, rank)
+    buf = local_logits
+    if sizes[rank] < width:
+        buf = torch.cat([local_logits, local_logits.new_zeros(width - sizes[rank], local_logits.shape[1])])
+    out = local_logits.new_empty(world * width, local_logits.shape[1])
+    dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
+    if all(s == width for s in sizes):
+        return out
+    return torch.cat([out[r * width: r * width + sizes[r]] for r in range(world)])

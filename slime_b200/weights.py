@@ -34,7 +34,11 @@ def resize_pos_table(pos: torch.Tensor, tgt: int) -> torch.Tensor:
     return out.permute(0, 2, 3, 1).flatten(0, 2).to(pos.dtype)
 
 
-def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device) -> Dict[str, torch.Tensor]:
+ALL_GROUPS = ("vit", "rs_local", "rs_global", "proj", "llm")
+
+
+def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device,
+                 groups=ALL_GROUPS) -> Dict[str, torch.Tensor]:
     """get(name) returns the reference tensor `name` (any dtype/device); returns canonical-name ->
     contiguous bf16 CUDA tensor (2-D).  Tensors are pulled one at a time so a lazy source (e.g. the
     on-GPU synthetic generator) never holds two copies of the model."""
@@ -45,6 +49,19 @@ def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device) -
 
     out: Dict[str, torch.Tensor] = {}
     D, H = cfg.vit_hidden, cfg.hidden_size
+    v = CLIP_PREFIX
+    if "vit" in groups:
+        _pack_vit(cfg, g, out)
+    _pack_adapter(cfg, g, out, device, groups)
+    if "llm" in groups:
+        _pack_llm(cfg, g, out)
+    for k, t in out.items():
+        assert t.dim() == 2 and t.is_contiguous() and t.dtype == bf, k
+    return out
+
+
+def _pack_vit(cfg, g, out):
+    D = cfg.vit_hidden
     v = CLIP_PREFIX
     pw = g(v + "embeddings.patch_embedding.weight").reshape(D, -1)
     out["vit.patch_w"] = F.pad(pw, (0, cfg.vit_kpad - pw.shape[1])).contiguous()
@@ -66,9 +83,16 @@ def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device) -
         out[c + "fc1_b"] = g(p + "mlp.fc1.bias").reshape(1, -1)
         out[c + "fc2_w"] = g(p + "mlp.fc2.weight").contiguous()
         out[c + "fc2_b"] = g(p + "mlp.fc2.bias").reshape(1, -1)
+
+
+def _pack_adapter(cfg, g, out, device, groups):
+    bf = torch.bfloat16
+    D = cfg.vit_hidden
     side = int(math.sqrt(cfg.vit_patches))
     for ref_prefix, c, nq in (("model.sampler.post_qformer.", "rs_local.", cfg.mm_resampler_dim),
                               ("model.mm_projector.attn.", "rs_global.", 576)):
+        if c[:-1] not in groups:
+            continue
         pos = g(ref_prefix + "pos_embed")
         out[c + "query"] = g(ref_prefix + "query").contiguous()
         out[c + "pos_q"] = pos.contiguous()
@@ -82,12 +106,18 @@ def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device) -
             out[c + ln + "_b"] = g(ref_prefix + ln + ".bias").reshape(1, -1)
         out[c + "derived_q"] = torch.zeros(nq, D, device=device, dtype=bf)
         out[c + "derived_kvbias"] = torch.zeros(cfg.vit_patches, 2 * D, device=device, dtype=bf)
+    if "proj" not in groups:
+        return
     m = "model.mm_projector."
     out["proj.fc1_w"] = g(m + "projection.0.weight").contiguous()
     out["proj.fc1_b"] = g(m + "projection.0.bias").reshape(1, -1)
     out["proj.fc2_w"] = g(m + "projection.2.weight").contiguous()
     out["proj.fc2_b"] = g(m + "projection.2.bias").reshape(1, -1)
     out["proj.w_gate"] = g(m + "w_gate").contiguous()
+
+
+def _pack_llm(cfg, g, out):
+    H = cfg.hidden_size
     out["llm.embed"] = g("model.embed_tokens.weight").contiguous()
     out["llm.norm_w"] = g("model.norm.weight").reshape(1, -1)
     out["llm.lm_head"] = g("lm_head.weight").contiguous()
@@ -101,6 +131,3 @@ def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device) -
         out[c + "down_w"] = g(p + "mlp.down_proj.weight").contiguous()
         out[c + "in_norm_w"] = g(p + "input_layernorm.weight").reshape(1, -1)
         out[c + "post_norm_w"] = g(p + "post_attention_layernorm.weight").reshape(1, -1)
-    for k, t in out.items():
-        assert t.dim() == 2 and t.is_contiguous() and t.dtype == bf, k
-    return out

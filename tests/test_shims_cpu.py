@@ -1,0 +1,99 @@
+"""CPU checks of the drop-in module API (slime_b200/model): same class names / attributes / state-dict keys as
+the reference's llava/model package, and no silent CPU fallback."""
+import json
+import os
+import tempfile
+
+import pytest
+import torch
+
+from slime_b200.config import SlimeConfig, preset
+from slime_b200.synth import synth_state_dict
+
+
+def make_model(pname="tiny", **over):
+    from slime_b200.model import LlavaConfig, LlavaLlamaForCausalLM
+
+    cfg = preset(pname, **over)
+    tmp = tempfile.mkdtemp(prefix="slime_clip_cfg_")
+    with open(os.path.join(tmp, "config.json"), "w") as f:
+        json.dump(dict(hidden_size=cfg.vit_hidden, intermediate_size=cfg.vit_mlp, num_hidden_layers=cfg.vit_layers,
+                       num_attention_heads=cfg.vit_heads, image_size=cfg.vit_image, patch_size=cfg.vit_patch,
+                       layer_norm_eps=cfg.vit_ln_eps), f)
+    hf = LlavaConfig(hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                     num_hidden_layers=cfg.num_hidden_layers, num_attention_heads=cfg.num_attention_heads,
+                     num_key_value_heads=cfg.num_key_value_heads, head_dim=cfg.head_dim, vocab_size=cfg.vocab_size,
+                     rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
+                     max_position_embeddings=cfg.max_position_embeddings, pad_token_id=cfg.pad_token_id,
+                     mm_vision_tower=tmp, mm_vision_select_layer=cfg.mm_vision_select_layer,
+                     mm_vision_select_feature="patch", mm_projector_type="gated", mm_hidden_size=cfg.vit_hidden,
+                     mm_resampler_type="cosine", mm_resampler_dim=cfg.mm_resampler_dim,
+                     mm_resampler_topp=cfg.mm_resampler_topp, mm_resampler_temp=cfg.mm_resampler_temp,
+                     mm_learnable_gated=-1, mm_patch_merge_type=cfg.mm_patch_merge_type, image_aspect_ratio="anyres",
+                     seperator=cfg.seperator, tokenizer_padding_side=cfg.tokenizer_padding_side,
+                     tokenizer_model_max_length=cfg.tokenizer_model_max_length,
+                     image_grid_pinpoints=[[336, 672], [672, 336], [672, 672], [1008, 336], [336, 1008]])
+    model = LlavaLlamaForCausalLM(hf)
+    model.get_vision_tower().load_model()
+    return cfg, model
+
+
+def test_state_dict_keys_match_reference_exactly():
+    """synth_state_dict is strict-loaded by the UNMODIFIED reference in oracle/gen_golden.py; loading the same
+    dict strictly here proves the shim tree has exactly the reference's parameter names and shapes."""
+    cfg, model = make_model()
+    sd = synth_state_dict(cfg)
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert set(model.state_dict().keys()) == set(sd.keys())
+
+
+def test_reference_attributes_present():
+    cfg, model = make_model()
+    inner = model.get_model()
+    assert inner.has_sampler is True
+    vt = model.get_vision_tower()
+    assert vt.is_loaded and vt.hidden_size == cfg.vit_hidden and vt.num_patches == 576
+    assert vt.num_patches_per_side == 24 and vt.config.image_size == 336
+    assert inner.sampler.grid_size == 12 and hasattr(inner.sampler, "post_qformer")
+    assert inner.mm_projector.expert_ffn[0] is inner.mm_projector.projection
+    assert inner.mm_projector.expert_ffn[1] is inner.mm_projector.attn
+    for name in ("forward", "generate", "prepare_inputs_for_generation", "encode_images", "get_pure_text_embedding",
+                 "prepare_inputs_labels_for_multimodal", "initialize_vision_tokenizer", "get_model",
+                 "get_vision_tower"):
+        assert callable(getattr(model, name))
+    from slime_b200.model import LlavaConfig
+
+    assert LlavaConfig.model_type == "llava_llama"
+    got = model._slime_config()
+    for k in ("vit_hidden", "vit_layers", "vit_heads", "vit_mlp", "hidden_size", "num_hidden_layers",
+              "num_attention_heads", "num_key_value_heads", "head_dim", "intermediate_size", "vocab_size",
+              "mm_resampler_dim", "mm_resampler_topp", "seperator", "mm_patch_merge_type"):
+        assert getattr(got, k) == getattr(cfg, k), k
+
+
+def test_no_cpu_fallback():
+    cfg, model = make_model()
+    model.load_state_dict(synth_state_dict(cfg))
+    ids = torch.randint(3, 100, (1, 8))
+    ids[0, 2] = -200
+    px = torch.randn(1, 5, 3, 336, 336)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_shims_gpu.py")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(input_ids=ids, images=px, image_sizes=[(672, 672)])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.get_vision_tower()(px[0])
+
+
+def test_unsupported_variants_fail_loudly():
+    from types import SimpleNamespace
+
+    from slime_b200.model.multimodal_projector.builder import build_vision_projector
+    from slime_b200.model.multimodal_resampler.builder import build_vision_sampler
+
+    with pytest.raises(NotImplementedError):
+        build_vision_projector(SimpleNamespace(mm_projector_type="mlp2x_gelu", mm_hidden_size=1024, hidden_size=4096))
+    with pytest.raises(NotImplementedError):
+        build_vision_sampler(SimpleNamespace(mm_resampler_type="qformer", mm_resampler_dim=144, mm_resampler_topp=0.9,
+                                             mm_resampler_temp=1.0, mm_hidden_size=1024, hidden_size=4096))
