@@ -172,7 +172,9 @@ int slime_op_gemm(const void* a, int lda, const void* w, int ldw, int m, int n, 
 int slime_op_attention(const void* q, const void* k, const void* v, void* o, int q_ld, int k_ld, int v_ld,
                        int o_ld, const int32_t* cu_q, const int32_t* cu_k, int seqlen_q, int seqlen_k,
                        int64_t q_batch_rows, int64_t k_batch_rows, int64_t o_batch_rows, int batch,
-                       int heads, int kv_heads, int head_dim, float scale, int causal, void* stream);
+                       int heads, int kv_heads, int head_dim, float scale, int causal, int64_t total_q_rows,
+                       int64_t total_k_rows, int impl /* 0 default, 1 mma.sync kernel, 2 tcgen05 kernel */,
+                       void* stream);
 int slime_op_layernorm(const void* x, const void* w, const void* b, void* y, int rows, int dim, float eps,
                        void* stream);
 int slime_op_rmsnorm(const void* x, const void* w, void* y, int rows, int dim, float eps, void* stream);

@@ -85,7 +85,7 @@ SIGNATURES = {
     "slime_decoder_prefill_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "slime_op_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "slime_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i64, _i64, _i64, _i, _i, _i,
-                                _i, _f, _i, _vp]),
+                                _i, _f, _i, _i64, _i64, _i, _vp]),
     "slime_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "slime_op_rmsnorm": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
     "slime_op_rope": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

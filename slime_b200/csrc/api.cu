@@ -303,6 +303,7 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
     ap.q_batch_rows = ap.k_batch_rows = ap.o_batch_rows = 0;
     ap.batch = B; ap.num_heads = d.heads; ap.num_kv_heads = d.kv_heads; ap.head_dim = hd;
     ap.scale = 1.0f / sqrtf(static_cast<float>(hd)); ap.causal = 1;
+    ap.total_q_rows = ap.total_k_rows = total;
     SLIME_PROPAGATE(slime_launch_attention(ap, s));
     SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, total, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s));
     SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.post_norm_w, t, H, total, H, d.rms_eps, nullptr, s));
@@ -769,7 +770,7 @@ int slime_op_gemm(const void* a, int lda, const void* w, int ldw, int m, int n, 
 int slime_op_attention(const void* q, const void* k, const void* v, void* o, int q_ld, int k_ld, int v_ld, int o_ld,
                        const int32_t* cu_q, const int32_t* cu_k, int seqlen_q, int seqlen_k, int64_t q_batch_rows,
                        int64_t k_batch_rows, int64_t o_batch_rows, int batch, int heads, int kv_heads, int head_dim,
-                       float scale, int causal, void* stream) {
+                       float scale, int causal, int64_t total_q_rows, int64_t total_k_rows, int impl, void* stream) {
   AttnParams ap;
   ap.q = static_cast<const bf16*>(q);
   ap.k = static_cast<const bf16*>(k);
@@ -781,6 +782,7 @@ int slime_op_attention(const void* q, const void* k, const void* v, void* o, int
   ap.q_batch_rows = q_batch_rows; ap.k_batch_rows = k_batch_rows; ap.o_batch_rows = o_batch_rows;
   ap.batch = batch; ap.num_heads = heads; ap.num_kv_heads = kv_heads; ap.head_dim = head_dim;
   ap.scale = scale; ap.causal = causal;
+  ap.total_q_rows = total_q_rows; ap.total_k_rows = total_k_rows; ap.impl = impl;
   return slime_launch_attention(ap, static_cast<cudaStream_t>(stream));
 }
 

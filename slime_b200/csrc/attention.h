@@ -19,6 +19,11 @@ struct AttnParams {
   int head_dim;  // 64 or 128
   float scale;   // softmax scale (1/sqrt(head_dim))
   int causal;    // 1: query i attends keys <= i + (seqlen_k - seqlen_q)
+  long long total_q_rows = 0;  // rows of the q matrix (needed for the TMA map when cu_q != nullptr; 0 = derive)
+  long long total_k_rows = 0;  // rows of the k / v matrices (same)
+  int impl = 0;                // 0 = default (tcgen05), 1 = mma.sync flash kernel, 2 = tcgen05
 };
 
 int slime_launch_attention(const AttnParams& p, cudaStream_t stream);
+// tcgen05 / TMEM implementation (attention_tc.cu)
+int slime_launch_attention_tc(const AttnParams& p, int num_sms, cudaStream_t stream);

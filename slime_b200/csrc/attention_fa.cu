@@ -11,6 +11,8 @@
 // Round-1 implementation: 64x64 tiles, 4 warps, K/V double-buffered with cp.async, S = QK^T and
 // O += PV on mma.sync.m16n8k16 with the online-softmax running max/sum in registers.  (Attention is
 // 3 % of the decoder FLOPs and 9 % of the ViT FLOPs; the tcgen05/TMEM version is the planned upgrade.)
+#include <cstdlib>
+
 #include "attention.h"
 #include "errors.h"
 
@@ -312,6 +314,19 @@ int slime_launch_attention(const AttnParams& p, cudaStream_t stream) {
                   reinterpret_cast<uintptr_t>(p.v) | reinterpret_cast<uintptr_t>(p.o)) & 15) == 0,
                 "attention: tensors must be 16-byte aligned");
   if (p.batch <= 0 || p.seqlen_q <= 0) return SLIME_OK;
+  // implementation choice: tcgen05/TMEM kernel by default; SLIME_ATTN_IMPL=fa2 (or impl == 1) selects the
+  // mma.sync kernel kept for A/B measurements
+  static int env_impl = -1;
+  static int num_sms = 0;
+  if (env_impl < 0) {
+    const char* e = getenv("SLIME_ATTN_IMPL");
+    env_impl = (e != nullptr && (e[0] == 't' || e[0] == '2')) ? 2 : 1;  // TODO flip once tcgen05 path is validated
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int impl = p.impl != 0 ? p.impl : env_impl;
+  if (impl == 2) return slime_launch_attention_tc(p, num_sms, stream);
   if (p.head_dim == 64) {
     return p.causal ? launch<64, true>(p, stream) : launch<64, false>(p, stream);
   }

@@ -1,0 +1,386 @@
+// tcgen05 / TMEM flash attention forward for sm_100a (bf16 in, fp32 softmax + accumulation, bf16 out).
+//
+// One persistent CTA per SM walks a static list of work items (batch, head, 128-row query tile).
+//   warp 0     : TMA producer - Q tile once per item, K and V tiles through a 2-stage ring
+//                (64-column slabs of 128 rows, 128-byte swizzle; heads are column slices of packed rows)
+//   warp 1     : tcgen05.mma issuer (one thread) + TMEM allocator
+//                  S_j = Q K_j^T       SS-MMA 128 x 128 x HD  -> TMEM S buffer (double buffered)
+//                  O  += P_j V_j       TS-MMA 128 x HD x 128  -> TMEM O, A = P_j read from TMEM,
+//                                      B = V_j in shared memory as an MN-major operand
+//   warps 2..5 : softmax + epilogue.  Thread r owns query row r of the tile (TMEM lane r): row max / row sum
+//                are thread-local, no shuffles.  exp2 with the softmax scale folded in; P_j (bf16, two per
+//                32-bit column) overwrites the first 64 columns of the S buffer it came from.
+//                O is only rescaled when the running max grows by more than 2^8 (lazy rescale), so the
+//                TMEM round trip of the accumulator is rare; the final 1/l normalisation absorbs the rest.
+// S_{j+1} is issued before the softmax of S_j finishes, so the tensor pipe alternates S and PV MMAs
+// back to back while the softmax of the next tile runs.
+//
+// Shapes on the SliME path: CLIP (16 heads x 64, S = 577, non-causal), Resampler cross-attention (8 x 128,
+// 144/576 shared queries x 576 keys), Llama decoder (h x 128, causal, GQA, packed variable-length rows).
+#include "attention.h"
+#include "errors.h"
+#include "gemm.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int SLAB_BYTES = 128 * 128;  // 128 rows x 64 bf16
+constexpr int NT = 192;
+constexpr int KV_STAGES = 2;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // in log2 units: P stays below 2^8
+
+template <int HD>
+struct TcCfg {
+  static constexpr int SLABS = HD / 64;
+  static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
+  // >= 120 KB so that two CTAs can never share an SM (each allocates all 512 TMEM columns)
+  static constexpr int SMEM_RAW = 1024 + TILE_BYTES * (1 + 2 * KV_STAGES) + 256;
+  static constexpr int SMEM_BYTES = SMEM_RAW > 120 * 1024 ? SMEM_RAW : 120 * 1024;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;
+};
+
+struct Item {
+  int b, head, kv_head, t;
+  int len_q, len_k, causal_off, n_tiles;
+  int q_row0, k_row0;  // first row of this sequence in the q / kv matrices
+  long long o_row0;
+  bool valid;
+};
+
+template <bool CAUSAL>
+SLIME_DEVINL Item decode_item(const AttnParams& p, int w, int q_tiles) {
+  Item it;
+  it.head = w % p.num_heads;
+  const int rest = w / p.num_heads;
+  it.b = rest % p.batch;
+  const int ti = rest / p.batch;
+  it.t = CAUSAL ? (q_tiles - 1 - ti) : ti;  // heavy (late) causal tiles first
+  it.kv_head = it.head / (p.num_heads / p.num_kv_heads);
+  if (p.cu_q != nullptr) {
+    it.q_row0 = p.cu_q[it.b];
+    it.len_q = p.cu_q[it.b + 1] - it.q_row0;
+    it.o_row0 = it.q_row0;
+  } else {
+    it.q_row0 = static_cast<int>(it.b * p.q_batch_rows);
+    it.o_row0 = it.b * p.o_batch_rows;
+    it.len_q = p.seqlen_q;
+  }
+  if (p.cu_k != nullptr) {
+    it.k_row0 = p.cu_k[it.b];
+    it.len_k = p.cu_k[it.b + 1] - it.k_row0;
+  } else {
+    it.k_row0 = static_cast<int>(it.b * p.k_batch_rows);
+    it.len_k = p.seqlen_k;
+  }
+  it.causal_off = it.len_k - it.len_q;
+  const int m0 = it.t * BM;
+  it.valid = m0 < it.len_q && it.len_k > 0;
+  int last = it.len_k;
+  if (CAUSAL) last = min(it.len_k, m0 + BM + it.causal_off);
+  it.n_tiles = it.valid ? max(0, (last + BN - 1) / BN) : 0;
+  if (it.n_tiles == 0) it.valid = false;
+  return it;
+}
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(NT, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+               const __grid_constant__ CUtensorMap tmap_v, const AttnParams p, int q_col0, int k_col0, int v_col0,
+               int q_tiles, int total_items) {
+  using Cfg = TcCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::TILE_BYTES;
+  uint8_t* sV = sK + KV_STAGES * Cfg::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * Cfg::TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;   // [2]
+  uint64_t* k_empty = bars + 4;  // [2]
+  uint64_t* v_full = bars + 6;   // [2]
+  uint64_t* v_empty = bars + 8;  // [2]
+  uint64_t* s_full = bars + 10;  // [2]
+  uint64_t* p_ready = bars + 12; // [2]
+  uint64_t* o_done = bars + 14;
+  uint64_t* o_free = bars + 15;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 128);
+    }
+    mbar_init(o_done, 1);
+    mbar_init(o_free, 128);
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp_idx == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int item_cnt = 0, g = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const Item it = decode_item<CAUSAL>(p, w, q_tiles);
+        if (!it.valid) continue;
+        mbar_wait(q_empty, (item_cnt & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, Cfg::TILE_BYTES);
+#pragma unroll
+        for (int s = 0; s < Cfg::SLABS; ++s)
+          tma_load_2d(sQ + s * SLAB_BYTES, &tmap_q, q_full, q_col0 + it.head * HD + s * 64, it.q_row0 + it.t * BM);
+        for (int j = 0; j < it.n_tiles; ++j, ++g) {
+          const int st = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int s = 0; s < Cfg::SLABS; ++s)
+            tma_load_2d(sK + st * Cfg::TILE_BYTES + s * SLAB_BYTES, &tmap_k, &k_full[st],
+                        k_col0 + it.kv_head * HD + s * 64, it.k_row0 + j * BN);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int s = 0; s < Cfg::SLABS; ++s)
+            tma_load_2d(sV + st * Cfg::TILE_BYTES + s * SLAB_BYTES, &tmap_v, &v_full[st],
+                        v_col0 + it.kv_head * HD + s * 64, it.k_row0 + j * BN);
+        }
+        ++item_cnt;
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_major(BM, BN, 0, 0);   // Q, K both K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16_major(BM, HD, 0, 1);  // P from TMEM, V MN-major
+      const uint32_t sQ_addr = smem_u32(sQ);
+      int item_cnt = 0, g = 0;
+
+      auto issue_s = [&](int gi, bool last_of_item) {
+        const int st = gi & 1;
+        mbar_wait(&k_full[st], (gi >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t sK_addr = smem_u32(sK + st * Cfg::TILE_BYTES);
+        const uint32_t tmem_s = tmem_base + (st ? Cfg::S_COL1 : Cfg::S_COL0);
+#pragma unroll
+        for (int s = 0; s < Cfg::SLABS; ++s) {
+          const uint64_t dq = make_umma_desc_sw128(sQ_addr + s * SLAB_BYTES);
+          const uint64_t dk = make_umma_desc_sw128(sK_addr + s * SLAB_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, (s | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[st]);
+        if (last_of_item) umma_commit(q_empty);
+      };
+
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const Item it = decode_item<CAUSAL>(p, w, q_tiles);
+        if (!it.valid) continue;
+        mbar_wait(q_full, item_cnt & 1);
+        tcgen05_fence_after();
+        issue_s(g, it.n_tiles == 1);
+        for (int j = 0; j < it.n_tiles; ++j) {
+          const int gj = g + j;
+          const int st = gj & 1;
+          if (j + 1 < it.n_tiles) issue_s(gj + 1, j + 2 == it.n_tiles);
+          if (j == 0) mbar_wait(o_free, (item_cnt & 1) ^ 1);  // epilogue of the previous item has drained O
+          mbar_wait(&p_ready[st], (gj >> 1) & 1);
+          mbar_wait(&v_full[st], (gj >> 1) & 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_p = tmem_base + (st ? Cfg::S_COL1 : Cfg::S_COL0);
+          const uint64_t dv = make_umma_desc_mn_sw128(smem_u32(sV + st * Cfg::TILE_BYTES), SLAB_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            // A: 16 kv positions = 8 TMEM columns of packed bf16 pairs;  B: 16 kv rows = 2048 bytes further down
+            umma_bf16_ts(tmem_base + Cfg::O_COL, tmem_p + kk * 8, dv + static_cast<uint64_t>(kk * (2048 >> 4)),
+                         idesc_pv, (j | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&v_empty[st]);
+          umma_commit(o_done);
+        }
+        g += it.n_tiles;
+        ++item_cnt;
+      }
+    }
+  } else {
+    // ================================ softmax + epilogue ==========================
+    const int quad = warp_idx & 3;
+    const int r_in_tile = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const float scale_log2 = p.scale * 1.4426950408889634f;
+    int item_cnt = 0, g = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const Item it = decode_item<CAUSAL>(p, w, q_tiles);
+      if (!it.valid) continue;
+      const int row = it.t * BM + r_in_tile;  // query index inside the sequence
+      float m_ref = -INFINITY;                // raw-score max the exponentials are taken against
+      float l_sum = 0.f;
+      for (int j = 0; j < it.n_tiles; ++j) {
+        const int gj = g + j;
+        const int buf = gj & 1;
+        const uint32_t s_addr = tmem_base + lane_addr + (buf ? Cfg::S_COL1 : Cfg::S_COL0);
+        mbar_wait(&s_full[buf], (gj >> 1) & 1);
+        tcgen05_fence_after();
+        uint32_t sr[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sr + c * 32);
+        tmem_ld_wait();
+
+        const int col_base = j * BN;
+        const bool need_mask = (col_base + BN > it.len_k) || (CAUSAL && (col_base + BN - 1 > it.t * BM + it.causal_off));
+        float m_tile = -INFINITY;
+        if (need_mask) {
+          const int limit = CAUSAL ? min(it.len_k - 1, row + it.causal_off) : it.len_k - 1;  // last visible column
+#pragma unroll
+          for (int c = 0; c < 128; ++c) {
+            float v = __uint_as_float(sr[c]);
+            if (col_base + c > limit) v = -INFINITY;
+            sr[c] = __float_as_uint(v);
+            m_tile = fmaxf(m_tile, v);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) m_tile = fmaxf(m_tile, __uint_as_float(sr[c]));
+        }
+
+        // lazy rescale: only move the reference max when it grew by more than 2^8 (or on the first tile)
+        bool grow = (m_tile - m_ref) * scale_log2 > RESCALE_THRESHOLD;  // also true when m_ref == -inf and m_tile finite
+        if (m_tile == -INFINITY) grow = false;
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? exp2f((m_ref - m_tile) * scale_log2) : 1.0f;  // m_ref == -inf -> 0
+          l_sum *= alpha;
+          mbar_wait(o_done, (gj - 1) & 1);  // PV_{j-1} finished: O is stable until p_ready lets PV_j go
+          tcgen05_fence_after();
+          const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t orow[32];
+            tmem_ld_32x32b_x32(o_addr + c * 32, orow);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr + c * 32, orow);
+          }
+          tmem_st_wait();
+        }
+        if (grow) m_ref = m_tile;
+        const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * scale_log2;
+
+        uint32_t pk[64];
+        float psum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const float p0 = exp2f(__uint_as_float(sr[2 * c]) * scale_log2 - m_scaled);
+          const float p1 = exp2f(__uint_as_float(sr[2 * c + 1]) * scale_log2 - m_scaled);
+          psum += p0 + p1;
+          pk[c] = pack_bf16x2(p0, p1);
+        }
+        l_sum += psum;
+        tmem_st_32x32b_x32(s_addr, pk);
+        tmem_st_32x32b_x32(s_addr + 32, pk + 32);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&p_ready[buf]);
+      }
+      // ---- epilogue: O / l -> bf16 -> HBM (one 2*HD-byte row per thread) ----
+      // parity waits are only unambiguous one phase back: PV_{last-1} may still be in flight here
+      const int g_last = g + it.n_tiles - 1;
+      if (it.n_tiles > 1) mbar_wait(o_done, (g_last - 1) & 1);
+      mbar_wait(o_done, g_last & 1);
+      tcgen05_fence_after();
+      const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
+      const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
+      bf16* orow_ptr = p.o + (it.o_row0 + row) * p.o_ld + it.head * HD;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t orow[32];
+        tmem_ld_32x32b_x32(o_addr + c * 32, orow);
+        tmem_ld_wait();
+        if (row < it.len_q) {
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            uint4 pkv;
+            pkv.x = pack_bf16x2(__uint_as_float(orow[v8 * 8 + 0]) * inv_l, __uint_as_float(orow[v8 * 8 + 1]) * inv_l);
+            pkv.y = pack_bf16x2(__uint_as_float(orow[v8 * 8 + 2]) * inv_l, __uint_as_float(orow[v8 * 8 + 3]) * inv_l);
+            pkv.z = pack_bf16x2(__uint_as_float(orow[v8 * 8 + 4]) * inv_l, __uint_as_float(orow[v8 * 8 + 5]) * inv_l);
+            pkv.w = pack_bf16x2(__uint_as_float(orow[v8 * 8 + 6]) * inv_l, __uint_as_float(orow[v8 * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow_ptr + c * 32 + v8 * 8) = pkv;
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(o_free);
+      g += it.n_tiles;
+      ++item_cnt;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int HD, bool CAUSAL>
+int launch_tc(const AttnParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = TcCfg<HD>;
+  auto kern = attn_tc_kernel<HD, CAUSAL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SLIME_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  // Tensor maps over the packed row matrices; the kernel addresses heads by column offset.  Base pointers are
+  // rounded down to the start of their row so q / k / v views of one packed qkv buffer share a map shape.
+  const long long q_rows = p.total_q_rows > 0 ? p.total_q_rows
+                           : (p.q_batch_rows > 0 ? p.q_batch_rows * p.batch : p.seqlen_q);
+  const long long k_rows = p.total_k_rows > 0 ? p.total_k_rows
+                           : (p.k_batch_rows > 0 ? p.k_batch_rows * p.batch : p.seqlen_k);
+  CUtensorMap tq, tk, tv;
+  SLIME_PROPAGATE(slime_get_tmap(p.q, static_cast<int>(q_rows), p.num_heads * HD, p.q_ld, BM, &tq));
+  SLIME_PROPAGATE(slime_get_tmap(p.k, static_cast<int>(k_rows), p.num_kv_heads * HD, p.k_ld, BN, &tk));
+  SLIME_PROPAGATE(slime_get_tmap(p.v, static_cast<int>(k_rows), p.num_kv_heads * HD, p.v_ld, BN, &tv));
+  const int q_tiles = (p.seqlen_q + BM - 1) / BM;
+  const int total = q_tiles * p.num_heads * p.batch;
+  const int grid = total < num_sms ? total : num_sms;
+  double flops = 0.0;
+  if (p.cu_q == nullptr)
+    flops = 4.0 * p.seqlen_q * static_cast<double>(p.seqlen_k) * HD * p.num_heads * p.batch * (CAUSAL ? 0.5 : 1.0);
+  slime_prof_begin(1, flops, stream);
+  kern<<<grid, NT, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p, 0, 0, 0, q_tiles, total);
+  slime_prof_end(stream);
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
+
+}  // namespace
+
+int slime_launch_attention_tc(const AttnParams& p, int num_sms, cudaStream_t stream) {
+  if (p.batch <= 0 || p.seqlen_q <= 0 || p.seqlen_k <= 0) return SLIME_OK;
+  if (p.head_dim == 64) {
+    return p.causal ? launch_tc<64, true>(p, num_sms, stream) : launch_tc<64, false>(p, num_sms, stream);
+  }
+  return p.causal ? launch_tc<128, true>(p, num_sms, stream) : launch_tc<128, false>(p, num_sms, stream);
+}

@@ -8,8 +8,9 @@
 //   * epilogue warps read TMEM with tcgen05.ld and apply bias / activation / residual / SwiGLU /
 //     row scatter before writing bf16 (or fp32) straight to HBM with 16-byte vector stores.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (warp w owns TMEM lane quadrant w % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (warp w owns TMEM lane quadrant w % 4; two warps per quadrant split the columns;
+// see gemm_epilogue.cuh).
 //
 // This one kernel carries every dense contraction of the SliME prefill path: CLIP patch-embed /
 // QKV / out-proj / MLP (HF clip/modeling_clip.py:209,310-312,334,348-350), the Resampler K/V and
@@ -27,7 +28,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int GROUP_M = 8;  // m-blocks per rasterisation group (L2 reuse of the W tiles)
 
 template <int BLOCK_N>
@@ -57,9 +59,7 @@ SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n) {
   return c;
 }
 
-SLIME_DEVINL float act_quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
-SLIME_DEVINL float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-SLIME_DEVINL float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+#include "gemm_epilogue.cuh"
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -96,7 +96,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], 32 * NUM_EPI_WARPS);
     }
     fence_barrier_init();
   } else if (warp_idx == 1) {
@@ -161,8 +161,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ============================ epilogue ================================
-    const int quad = warp_idx & 3;  // TMEM lane quadrant this warp may access
+    // ============================ epilogue (8 warps) ======================
+    const int quad = warp_idx & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp_idx - 2) >> 2;   // warps 2..5 take the low half of the columns, 6..9 the high half
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const TileCoord tc = tile_coord(t, num_m, num_n);
@@ -170,93 +171,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-
-      const int row = tc.m_blk * BLOCK_M + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      int out_row = row;
-      if (row_ok && p.row_map != nullptr) out_row = p.row_map[row];
-      const bool store_ok = row_ok && out_row >= 0;
-      int res_row = row;
-      if (p.res_period > 0) res_row = row % p.res_period;
-
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = tc.n_blk * BLOCK_N + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N +
-                               c * 32,
-                           r);
-        tmem_ld_wait();
-        if (!store_ok) continue;
-
-        if constexpr (EPI == GEMM_EPI_SWIGLU) {
-          // columns are (gate_j, up_j) interleaved -> 16 outputs per 32 accumulator columns
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int col = col0 + g * 16;
-            if (col >= p.N) break;
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float gate = __uint_as_float(r[g * 16 + 2 * j]);
-              const float up = __uint_as_float(r[g * 16 + 2 * j + 1]);
-              o[j] = act_silu(gate) * up;
-            }
-            uint4 pk;
-            pk.x = pack_bf16x2(o[0], o[1]);
-            pk.y = pack_bf16x2(o[2], o[3]);
-            pk.z = pack_bf16x2(o[4], o[5]);
-            pk.w = pack_bf16x2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(out_row) * p.out_ld + (col >> 1)) =
-                pk;
-          }
-        } else {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col >= p.N) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-            if (p.bias != nullptr) {
-              const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-              const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y),
-                           b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
-              v[4] += b2.x; v[5] += b2.y; v[6] += b3.x; v[7] += b3.y;
-            }
-            if constexpr (EPI == GEMM_EPI_QUICK_GELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = act_quick_gelu(v[j]);
-            } else if constexpr (EPI == GEMM_EPI_GELU_ERF) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = act_gelu_erf(v[j]);
-            }
-            if (p.residual != nullptr) {
-              const uint4 q = *reinterpret_cast<const uint4*>(
-                  p.residual + static_cast<size_t>(res_row) * p.res_ld + col);
-              const float2 q0 = unpack_bf16x2(q.x), q1 = unpack_bf16x2(q.y),
-                           q2 = unpack_bf16x2(q.z), q3 = unpack_bf16x2(q.w);
-              v[0] += q0.x; v[1] += q0.y; v[2] += q1.x; v[3] += q1.y;
-              v[4] += q2.x; v[5] += q2.y; v[6] += q3.x; v[7] += q3.y;
-            }
-            if (p.out_f32 != nullptr) {
-              float4* dst =
-                  reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(out_row) * p.out_ld + col);
-              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              uint4 pk;
-              pk.x = pack_bf16x2(v[0], v[1]);
-              pk.y = pack_bf16x2(v[2], v[3]);
-              pk.z = pack_bf16x2(v[4], v[5]);
-              pk.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(out_row) * p.out_ld + col) = pk;
-            }
-          }
-        }
-      }
+      epilogue_tile<BLOCK_N, EPI>(p, tmem_base + acc * BLOCK_N, tc.m_blk * BLOCK_M, tc.n_blk * BLOCK_N, quad, half,
+                                  lane);
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
     }
@@ -393,6 +309,10 @@ int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
 }
 
 }  // namespace
+
+int slime_get_tmap(const bf16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  return get_tmap(ptr, rows, cols, ld, box_rows, out);
+}
 
 int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                       int num_sms, cudaStream_t stream) {

@@ -161,7 +161,8 @@ def attention(q, k, v, o_rows, o_ld, **kw):
                                 L.ptr(kw.get("cu_q")), L.ptr(kw.get("cu_k")), kw["seqlen_q"], kw["seqlen_k"],
                                 kw.get("q_batch_rows", 0), kw.get("k_batch_rows", 0), kw.get("o_batch_rows", 0),
                                 kw["batch"], kw["heads"], kw["kv_heads"], kw["head_dim"], kw["scale"],
-                                kw.get("causal", 0), L.stream_ptr())
+                                kw.get("causal", 0), kw.get("total_q_rows", 0), kw.get("total_k_rows", 0),
+                                kw.get("impl", 0), L.stream_ptr())
     L.check(rc, "op_attention")
     torch.cuda.synchronize()
     return o
@@ -177,7 +178,11 @@ def ref_attention(q, k, v, scale, causal):
     return torch.softmax(s, dim=-1) @ v
 
 
-def test_attention_clip_shape():
+IMPLS = [pytest.param(2, id="tcgen05"), pytest.param(1, id="mma_sync")]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_attention_clip_shape(impl):
     """16 heads x 64, S = 577 (4*128+65: ragged tail tile), non-causal, packed qkv rows."""
     torch.manual_seed(6)
     B, h, d, S = 3, 16, 64, 577
@@ -185,14 +190,15 @@ def test_attention_clip_shape():
     qkv = rnd(B * S, 3 * D)
     o = attention(qkv, qkv[:, D:], qkv[:, 2 * D:], B * S, D, q_ld=3 * D, k_ld=3 * D, v_ld=3 * D, seqlen_q=S,
                   seqlen_k=S, q_batch_rows=S, k_batch_rows=S, o_batch_rows=S, batch=B, heads=h, kv_heads=h,
-                  head_dim=d, scale=d ** -0.5)
+                  head_dim=d, scale=d ** -0.5, impl=impl)
     x = qkv.float().view(B, S, 3, h, d).permute(2, 0, 3, 1, 4)
     ref = ref_attention(x[0], x[1], x[2], d ** -0.5, False).permute(0, 2, 1, 3).reshape(B * S, D)
     assert_close_bf16(o, ref, "attention clip")
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("nq", [144, 576])
-def test_attention_resampler_shape(nq):
+def test_attention_resampler_shape(nq, impl):
     """8 heads x 128, shared learned queries (q_batch_rows = 0) against 576 keys per crop."""
     torch.manual_seed(7)
     n, h, d, NK = 4, 8, 128, 576
@@ -201,7 +207,7 @@ def test_attention_resampler_shape(nq):
     kv = rnd(n * NK, 2 * D)
     o = attention(q, kv, kv[:, D:], n * nq, D, q_ld=D, k_ld=2 * D, v_ld=2 * D, seqlen_q=nq, seqlen_k=NK,
                   q_batch_rows=0, k_batch_rows=NK, o_batch_rows=nq, batch=n, heads=h, kv_heads=h, head_dim=d,
-                  scale=d ** -0.5)
+                  scale=d ** -0.5, impl=impl)
     qf = q.float().view(1, nq, h, d).permute(0, 2, 1, 3).expand(n, h, nq, d)
     kf = kv[:, :D].float().view(n, NK, h, d).permute(0, 2, 1, 3)
     vf = kv[:, D:].float().view(n, NK, h, d).permute(0, 2, 1, 3)
@@ -209,18 +215,19 @@ def test_attention_resampler_shape(nq):
     assert_close_bf16(o, ref, f"attention resampler nq={nq}")
 
 
-def test_attention_decoder_causal_varlen_gqa():
+@pytest.mark.parametrize("impl", IMPLS)
+def test_attention_decoder_causal_varlen_gqa(impl):
     """Packed variable-length causal attention with GQA 32/8 heads x 128 (Llama-3 layout)."""
     torch.manual_seed(8)
     h, kvh, d = 8, 2, 128
-    lens = [1, 63, 64, 65, 200, 333]
+    lens = [1, 63, 64, 65, 127, 128, 129, 200, 333, 1400]
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device="cuda", dtype=torch.int32)
     total = sum(lens)
     W = (h + 2 * kvh) * d
     qkv = rnd(total, W)
     o = attention(qkv, qkv[:, h * d:], qkv[:, (h + kvh) * d:], total, h * d, q_ld=W, k_ld=W, v_ld=W, cu_q=cu,
                   cu_k=cu, seqlen_q=max(lens), seqlen_k=max(lens), batch=len(lens), heads=h, kv_heads=kvh,
-                  head_dim=d, scale=d ** -0.5, causal=1)
+                  head_dim=d, scale=d ** -0.5, causal=1, total_q_rows=total, total_k_rows=total, impl=impl)
     off = 0
     for L_ in lens:
         blk = qkv[off:off + L_].float()
