@@ -320,7 +320,7 @@ int slime_launch_attention(const AttnParams& p, cudaStream_t stream) {
   static int num_sms = 0;
   if (env_impl < 0) {
     const char* e = getenv("SLIME_ATTN_IMPL");
-    env_impl = (e != nullptr && (e[0] == 't' || e[0] == '2')) ? 2 : 1;  // TODO flip once tcgen05 path is validated
+    env_impl = (e != nullptr && (e[0] == 'f' || e[0] == '1')) ? 1 : 2;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);

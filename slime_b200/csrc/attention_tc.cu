@@ -104,9 +104,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* v_empty = bars + 8;  // [2]
   uint64_t* s_full = bars + 10;  // [2]
   uint64_t* p_ready = bars + 12; // [2]
-  uint64_t* o_done = bars + 14;
-  uint64_t* o_free = bars + 15;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* o_done = bars + 14;  // [2]: PV with global index g commits o_done[g & 1] (phase g >> 1), so a waiter is
+                                 // never more than one phase behind and parity waits stay unambiguous
+  uint64_t* o_free = bars + 16;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,7 +126,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&s_full[s], 1);
       mbar_init(&p_ready[s], 128);
     }
-    mbar_init(o_done, 1);
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
     mbar_init(o_free, 128);
     fence_barrier_init();
   } else if (warp_idx == 1) {
@@ -216,7 +218,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                          idesc_pv, (j | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&v_empty[st]);
-          umma_commit(o_done);
+          umma_commit(&o_done[gj & 1]);
         }
         g += it.n_tiles;
         ++item_cnt;
@@ -269,7 +271,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
           const float alpha = grow ? exp2f((m_ref - m_tile) * scale_log2) : 1.0f;  // m_ref == -inf -> 0
           l_sum *= alpha;
-          mbar_wait(o_done, (gj - 1) & 1);  // PV_{j-1} finished: O is stable until p_ready lets PV_j go
+          mbar_wait(&o_done[(gj - 1) & 1], ((gj - 1) >> 1) & 1);  // PV_{j-1} finished: O is stable until p_ready lets PV_j go
           tcgen05_fence_after();
           const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
 #pragma unroll
@@ -303,10 +305,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         mbar_arrive(&p_ready[buf]);
       }
       // ---- epilogue: O / l -> bf16 -> HBM (one 2*HD-byte row per thread) ----
-      // parity waits are only unambiguous one phase back: PV_{last-1} may still be in flight here
       const int g_last = g + it.n_tiles - 1;
-      if (it.n_tiles > 1) mbar_wait(o_done, (g_last - 1) & 1);
-      mbar_wait(o_done, g_last & 1);
+      mbar_wait(&o_done[g_last & 1], (g_last >> 1) & 1);
       tcgen05_fence_after();
       const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
       const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;

@@ -26,7 +26,7 @@ def setup():
     cfg, model = make_model("tiny")
     sd = synth_state_dict(cfg)
     model.load_state_dict(sd, strict=True)
-    model = model.to(device="cuda", dtype=torch.bfloat16)
+    model = model.to(device="cuda", dtype=torch.bfloat16).eval()
     px, ids, mask = synth_inputs(cfg, 2, 5, 24, image_pos=5, ragged=True)
     with torch.no_grad():
         ora = O.prefill(sd, cfg, px, ids, mask, [(2, 2)] * 2)
