@@ -41,6 +41,13 @@ struct TcCfg {
   static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;
 };
 
+// MUFU.EX2 without the denormal/range fix-up code exp2f() adds (inputs here are <= 8, -inf -> 0)
+SLIME_DEVINL float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct Item {
   int b, head, kv_head, t;
   int len_q, len_k, causal_off, n_tiles;
@@ -250,7 +257,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
         const int col_base = j * BN;
         const bool need_mask = (col_base + BN > it.len_k) || (CAUSAL && (col_base + BN - 1 > it.t * BM + it.causal_off));
-        float m_tile = -INFINITY;
+        // 4 independent max chains: with one warp per scheduler a single 128-long dependent chain would
+        // cost 128 x the FMNMX latency
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (need_mask) {
           const int limit = CAUSAL ? min(it.len_k - 1, row + it.causal_off) : it.len_k - 1;  // last visible column
 #pragma unroll
@@ -258,12 +267,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             float v = __uint_as_float(sr[c]);
             if (col_base + c > limit) v = -INFINITY;
             sr[c] = __float_as_uint(v);
-            m_tile = fmaxf(m_tile, v);
+            mx4[c & 3] = fmaxf(mx4[c & 3], v);
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 128; ++c) m_tile = fmaxf(m_tile, __uint_as_float(sr[c]));
+          for (int c = 0; c < 128; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(sr[c]));
         }
+        const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 
         // lazy rescale: only move the reference max when it grew by more than 2^8 (or on the first tile)
         bool grow = (m_tile - m_ref) * scale_log2 > RESCALE_THRESHOLD;  // also true when m_ref == -inf and m_tile finite
@@ -289,15 +299,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * scale_log2;
 
         uint32_t pk[64];
-        float psum = 0.f;
+        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
-          const float p0 = exp2f(__uint_as_float(sr[2 * c]) * scale_log2 - m_scaled);
-          const float p1 = exp2f(__uint_as_float(sr[2 * c + 1]) * scale_log2 - m_scaled);
-          psum += p0 + p1;
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_scaled));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_scaled));
+          ps4[c & 3] += p0 + p1;
           pk[c] = pack_bf16x2(p0, p1);
         }
-        l_sum += psum;
+        l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         tmem_st_32x32b_x32(s_addr, pk);
         tmem_st_32x32b_x32(s_addr + 32, pk + 32);
         tmem_st_wait();
