@@ -182,6 +182,9 @@ int slime_op_rope(slime_ctx* ctx, void* qkv, int ld, int rows, const int32_t* po
 
 /* ---- accounting: kernels launched by the library since load; optional CUDA-event profiling of the
  * library's own launches (class 0 = tcgen05 GEMM [work = FLOPs], 1 = attention, 2 = other) ---- */
+/* GEMM kernel selection: 0 = 1-CTA kernel only, 1 = force the 2-CTA (cta_group::2) kernel, 2 = 2-CTA for problems
+ * that fill the GPU, -1 = back to the default (SLIME_GEMM_2CTA environment variable / build default). */
+int slime_gemm_set_2cta_mode(int mode);
 long long slime_launch_count(void);
 int slime_profile_enable(int on);
 int slime_profile_collect(double* ms3, double* work3, long long* launches3);

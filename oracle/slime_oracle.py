@@ -176,6 +176,7 @@ def top_p_select(probs: torch.Tensor, top_p: float) -> torch.Tensor:
     """The selection rule of TextGuidedSampler.forward (reference multimodal_resampler/builder.py:259-273),
     with the tie-break the framework specifies (stable: lower index first among equal probabilities;
     torch.sort(descending) is unstable).  Returns ascending kept indices."""
+    probs = probs.detach().cpu()
     order = sorted(range(probs.numel()), key=lambda i: (-float(probs[i]), i))
     sp = probs[order]
     cum = torch.cumsum(sp, dim=0)

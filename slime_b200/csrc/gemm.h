@@ -1,4 +1,4 @@
-// Host-side interface of the tcgen05 bf16 GEMM (gemm_sm100.cu).
+// Host-side interface of the tcgen05 bf16 GEMM (gemm_sm100.cu, gemm2_sm100.cu).
 #pragma once
 #include "common.cuh"
 
@@ -21,9 +21,18 @@ struct GemmParams {
   int out_ld;          // leading dimension of the output (elements)
 };
 
+// 0 = 1-CTA kernel only, 1 = always the 2-CTA kernel, 2 = 2-CTA for problems that fill the GPU.
+// (the SLIME_GEMM_2CTA environment variable overrides this at run time)
+#ifndef SLIME_GEMM_2CTA_DEFAULT
+#define SLIME_GEMM_2CTA_DEFAULT 0
+#endif
+
 // Returns 0 on success; negative SLIME_E* otherwise (message via slime_set_error).
 int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                       int num_sms, cudaStream_t stream);
+// cta_group::2 variant (256 x 256 cluster tiles); arguments already validated by slime_launch_gemm.
+int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
+                           int num_sms, cudaStream_t stream);
 
 // Cached 2-D TMA descriptor over a row-major bf16 matrix [rows, cols] with leading dimension ld:
 // box = {64 columns (one 128-byte swizzled row), box_rows rows}, SWIZZLE_128B, zero fill out of bounds.

@@ -1,0 +1,268 @@
+// 2-CTA (cta_group::2) variant of the persistent tcgen05 GEMM:  C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).
+//
+// A cluster of two CTAs on one TPC executes UMMA 256 x 256 x 16: CTA r owns rows [r*128, r*128+128) of the
+// 256-row tile (its own A tile and its own 128 TMEM lanes x 256 accumulator columns) and stages only HALF of
+// the W tile (128 of the 256 output columns); the tensor cores of the pair read both halves.  Per SM and
+// k-block that is 16 KB (A) + 16 KB (half of W) of shared-memory traffic instead of 16 + 32 KB, and 6 pipeline
+// stages fit where the 1-CTA kernel has 4 - less shared-memory power per FLOP on a power-capped part.
+//
+//   warp 0 (both CTAs): TMA producer; loads signal the LEADER's (rank 0) full barrier (.cta_group::2 TMA)
+//   warp 1 (leader)   : issues tcgen05.mma.cta_group::2; commits multicast to both CTAs' barriers
+//   warps 2..9 (both) : epilogue of the CTA's own 128 rows (gemm_epilogue.cuh), arriving on the leader's
+//                       tmem_empty barrier
+#include "errors.h"
+#include "gemm.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;      // rows per CTA (256 per cluster tile)
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 6;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int GROUP_M = 4;        // 256-row tiles per rasterisation group
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
+constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KB: this CTA's half of the W tile
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TMEM_COLS = 2 * BLOCK_N;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0
+
+#include "gemm_epilogue.cuh"
+
+struct TileCoord {
+  int m_blk, n_blk;
+};
+SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n) {
+  const int per_group = GROUP_M * num_n;
+  const int group = t / per_group;
+  const int first_m = group * GROUP_M;
+  const int gsize = min(GROUP_M, num_m - first_m);
+  const int in = t - group * per_group;
+  TileCoord c;
+  c.m_blk = first_m + in % gsize;
+  c.n_blk = in / gsize;
+  return c;
+}
+
+SLIME_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+SLIME_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in the LEADER CTA (works from either CTA)
+SLIME_DEVINL void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+SLIME_DEVINL void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+SLIME_DEVINL void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive on the barrier at this offset in BOTH CTAs of the pair
+SLIME_DEVINL void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+SLIME_DEVINL void tmem_alloc_2sm(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+SLIME_DEVINL void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);  // 256-row tiles
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer producer's remote arrive
+      mbar_init(&empty_bar[s], 1);  // one multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * 32 * NUM_EPI_WARPS);  // epilogue threads of BOTH CTAs (leader's copy is used)
+    }
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc_2sm(tmem_holder, TMEM_COLS);
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp_idx == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const TileCoord tc = tile_coord(t, num_m, num_n);
+        const int m_row = tc.m_blk * 2 * BLOCK_M + rank * BLOCK_M;          // this CTA's 128 rows of A
+        const int n_row = tc.n_blk * BLOCK_N + rank * (BLOCK_N / 2);        // this CTA's half of the W tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);  // bytes of both CTAs land on this barrier
+          } else {
+            mbar_arrive_leader(&full_bar[stage]);
+          }
+          tma_load_2d_2sm(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row);
+          tma_load_2d_2sm(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================ MMA issuer (leader CTA only) ========================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t desc_a = make_umma_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
+          const uint64_t desc_b = make_umma_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_bf16_ss_2sm(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ============================ epilogue (both CTAs, own 128 rows) ==================
+    const int quad = warp_idx & 3;
+    const int half = (warp_idx - 2) >> 2;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      const TileCoord tc = tile_coord(t, num_m, num_n);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      epilogue_tile<BLOCK_N, EPI>(p, tmem_base + acc * BLOCK_N, tc.m_blk * 2 * BLOCK_M + rank * BLOCK_M,
+                                  tc.n_blk * BLOCK_N, quad, half, lane);
+      tcgen05_fence_before();
+      mbar_arrive_leader(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still touch this CTA's smem / TMEM
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = gemm_bf16_tn_2cta_kernel<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SLIME_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = num_m * num_n;
+  const int max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  slime_prof_begin(0, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
+  kern<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  slime_prof_end(stream);
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
+
+}  // namespace
+
+int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms,
+                           cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  SLIME_PROPAGATE(slime_get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
+  SLIME_PROPAGATE(slime_get_tmap(W, p.N, p.K, ldw, BLOCK_N / 2, &tb));
+  switch (epi) {
+    case GEMM_EPI_NONE:
+      return launch2<GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_QUICK_GELU:
+      return launch2<GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_GELU_ERF:
+      return launch2<GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_SWIGLU:
+      return launch2<GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
+    default:
+      slime_set_error("unknown GEMM epilogue %d", epi);
+      return SLIME_EINVAL;
+  }
+}

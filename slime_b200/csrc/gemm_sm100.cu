@@ -17,6 +17,7 @@
 // out projections (reference llava/model/multimodal_resampler/sampler.py:128), the mm_projector
 // MLP (reference llava/model/multimodal_projector/builder.py:53-57), and the Llama QKV / o-proj /
 // gate-up / down / lm_head projections (HF llama/modeling_llama.py:183,262-288,487).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -310,6 +311,13 @@ int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
 
 }  // namespace
 
+static int g_mode_2cta = -1;  // -1: read SLIME_GEMM_2CTA / the compile-time default on first use
+
+extern "C" int slime_gemm_set_2cta_mode(int mode) {
+  g_mode_2cta = mode;
+  return SLIME_OK;
+}
+
 int slime_get_tmap(const bf16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
   return get_tmap(ptr, rows, cols, ld, box_rows, out);
 }
@@ -339,6 +347,16 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
   const int tiles256 = num_m * ((p.N + 255) / 256);
   const bool use256 = p.N >= 256 && tiles256 >= num_sms;
   const int block_n = use256 ? 256 : 128;
+
+  // Large problems go to the 2-CTA kernel (gemm2_sm100.cu).  SLIME_GEMM_2CTA=0 disables it, =1 forces it.
+  if (g_mode_2cta < 0) {
+    const char* e = getenv("SLIME_GEMM_2CTA");
+    g_mode_2cta = (e == nullptr) ? SLIME_GEMM_2CTA_DEFAULT : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2));
+  }
+  const int mode_2cta = g_mode_2cta;
+  const int tiles2 = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+  if (mode_2cta == 1 || (mode_2cta == 2 && tiles2 >= num_sms / 2 && p.N >= 256))
+    return slime_launch_gemm_2cta(A, lda, W, ldw, p, epi, num_sms, stream);
 
   CUtensorMap ta, tb;
   SLIME_PROPAGATE(get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));

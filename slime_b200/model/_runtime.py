@@ -16,11 +16,17 @@ from ..engine import SlimeEngine
 class EngineBinding:
     def __init__(self, owner: torch.nn.Module, cfg: SlimeConfig, key_prefix: str, groups: Sequence[str]):
         self._owner = weakref.ref(owner)
-        self.cfg = cfg
+        self._cfg = cfg                   # SlimeConfig or a zero-argument callable producing one (lazy)
         self.key_prefix = key_prefix      # prepended to owner.state_dict() keys to obtain reference keys
         self.groups = tuple(groups)
         self._engine: Optional[SlimeEngine] = None
         self._stamp = None
+
+    @property
+    def cfg(self) -> SlimeConfig:
+        if callable(self._cfg):
+            self._cfg = self._cfg()
+        return self._cfg
 
     def _current_stamp(self, owner):
         # cheap change detector: (device, data_ptr, version) of every parameter

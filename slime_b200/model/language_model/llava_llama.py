@@ -121,6 +121,8 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         self.pretraining_tp = getattr(config, "pretraining_tp", 1)
         self.vocab_size = config.vocab_size
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        # one engine for the whole tree: sub-modules called on their own (tower, projector, sampler) share it
+        bind(self, EngineBinding(self, self._slime_config, "", ("vit", "rs_local", "rs_global", "proj", "llm")))
 
     # ------------------------------------------------------------------ plumbing
     def get_model(self):
@@ -152,9 +154,6 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             vt.load_model()
             vt.to(device=self.device, dtype=self.dtype)
         b = binding_of(self)
-        if b is None or b._owner() is not self:
-            b = EngineBinding(self, self._slime_config(), "", ("vit", "rs_local", "rs_global", "proj", "llm"))
-            bind(self, b)
         return b.engine(device if device is not None and device.type == "cuda" else None)
 
     # ------------------------------------------------------------------ forward (reference :57-104)

@@ -54,7 +54,7 @@ class Resampler(nn.Module):
     def _engine(self, device):
         b = binding_of(self)
         if b is None:
-            cfg = SlimeConfig(vit_hidden=self.embed_dim, hidden_size=self.llm_hidden_size,
+            cfg = SlimeConfig(vit_hidden=self.embed_dim, vit_heads=self.embed_dim // 64, hidden_size=self.llm_hidden_size,
                               mm_resampler_dim=self.num_queries if self._which == 0 else 144)
             prefix = "model.sampler.post_qformer." if self._which == 0 else "model.mm_projector.attn."
             b = EngineBinding(self, cfg, prefix, ("rs_local",) if self._which == 0 else ("rs_global",))

@@ -258,3 +258,38 @@ def test_layernorm_rmsnorm(D):
     ref = (w * normed).float()  # HF: weight * hidden_states.to(input_dtype), product in bf16
     assert (y.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 1e-6
     assert rel_l2(y, ref) < 3e-3
+
+
+@pytest.fixture
+def force_2cta():
+    L = _lib()
+    lib = L.load()
+    lib.slime_gemm_set_2cta_mode(1)
+    yield
+    lib.slime_gemm_set_2cta_mode(-1)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 512), (300, 520, 200), (577 * 5, 3072, 1024),
+                                   (1408 * 8, 6144, 4096), (1408 * 4, 4096, 14336)])
+def test_gemm_2cta_plain(force_2cta, M, N, K):
+    """cta_group::2 kernel (256 x 256 cluster tiles): same results as the fp32 reference."""
+    torch.manual_seed(M + N + K)
+    a, w, bias = rnd(M, K), rnd(N, K, scale=0.05), rnd(N)
+    out = gemm(a, w, bias=bias)
+    ref = a.float() @ w.float().t() + bias.float()
+    assert_close_bf16(out, ref, f"gemm 2cta {M}x{N}x{K}")
+
+
+def test_gemm_2cta_epilogues(force_2cta):
+    L = _lib()
+    torch.manual_seed(12)
+    a, h = rnd(1000, 1024), rnd(1000, 1024)
+    w, bias = rnd(1024, 1024, scale=0.05), rnd(1024)
+    out = gemm(a, w, bias=bias, residual=h)
+    assert_close_bf16(out, a.float() @ w.float().t() + bias.float() + h.float(), "gemm 2cta + residual")
+    gate, up = rnd(1024, 512, scale=0.05), rnd(1024, 512, scale=0.05)
+    x = rnd(900, 512)
+    inter = torch.stack([gate, up], dim=1).reshape(2048, 512).contiguous()
+    out = gemm(x, inter, epi=L.EPI_SWIGLU)
+    ref = torch.nn.functional.silu(x.float() @ gate.float().t()) * (x.float() @ up.float().t())
+    assert_close_bf16(out, ref, "gemm 2cta + swiglu")
