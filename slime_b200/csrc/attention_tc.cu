@@ -7,8 +7,8 @@
 //                  S_j = Q K_j^T       SS-MMA 128 x 128 x HD  -> TMEM S buffer (double buffered)
 //                  O  += P_j V_j       TS-MMA 128 x HD x 128  -> TMEM O, A = P_j read from TMEM,
 //                                      B = V_j in shared memory as an MN-major operand
-//   warps 2..5 : softmax + epilogue.  Thread r owns query row r of the tile (TMEM lane r): row max / row sum
-//                are thread-local, no shuffles.  exp2 with the softmax scale folded in; P_j (bf16, two per
+//   warps 2..9 : softmax + epilogue.  Two threads per query row (TMEM lane r is shared by warps w and w+4), each
+//                covering 64 of the 128 score columns; half-row max / sum are exchanged through shared memory.  exp2 with the softmax scale folded in; P_j (bf16, two per
 //                32-bit column) overwrites the first 64 columns of the S buffer it came from.
 //                O is only rescaled when the running max grows by more than 2^8 (lazy rescale), so the
 //                TMEM round trip of the accumulator is rare; the final 1/l normalisation absorbs the rest.
@@ -26,7 +26,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int SLAB_BYTES = 128 * 128;  // 128 rows x 64 bf16
-constexpr int NT = 192;
+constexpr int NT = 64 + 8 * 32;  // TMA warp + MMA warp + 8 softmax/epilogue warps
 constexpr int KV_STAGES = 2;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // in log2 units: P stays below 2^8
 
@@ -35,7 +35,7 @@ struct TcCfg {
   static constexpr int SLABS = HD / 64;
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   // >= 120 KB so that two CTAs can never share an SM (each allocates all 512 TMEM columns)
-  static constexpr int SMEM_RAW = 1024 + TILE_BYTES * (1 + 2 * KV_STAGES) + 256;
+  static constexpr int SMEM_RAW = 1024 + TILE_BYTES * (1 + 2 * KV_STAGES) + 256 + 6 * 128 * 4;
   static constexpr int SMEM_BYTES = SMEM_RAW > 120 * 1024 ? SMEM_RAW : 120 * 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;
@@ -115,6 +115,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                                  // never more than one phase behind and parity waits stay unambiguous
   uint64_t* o_free = bars + 16;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
+  float* xch = reinterpret_cast<float*>(bars + 18);  // [6][128]: per-tile half-row max (2 slots x 2 halves), item sums (2 halves)
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,11 +132,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 128);
+      mbar_init(&p_ready[s], 256);
     }
     mbar_init(&o_done[0], 1);
     mbar_init(&o_done[1], 1);
-    mbar_init(o_free, 128);
+    mbar_init(o_free, 256);
     fence_barrier_init();
   } else if (warp_idx == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
@@ -232,38 +233,41 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
     }
   } else {
-    // ================================ softmax + epilogue ==========================
+    // ================================ softmax + epilogue (8 warps) ================
+    // Two threads per query row: warps w and w+4 share TMEM lane quadrant w % 4 and split the 128 score
+    // columns (and the O columns) in halves; they exchange their half-row max (per tile) and sum (per item)
+    // through shared memory with a 64-thread named barrier.
     const int quad = warp_idx & 3;
+    const int half = (warp_idx - 2) >> 2;
     const int r_in_tile = quad * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const float scale_log2 = p.scale * 1.4426950408889634f;
+    const int pair_bar = 1 + quad;  // named barrier id (0 is __syncthreads)
     int item_cnt = 0, g = 0;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
       const Item it = decode_item<CAUSAL>(p, w, q_tiles);
       if (!it.valid) continue;
       const int row = it.t * BM + r_in_tile;  // query index inside the sequence
       float m_ref = -INFINITY;                // raw-score max the exponentials are taken against
-      float l_sum = 0.f;
+      float l_sum = 0.f;                      // sum over THIS thread's 64 columns of every tile
       for (int j = 0; j < it.n_tiles; ++j) {
         const int gj = g + j;
         const int buf = gj & 1;
-        const uint32_t s_addr = tmem_base + lane_addr + (buf ? Cfg::S_COL1 : Cfg::S_COL0);
+        const uint32_t s_base = tmem_base + lane_addr + (buf ? Cfg::S_COL1 : Cfg::S_COL0);
         mbar_wait(&s_full[buf], (gj >> 1) & 1);
         tcgen05_fence_after();
-        uint32_t sr[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sr + c * 32);
+        uint32_t sr[64];
+        tmem_ld_32x32b_x32(s_base + half * 64, sr);
+        tmem_ld_32x32b_x32(s_base + half * 64 + 32, sr + 32);
         tmem_ld_wait();
 
-        const int col_base = j * BN;
-        const bool need_mask = (col_base + BN > it.len_k) || (CAUSAL && (col_base + BN - 1 > it.t * BM + it.causal_off));
-        // 4 independent max chains: with one warp per scheduler a single 128-long dependent chain would
-        // cost 128 x the FMNMX latency
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        const int col_base = j * BN + half * 64;
+        const bool need_mask = (j * BN + BN > it.len_k) || (CAUSAL && (j * BN + BN - 1 > it.t * BM + it.causal_off));
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (one warp per scheduler)
         if (need_mask) {
           const int limit = CAUSAL ? min(it.len_k - 1, row + it.causal_off) : it.len_k - 1;  // last visible column
 #pragma unroll
-          for (int c = 0; c < 128; ++c) {
+          for (int c = 0; c < 64; ++c) {
             float v = __uint_as_float(sr[c]);
             if (col_base + c > limit) v = -INFINITY;
             sr[c] = __float_as_uint(v);
@@ -271,21 +275,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 128; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(sr[c]));
+          for (int c = 0; c < 64; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(sr[c]));
         }
-        const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const float m_half = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        xch[((j & 1) * 2 + half) * BM + r_in_tile] = m_half;
+        asm volatile("bar.sync %0, 64;\n" ::"r"(pair_bar) : "memory");
+        const float m_tile = fmaxf(m_half, xch[((j & 1) * 2 + (half ^ 1)) * BM + r_in_tile]);
 
-        // lazy rescale: only move the reference max when it grew by more than 2^8 (or on the first tile)
-        bool grow = (m_tile - m_ref) * scale_log2 > RESCALE_THRESHOLD;  // also true when m_ref == -inf and m_tile finite
+        // lazy rescale: only move the reference max when it grew by more than 2^8 (or on the first tile).
+        // Both threads of a row see the same m_tile / m_ref, so the two warps take the same branches.
+        bool grow = (m_tile - m_ref) * scale_log2 > RESCALE_THRESHOLD;
         if (m_tile == -INFINITY) grow = false;
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
-          const float alpha = grow ? exp2f((m_ref - m_tile) * scale_log2) : 1.0f;  // m_ref == -inf -> 0
+          const float alpha = grow ? fast_exp2((m_ref - m_tile) * scale_log2) : 1.0f;  // m_ref == -inf -> 0
           l_sum *= alpha;
-          mbar_wait(&o_done[(gj - 1) & 1], ((gj - 1) >> 1) & 1);  // PV_{j-1} finished: O is stable until p_ready lets PV_j go
+          mbar_wait(&o_done[(gj - 1) & 1], ((gj - 1) >> 1) & 1);  // PV_{j-1} finished: O is stable until PV_j
           tcgen05_fence_after();
-          const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
+          const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + half * (HD / 2);
 #pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
+          for (int c = 0; c < HD / 64; ++c) {
             uint32_t orow[32];
             tmem_ld_32x32b_x32(o_addr + c * 32, orow);
             tmem_ld_wait();
@@ -298,31 +306,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (grow) m_ref = m_tile;
         const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * scale_log2;
 
-        uint32_t pk[64];
+        uint32_t pk[32];
         float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
+        for (int c = 0; c < 32; ++c) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_scaled));
           const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_scaled));
           ps4[c & 3] += p0 + p1;
           pk[c] = pack_bf16x2(p0, p1);
         }
         l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-        tmem_st_32x32b_x32(s_addr, pk);
-        tmem_st_32x32b_x32(s_addr + 32, pk + 32);
+        tmem_st_32x32b_x32(s_base + half * 32, pk);  // P: 64 packed columns per row, this thread's half
         tmem_st_wait();
         tcgen05_fence_before();
         mbar_arrive(&p_ready[buf]);
       }
-      // ---- epilogue: O / l -> bf16 -> HBM (one 2*HD-byte row per thread) ----
+      // ---- epilogue: O / l -> bf16 -> HBM (each thread of the pair writes HD/2 columns of its row) ----
+      xch[(4 + half) * BM + r_in_tile] = l_sum;
+      asm volatile("bar.sync %0, 64;\n" ::"r"(pair_bar) : "memory");
+      const float l_tot = l_sum + xch[(4 + (half ^ 1)) * BM + r_in_tile];
       const int g_last = g + it.n_tiles - 1;
       mbar_wait(&o_done[g_last & 1], (g_last >> 1) & 1);
       tcgen05_fence_after();
-      const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
-      const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL;
-      bf16* orow_ptr = p.o + (it.o_row0 + row) * p.o_ld + it.head * HD;
+      const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + half * (HD / 2);
+      bf16* orow_ptr = p.o + (it.o_row0 + row) * p.o_ld + it.head * HD + half * (HD / 2);
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
+      for (int c = 0; c < HD / 64; ++c) {
         uint32_t orow[32];
         tmem_ld_32x32b_x32(o_addr + c * 32, orow);
         tmem_ld_wait();
@@ -340,6 +350,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
       tcgen05_fence_before();
       mbar_arrive(o_free);
+      // the sum slots are rewritten by the next item only after both threads passed this item's barrier and
+      // the next item's first per-tile barrier orders the max slots
       g += it.n_tiles;
       ++item_cnt;
     }

@@ -24,7 +24,7 @@ struct GemmParams {
 // 0 = 1-CTA kernel only, 1 = always the 2-CTA kernel, 2 = 2-CTA for problems that fill the GPU.
 // (the SLIME_GEMM_2CTA environment variable overrides this at run time)
 #ifndef SLIME_GEMM_2CTA_DEFAULT
-#define SLIME_GEMM_2CTA_DEFAULT 0
+#define SLIME_GEMM_2CTA_DEFAULT 2
 #endif
 
 // Returns 0 on success; negative SLIME_E* otherwise (message via slime_set_error).
