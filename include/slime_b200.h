@@ -165,6 +165,17 @@ int slime_decoder_prefill_fwd(slime_ctx* ctx, const void* embeds, const int32_t*
                               float* logits_last, void* logits_all, void* hidden_out, void* ws,
                               size_t ws_bytes, void* stream);
 
+/* ---- KV cache + decode step: the step right after the prefill in generate() (llava_llama.py:139, early-out
+ * llava_arch.py:279).  The cache is caller-owned bf16 [layers][2][batch][cache_len][kv_heads*head_dim].
+ * While a cache is attached, slime_decoder_prefill_fwd also stores K (post-RoPE) and V of every real token into it.
+ * decode: x [batch, hidden] = embeddings of the tokens to append, lens [batch] int32 (device) = tokens already cached
+ * -> logits [batch, vocab] fp32; the caller increments lens afterwards. */
+size_t slime_kv_cache_bytes(const slime_ctx* ctx, int batch, int cache_len);
+int slime_decoder_set_kv_cache(slime_ctx* ctx, void* cache, int batch, int cache_len);
+size_t slime_decoder_decode_workspace_bytes(const slime_ctx* ctx, int batch);
+int slime_decoder_decode_fwd(slime_ctx* ctx, const void* x, const int32_t* lens, int batch, float* logits, void* ws,
+                             size_t ws_bytes, void* stream);
+
 /* ---- single-op entry points (unit parity tests of the kernels through the same ABI) ---- */
 int slime_op_gemm(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
                   const void* residual, int res_ld, int res_period, const int32_t* row_map, int epilogue,

@@ -83,6 +83,10 @@ SIGNATURES = {
     "slime_splice_pad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "slime_decoder_workspace_bytes": (_sz, [_vp, _i, _i]),
     "slime_decoder_prefill_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "slime_kv_cache_bytes": (_sz, [_vp, _i, _i]),
+    "slime_decoder_set_kv_cache": (_i, [_vp, _vp, _i, _i]),
+    "slime_decoder_decode_workspace_bytes": (_sz, [_vp, _i]),
+    "slime_decoder_decode_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "slime_op_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "slime_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i64, _i64, _i64, _i, _i, _i,
                                 _i, _f, _i, _i64, _i64, _i, _vp]),

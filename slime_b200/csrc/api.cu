@@ -73,6 +73,8 @@ struct slime_ctx {
   float* rope_table = nullptr;  // [max_pos, head_dim/2] (cos, sin) fp32, owned
   int* err_flag = nullptr;      // device int, owned
   bool finalized = false;
+  bf16* kv_cache = nullptr;  // caller-owned [layers][2][kv_cache_batch][kv_cache_len][kv_heads*head_dim], or nullptr
+  int kv_cache_batch = 0, kv_cache_len = 0;
   bool has_vit = false, has_rs[2] = {false, false}, has_proj = false, has_llm = false;
   std::mutex mu;
   // resolved at finalize
@@ -284,6 +286,7 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
   bf16* act = a.get<bf16>(static_cast<size_t>(total) * I);
   int* last_rows = a.get<int>(B);
   bf16* last_h = a.get<bf16>(static_cast<size_t>(B) * H);
+  int* cache_rows = a.get<int>(total);  // packed row -> slot of the per-sequence KV cache (when one is attached)
   ARENA_CHECK(a, "decoder");
   if (a.dry || total <= 0) return SLIME_OK;
 
@@ -295,6 +298,15 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
     SLIME_PROPAGATE(gemm(c, t, H, L.qkv_w, H, total, QKV, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, qkv,
                          nullptr, QKV, s));
     SLIME_PROPAGATE(slime_launch_rope(qkv, QKV, total, d.heads, d.kv_heads, hd, pos_ids, c->rope_table, d.max_pos, s));
+    if (c->kv_cache != nullptr) {
+      // keep K (post-RoPE) and V of every real token for the decode steps that follow the prefill
+      if (l == 0) SLIME_PROPAGATE(slime_launch_cache_rows(cu, pos_ids, B, total, c->kv_cache_len, cache_rows, s));
+      const size_t plane = static_cast<size_t>(c->kv_cache_batch) * c->kv_cache_len * KD;
+      bf16* kc = c->kv_cache + (static_cast<size_t>(l) * 2 + 0) * plane;
+      bf16* vc = c->kv_cache + (static_cast<size_t>(l) * 2 + 1) * plane;
+      SLIME_PROPAGATE(slime_launch_scatter_rows(qkv + QD, QKV, kc, KD, total, KD, cache_rows, s));
+      SLIME_PROPAGATE(slime_launch_scatter_rows(qkv + QD + KD, QKV, vc, KD, total, KD, cache_rows, s));
+    }
     AttnParams ap;
     ap.q = qkv; ap.k = qkv + QD; ap.v = qkv + QD + KD; ap.o = att;
     ap.q_ld = ap.k_ld = ap.v_ld = QKV; ap.o_ld = QD;
@@ -325,6 +337,46 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
                            GEMM_EPI_NONE, logits_all, nullptr, d.vocab, s));
     }
   }
+  return SLIME_OK;
+}
+
+// One decode step for B sequences: x [B, H] = embeddings of the tokens to append; lens[b] = tokens already cached.
+int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B, float* logits, cudaStream_t s) {
+  const slime_model_desc& d = c->d;
+  const int H = d.hidden, I = d.mlp, hd = d.head_dim;
+  const int QKV = (d.heads + 2 * d.kv_heads) * hd, QD = d.heads * hd, KD = d.kv_heads * hd;
+  bf16* h = a.get<bf16>(static_cast<size_t>(B) * H);
+  bf16* t = a.get<bf16>(static_cast<size_t>(B) * H);
+  bf16* qkv = a.get<bf16>(static_cast<size_t>(B) * QKV);
+  bf16* att = a.get<bf16>(static_cast<size_t>(B) * QD);
+  bf16* act = a.get<bf16>(static_cast<size_t>(B) * I);
+  int* rows = a.get<int>(B);
+  ARENA_CHECK(a, "decode");
+  if (a.dry || B <= 0) return SLIME_OK;
+  SLIME_CHECK_CUDA(cudaMemcpyAsync(h, x_in, static_cast<size_t>(B) * H * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+  SLIME_PROPAGATE(slime_launch_append_rows(lens, B, c->kv_cache_len, rows, s));
+  const size_t plane = static_cast<size_t>(c->kv_cache_batch) * c->kv_cache_len * KD;
+  for (int l = 0; l < d.layers; ++l) {
+    const LlmLayer& L = c->llm[l];
+    bf16* kc = c->kv_cache + (static_cast<size_t>(l) * 2 + 0) * plane;
+    bf16* vc = c->kv_cache + (static_cast<size_t>(l) * 2 + 1) * plane;
+    SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.in_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
+    SLIME_PROPAGATE(gemm(c, t, H, L.qkv_w, H, B, QKV, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, qkv, nullptr,
+                         QKV, s));
+    SLIME_PROPAGATE(slime_launch_rope(qkv, QKV, B, d.heads, d.kv_heads, hd, lens, c->rope_table, d.max_pos, s));
+    SLIME_PROPAGATE(slime_launch_scatter_rows(qkv + QD, QKV, kc, KD, B, KD, rows, s));
+    SLIME_PROPAGATE(slime_launch_scatter_rows(qkv + QD + KD, QKV, vc, KD, B, KD, rows, s));
+    SLIME_PROPAGATE(slime_launch_decode_attention(qkv, QKV, kc, vc, c->kv_cache_len, lens, B, d.heads, d.kv_heads, hd,
+                                                  1.0f / sqrtf(static_cast<float>(hd)), att, QD, s));
+    SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, B, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s));
+    SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.post_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
+    SLIME_PROPAGATE(gemm(c, t, H, L.gate_up_w, H, B, 2 * I, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_SWIGLU, act,
+                         nullptr, I, s));
+    SLIME_PROPAGATE(gemm(c, act, I, L.down_w, I, B, H, I, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s));
+  }
+  SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, c->llm_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
+  SLIME_PROPAGATE(gemm(c, t, H, c->llm_lm_head, H, B, d.vocab, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, nullptr,
+                       logits, d.vocab, s));
   return SLIME_OK;
 }
 
@@ -744,6 +796,39 @@ int slime_decoder_prefill_fwd(slime_ctx* ctx, const void* embeds, const int32_t*
   return decoder_body(ctx, a, static_cast<const bf16*>(embeds), cu_seqlens, pos_ids, batch, total_rows, max_seqlen,
                       logits_last, static_cast<bf16*>(logits_all), static_cast<bf16*>(hidden_out),
                       static_cast<cudaStream_t>(stream));
+}
+
+// ---- KV cache + decode step ----
+size_t slime_kv_cache_bytes(const slime_ctx* ctx, int batch, int cache_len) {
+  if (ctx == nullptr || batch <= 0 || cache_len <= 0) return 0;
+  return static_cast<size_t>(ctx->d.layers) * 2 * batch * cache_len * ctx->d.kv_heads * ctx->d.head_dim * sizeof(bf16);
+}
+int slime_decoder_set_kv_cache(slime_ctx* ctx, void* cache, int batch, int cache_len) {
+  SLIME_REQUIRE(ctx != nullptr, "set_kv_cache: null context");
+  SLIME_REQUIRE(cache == nullptr || (batch > 0 && cache_len > 0 && cache_len <= ctx->d.max_pos),
+                "set_kv_cache: bad geometry batch=%d cache_len=%d (max_pos %d)", batch, cache_len, ctx->d.max_pos);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->kv_cache = static_cast<bf16*>(cache);
+  ctx->kv_cache_batch = cache != nullptr ? batch : 0;
+  ctx->kv_cache_len = cache != nullptr ? cache_len : 0;
+  return SLIME_OK;
+}
+size_t slime_decoder_decode_workspace_bytes(const slime_ctx* ctx, int batch) {
+  Arena a(nullptr, 0);
+  decode_body(const_cast<slime_ctx*>(ctx), a, nullptr, nullptr, batch > 0 ? batch : 1, nullptr, nullptr);
+  return a.off + 256;
+}
+int slime_decoder_decode_fwd(slime_ctx* ctx, const void* x, const int32_t* lens, int batch, float* logits, void* ws,
+                             size_t ws_bytes, void* stream) {
+  SLIME_PROPAGATE(check_ready(ctx, G_LLM));
+  SLIME_REQUIRE(x && lens && logits && ws, "decode: null pointer");
+  SLIME_REQUIRE(ctx->kv_cache != nullptr, "decode: no KV cache attached (slime_decoder_set_kv_cache)");
+  SLIME_REQUIRE(batch <= ctx->kv_cache_batch, "decode: batch %d exceeds the KV cache's %d sequences", batch,
+                ctx->kv_cache_batch);
+  if (batch <= 0) return SLIME_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Arena a(ws, ws_bytes);
+  return decode_body(ctx, a, static_cast<const bf16*>(x), lens, batch, logits, static_cast<cudaStream_t>(stream));
 }
 
 // ---- single ops ----

@@ -1,4 +1,4 @@
-// Host-side interface of the fused attention kernels (attention_fa.cu).
+// Host-side interface of the fused attention kernels (attention_tc.cu, attention_fa.cu, decode_attn.cu).
 #pragma once
 #include "common.cuh"
 
@@ -27,3 +27,15 @@ struct AttnParams {
 int slime_launch_attention(const AttnParams& p, cudaStream_t stream);
 // tcgen05 / TMEM implementation (attention_tc.cu)
 int slime_launch_attention_tc(const AttnParams& p, int num_sms, cudaStream_t stream);
+
+// ---- decode step (decode_attn.cu) ----
+// q [batch, heads*head_dim] (row stride q_ld) against the cache k/v [batch, cache_len, kv_heads*head_dim];
+// sequence b attends its first lens[b] + 1 cached positions.
+int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, const bf16* vcache, int cache_len,
+                                  const int* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
+                                  bf16* out, int out_ld, cudaStream_t stream);
+// rows[i] = sample(i) * cache_len + pos_ids[i] for the packed prefill rows (-1 when pos >= cache_len)
+int slime_launch_cache_rows(const int* cu, const int* pos_ids, int B, int total, int cache_len, int* rows,
+                            cudaStream_t stream);
+// rows[b] = b * cache_len + lens[b]
+int slime_launch_append_rows(const int* lens, int B, int cache_len, int* rows, cudaStream_t stream);

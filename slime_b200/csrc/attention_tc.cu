@@ -1,7 +1,7 @@
 // tcgen05 / TMEM flash attention forward for sm_100a (bf16 in, fp32 softmax + accumulation, bf16 out).
 //
 // One persistent CTA per SM walks a static list of work items (batch, head, 128-row query tile).
-//   warp 0     : TMA producer - Q tile once per item, K and V tiles through a 2-stage ring
+//   warp 0     : TMA producer - Q tile once per item, K and V tiles through 3/2-stage (hd 128) or 4/3-stage (hd 64) rings
 //                (64-column slabs of 128 rows, 128-byte swizzle; heads are column slices of packed rows)
 //   warp 1     : tcgen05.mma issuer (one thread) + TMEM allocator
 //                  S_j = Q K_j^T       SS-MMA 128 x 128 x HD  -> TMEM S buffer (double buffered)
@@ -27,7 +27,6 @@ constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int SLAB_BYTES = 128 * 128;  // 128 rows x 64 bf16
 constexpr int NT = 64 + 8 * 32;  // TMA warp + MMA warp + 8 softmax/epilogue warps
-constexpr int KV_STAGES = 2;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // in log2 units: P stays below 2^8
 
 template <int HD>
@@ -35,7 +34,9 @@ struct TcCfg {
   static constexpr int SLABS = HD / 64;
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
   // >= 120 KB so that two CTAs can never share an SM (each allocates all 512 TMEM columns)
-  static constexpr int SMEM_RAW = 1024 + TILE_BYTES * (1 + 2 * KV_STAGES) + 256 + 6 * 128 * 4;
+  static constexpr int NK = HD == 128 ? 3 : 4;  // K ring depth (TMA latency must be covered by ~2 tile times)
+  static constexpr int NV = HD == 128 ? 2 : 3;  // V ring depth
+  static constexpr int SMEM_RAW = 1024 + TILE_BYTES * (1 + NK + NV) + 256 + 6 * 128 * 4;
   static constexpr int SMEM_BYTES = SMEM_RAW > 120 * 1024 ? SMEM_RAW : 120 * 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;
@@ -101,21 +102,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::TILE_BYTES;
-  uint8_t* sV = sK + KV_STAGES * Cfg::TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * Cfg::TILE_BYTES);
+  constexpr int NK = Cfg::NK, NV = Cfg::NV;
+  uint8_t* sV = sK + NK * Cfg::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NV * Cfg::TILE_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;   // [2]
-  uint64_t* k_empty = bars + 4;  // [2]
-  uint64_t* v_full = bars + 6;   // [2]
-  uint64_t* v_empty = bars + 8;  // [2]
-  uint64_t* s_full = bars + 10;  // [2]
-  uint64_t* p_ready = bars + 12; // [2]
-  uint64_t* o_done = bars + 14;  // [2]: PV with global index g commits o_done[g & 1] (phase g >> 1), so a waiter is
+  uint64_t* k_full = bars + 2;    // [NK <= 4]
+  uint64_t* k_empty = bars + 6;   // [NK]
+  uint64_t* v_full = bars + 10;   // [NV <= 4]
+  uint64_t* v_empty = bars + 14;  // [NV]
+  uint64_t* s_full = bars + 18;   // [2]
+  uint64_t* p_ready = bars + 20;  // [2]
+  uint64_t* o_done = bars + 22;   // [2]: PV with global index g commits o_done[g & 1] (phase g >> 1), so a waiter is
                                  // never more than one phase behind and parity waits stay unambiguous
-  uint64_t* o_free = bars + 16;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 17);
-  float* xch = reinterpret_cast<float*>(bars + 18);  // [6][128]: per-tile half-row max (2 slots x 2 halves), item sums (2 halves)
+  uint64_t* o_free = bars + 24;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 25);
+  float* xch = reinterpret_cast<float*>(bars + 26);  // [6][128]: per-tile half-row max (2 slots x 2 halves), item sums (2 halves)
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,11 +128,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NK; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < NV; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&p_ready[s], 256);
     }
@@ -158,22 +164,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
         for (int s = 0; s < Cfg::SLABS; ++s)
           tma_load_2d(sQ + s * SLAB_BYTES, &tmap_q, q_full, q_col0 + it.head * HD + s * 64, it.q_row0 + it.t * BM);
-        for (int j = 0; j < it.n_tiles; ++j, ++g) {
-          const int st = g & 1;
-          const uint32_t ph = (g >> 1) & 1;
-          mbar_wait(&k_empty[st], ph ^ 1);
+        // K runs two tiles ahead of V: a K tile is needed one S-MMA earlier than the V tile of the same index, and
+        // the TMA latency (~1.5-2 k cycles) has to be covered by about two tile times of tensor work.
+        auto load_k = [&](int j) {
+          const int gi = g + j, st = gi % NK;
+          mbar_wait(&k_empty[st], ((gi / NK) & 1) ^ 1);
           mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
 #pragma unroll
           for (int s = 0; s < Cfg::SLABS; ++s)
             tma_load_2d(sK + st * Cfg::TILE_BYTES + s * SLAB_BYTES, &tmap_k, &k_full[st],
                         k_col0 + it.kv_head * HD + s * 64, it.k_row0 + j * BN);
-          mbar_wait(&v_empty[st], ph ^ 1);
+        };
+        auto load_v = [&](int j) {
+          const int gi = g + j, st = gi % NV;
+          mbar_wait(&v_empty[st], ((gi / NV) & 1) ^ 1);
           mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
 #pragma unroll
           for (int s = 0; s < Cfg::SLABS; ++s)
             tma_load_2d(sV + st * Cfg::TILE_BYTES + s * SLAB_BYTES, &tmap_v, &v_full[st],
                         v_col0 + it.kv_head * HD + s * 64, it.k_row0 + j * BN);
+        };
+        load_k(0);
+        if (it.n_tiles > 1) load_k(1);
+        for (int j = 0; j < it.n_tiles; ++j) {
+          if (j + 2 < it.n_tiles) load_k(j + 2);
+          load_v(j);
         }
+        g += it.n_tiles;
         ++item_cnt;
       }
     }
@@ -186,11 +203,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       int item_cnt = 0, g = 0;
 
       auto issue_s = [&](int gi, bool last_of_item) {
-        const int st = gi & 1;
-        mbar_wait(&k_full[st], (gi >> 1) & 1);
+        const int st = gi % NK;
+        mbar_wait(&k_full[st], (gi / NK) & 1);
         tcgen05_fence_after();
         const uint32_t sK_addr = smem_u32(sK + st * Cfg::TILE_BYTES);
-        const uint32_t tmem_s = tmem_base + (st ? Cfg::S_COL1 : Cfg::S_COL0);
+        const uint32_t tmem_s = tmem_base + ((gi & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
 #pragma unroll
         for (int s = 0; s < Cfg::SLABS; ++s) {
           const uint64_t dq = make_umma_desc_sw128(sQ_addr + s * SLAB_BYTES);
@@ -199,7 +216,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, (s | k) != 0 ? 1u : 0u);
         }
         umma_commit(&k_empty[st]);
-        umma_commit(&s_full[st]);
+        umma_commit(&s_full[gi & 1]);
         if (last_of_item) umma_commit(q_empty);
       };
 
@@ -211,21 +228,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         issue_s(g, it.n_tiles == 1);
         for (int j = 0; j < it.n_tiles; ++j) {
           const int gj = g + j;
-          const int st = gj & 1;
+          const int sb = gj & 1;    // S / P buffer
+          const int vs = gj % NV;   // V ring stage
           if (j + 1 < it.n_tiles) issue_s(gj + 1, j + 2 == it.n_tiles);
           if (j == 0) mbar_wait(o_free, (item_cnt & 1) ^ 1);  // epilogue of the previous item has drained O
-          mbar_wait(&p_ready[st], (gj >> 1) & 1);
-          mbar_wait(&v_full[st], (gj >> 1) & 1);
+          mbar_wait(&p_ready[sb], (gj >> 1) & 1);
+          mbar_wait(&v_full[vs], (gj / NV) & 1);
           tcgen05_fence_after();
-          const uint32_t tmem_p = tmem_base + (st ? Cfg::S_COL1 : Cfg::S_COL0);
-          const uint64_t dv = make_umma_desc_mn_sw128(smem_u32(sV + st * Cfg::TILE_BYTES), SLAB_BYTES);
+          const uint32_t tmem_p = tmem_base + (sb ? Cfg::S_COL1 : Cfg::S_COL0);
+          const uint64_t dv = make_umma_desc_mn_sw128(smem_u32(sV + vs * Cfg::TILE_BYTES), SLAB_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk) {
             // A: 16 kv positions = 8 TMEM columns of packed bf16 pairs;  B: 16 kv rows = 2048 bytes further down
             umma_bf16_ts(tmem_base + Cfg::O_COL, tmem_p + kk * 8, dv + static_cast<uint64_t>(kk * (2048 >> 4)),
                          idesc_pv, (j | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(&v_empty[st]);
+          umma_commit(&v_empty[vs]);
           umma_commit(&o_done[gj & 1]);
         }
         g += it.n_tiles;

@@ -318,6 +318,74 @@ class SlimeEngine:
         self._row_maps[key] = out
         return out
 
+    # ------------------------------------------------------------------ KV cache + decode step
+    @_locked
+    def attach_kv_cache(self, batch: int, cache_len: int) -> torch.Tensor:
+        """Allocate and attach a KV cache [layers, 2, batch, cache_len, kv_heads*head_dim]; while attached, every
+        decoder_prefill stores K (post-RoPE) / V of its sequences into it (sequence b -> cache slot b)."""
+        cfg = self.cfg
+        cache = torch.zeros(cfg.num_hidden_layers, 2, batch, cache_len, cfg.num_key_value_heads * cfg.head_dim,
+                            dtype=torch.bfloat16, device=self.device)
+        L.check(self.lib.slime_decoder_set_kv_cache(self._ctx, L.ptr(cache), batch, cache_len), "set_kv_cache")
+        self._kv_cache = cache
+        return cache
+
+    @_locked
+    def detach_kv_cache(self) -> None:
+        L.check(self.lib.slime_decoder_set_kv_cache(self._ctx, None, 0, 0), "set_kv_cache")
+        self._kv_cache = None
+
+    @_locked
+    def decode_step(self, x: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+        """One decode step: x [B, H] embeddings of the tokens to append, lens [B] int32 (device) tokens already cached
+        -> logits [B, V] fp32 (HF generation loop step after the prefill; reference llava_llama.py:139)."""
+        x = x.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        B = x.shape[0]
+        logits = torch.empty(B, self.cfg.vocab_size, dtype=torch.float32, device=self.device)
+        ws = self._workspace(self.lib.slime_decoder_decode_workspace_bytes(self._ctx, B))
+        L.check(self.lib.slime_decoder_decode_fwd(self._ctx, L.ptr(x), L.ptr(lens), B, L.ptr(logits), L.ptr(ws),
+                                                  ws.numel(), L.stream_ptr()), "decode_fwd")
+        return logits
+
+    @torch.no_grad()
+    def generate(self, pixels, input_ids, attention_mask=None, grids=None, image_sizes=None, max_new_tokens: int = 20,
+                 eos_token_ids=(), sample_fn=None) -> torch.Tensor:
+        """Prefill (with KV cache) + greedy / sampled decode.  sample_fn(logits [B,V]) -> next ids [B]; default
+        argmax.  Returns the generated ids [B, <= max_new_tokens] (like the reference with inputs_embeds)."""
+        if grids is None and image_sizes is not None and self.cfg.mm_patch_merge_type == "spatial":
+            grids = [get_anyres_image_grid_shape(sz, None, self.cfg.vit_image) for sz in image_sizes]
+        s = self.prefill_splice(pixels, input_ids, attention_mask, grids=grids, padded=False)["splice"]
+        return self.generate_packed(s["embeds"], s["cu_seqlens"], s["pos_ids"], s["lengths"], max_new_tokens,
+                                    eos_token_ids, sample_fn)
+
+    @torch.no_grad()
+    def generate_packed(self, rows, cu_seqlens, pos_ids, lengths, max_new_tokens: int = 20, eos_token_ids=(),
+                        sample_fn=None) -> torch.Tensor:
+        """Decoder prefill of packed embedding rows with the KV cache attached, then decode steps."""
+        B = len(lengths)
+        cache_len = min(self._desc.max_pos, max(lengths) + max_new_tokens + 1)
+        self.attach_kv_cache(B, cache_len)
+        try:
+            logits, _, _ = self.decoder_prefill(rows, cu_seqlens, pos_ids, lengths, want_last=True)
+            lens = torch.tensor(list(lengths), dtype=torch.int32, device=self.device)
+            table = self.weights["llm.embed"]
+            out, done = [], torch.zeros(B, dtype=torch.bool, device=self.device)
+            eos = torch.tensor(list(eos_token_ids), dtype=torch.long, device=self.device)
+            for step in range(max_new_tokens):
+                nxt = logits.argmax(-1) if sample_fn is None else sample_fn(logits)
+                out.append(nxt)
+                if eos.numel():
+                    done |= torch.isin(nxt, eos)
+                    if bool(done.all()):
+                        break
+                if step + 1 == max_new_tokens or int(lens.max()) + 1 >= cache_len:
+                    break
+                logits = self.decode_step(table[nxt], lens)
+                lens = lens + 1
+            return torch.stack(out, 1)
+        finally:
+            self.detach_kv_cache()
+
     # ------------------------------------------------------------------ module-API helpers (slime_b200/model)
     @torch.no_grad()
     def prefill_splice(self, pixels, input_ids, attention_mask=None, grids=None, labels=None, padded=True,

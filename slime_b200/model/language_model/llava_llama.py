@@ -4,9 +4,9 @@ state-dict keys (model.embed_tokens, model.layers.N.*, model.norm, lm_head, mode
 model.mm_projector.*, model.sampler.*).  The nn.Modules only HOLD the parameters; every FLOP of forward()
 runs in libslime_b200 (vision tower, adapter, router, splice, Llama prefill on packed rows).
 
-Not built (SURVEY.md section 8f "next"): the KV-cache decode step - generate() re-runs the packed prefill on the
-grown sequence for every new token (correct, O(n^2)); beam search; training (loss is provided for parity of
-the forward signature, computed from the returned logits with torch).
+generate() = packed prefill with the KV cache attached + native decode steps (slime_decoder_decode_fwd); greedy or
+temperature / top-p sampling (the token choice itself is torch plumbing).  Not built: beam search, training (loss is
+provided for parity of the forward signature, computed from the returned logits with torch).
 """
 from __future__ import annotations
 
@@ -224,46 +224,38 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         table = eng.weights["llm.embed"]
         if images is not None:
             sp = self._spliced(inputs, attention_mask, None, images, image_sizes, None, padded=False)["splice"]
-            lengths = list(sp["lengths"])
-            cu = sp["cu_seqlens"].cpu().tolist()
-            seqs = [sp["embeds"][cu[b]:cu[b + 1]] for b in range(len(lengths))]
+            rows, cu_t, pos, lengths = sp["embeds"], sp["cu_seqlens"], sp["pos_ids"], list(sp["lengths"])
         else:
             am = torch.ones_like(inputs, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
             seqs = [table[inputs[b][am[b]].to(table.device)] for b in range(inputs.shape[0])]
-        B = len(seqs)
-        out_tokens = [[] for _ in range(B)]
-        done = [False] * B
-        gen = torch.Generator(device=eng.device)
-        gen.manual_seed(int(kwargs.pop("seed", 0)))
-        for _ in range(max_new):
             lengths = [s.shape[0] for s in seqs]
             rows = torch.cat(seqs).contiguous()
             cu_t = torch.tensor([0] + list(torch.tensor(lengths).cumsum(0)), dtype=torch.int32, device=eng.device)
             pos = torch.cat([torch.arange(L) for L in lengths]).to(device=eng.device, dtype=torch.int32)
-            last, _, _ = eng.decoder_prefill(rows, cu_t, pos, lengths, want_last=True)
-            if do_sample:
-                probs = torch.softmax(last / max(temperature, 1e-5), dim=-1)
-                if top_p is not None and top_p < 1.0:
-                    sp_, si = torch.sort(probs, descending=True)
-                    keep = (torch.cumsum(sp_, -1) - sp_) < top_p
-                    sp_ = sp_ * keep
-                    probs = torch.zeros_like(probs).scatter(1, si, sp_ / sp_.sum(-1, keepdim=True))
-                nxt = torch.multinomial(probs, 1, generator=gen).squeeze(1)
-            else:
-                nxt = last.argmax(-1)
-            nxt_l = nxt.tolist()
-            for b in range(B):
-                if done[b]:
-                    continue
-                out_tokens[b].append(nxt_l[b])
-                if nxt_l[b] in eos:
-                    done[b] = True
-                seqs[b] = torch.cat([seqs[b], table[nxt[b]][None]])
-            if all(done):
-                break
-        width = max(len(t) for t in out_tokens)
+        gen = torch.Generator(device=eng.device)
+        gen.manual_seed(int(kwargs.pop("seed", 0)))
+
+        def sample(last):
+            if not do_sample:
+                return last.argmax(-1)
+            probs = torch.softmax(last / max(temperature, 1e-5), dim=-1)
+            if top_p is not None and top_p < 1.0:
+                sp_, si = torch.sort(probs, descending=True)
+                keep = (torch.cumsum(sp_, -1) - sp_) < top_p
+                sp_ = sp_ * keep
+                probs = torch.zeros_like(probs).scatter(1, si, sp_ / sp_.sum(-1, keepdim=True))
+            return torch.multinomial(probs, 1, generator=gen).squeeze(1)
+
+        # prefill with the KV cache attached, then native decode steps (slime_decoder_decode_fwd)
+        toks = eng.generate_packed(rows, cu_t, pos, lengths, max_new, tuple(eos), sample)
+        # like HF: positions after a sequence's EOS are padded
         pad = getattr(self.config, "pad_token_id", 0) or 0
-        return torch.tensor([t + [pad] * (width - len(t)) for t in out_tokens], dtype=torch.long, device=inputs.device)
+        if eos:
+            e = torch.tensor(sorted(eos), device=toks.device)
+            hit = torch.isin(toks, e)
+            after = (hit.cumsum(1) - hit.long()) > 0
+            toks = toks.masked_fill(after, pad)
+        return toks.to(inputs.device)
 
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
         images = kwargs.pop("images", None)

@@ -1,0 +1,67 @@
+"""KV-cache decode step: every decode step must reproduce the logits a fresh prefill of the grown
+sequence gives (same weights, packed rows), and the oracle's logits for the same grown sequence."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("pname", ["tiny", "small"])
+def test_decode_matches_reprefill_and_oracle(pname):
+    from oracle import slime_oracle as O
+    from slime_b200.config import preset
+    from slime_b200.engine import SlimeEngine
+    from slime_b200.synth import synth_inputs, synth_state_dict
+
+    cfg = preset(pname)
+    sd = synth_state_dict(cfg)
+    eng = SlimeEngine(cfg, 0)
+    eng.load_state_dict(sd)
+    B, n, T, steps = 3, 5, 20, 5
+    px, ids, mask = synth_inputs(cfg, B, n, T, image_pos=4, ragged=True)
+    grids = [(2, 2)] * B
+    # reference trajectory: re-run the packed prefill on the grown sequences
+    base = eng.prefill(px, ids, mask, grids=grids, keep_stages=True)
+    cu = base.cu_seqlens.cpu().tolist()
+    seqs = [base.embeds[cu[b]:cu[b + 1]].clone() for b in range(B)]
+    table = eng.weights["llm.embed"]
+    ref_logits, ref_tokens = [base.logits_last.clone()], []
+    for s in range(steps):
+        nxt = ref_logits[-1].argmax(-1)
+        ref_tokens.append(nxt)
+        seqs = [torch.cat([seqs[b], table[nxt[b]][None]]) for b in range(B)]
+        lens = [x.shape[0] for x in seqs]
+        rows = torch.cat(seqs).contiguous()
+        cu_t = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device="cuda")
+        pos = torch.cat([torch.arange(L) for L in lens]).to(device="cuda", dtype=torch.int32)
+        last, _, _ = eng.decoder_prefill(rows, cu_t, pos, lens)
+        ref_logits.append(last.clone())
+    # KV-cache trajectory (teacher-forced with the same tokens so the comparison is step by step)
+    eng.attach_kv_cache(B, 1400)
+    try:
+        res = eng.prefill(px, ids, mask, grids=grids)
+        assert torch.equal(res.logits_last, base.logits_last)
+        lens_d = torch.tensor(res.lengths, dtype=torch.int32, device="cuda")
+        for s in range(steps):
+            logits = eng.decode_step(table[ref_tokens[s]], lens_d)
+            lens_d = lens_d + 1
+            e = rel(logits, ref_logits[s + 1])
+            print(f"[{pname}] decode step {s}: rel-L2 vs re-prefill {e:.3e}")
+            assert e < 1e-2
+            assert torch.equal(logits.argmax(-1), ref_logits[s + 1].argmax(-1)) or e < 3e-3
+    finally:
+        eng.detach_kv_cache()
+    # oracle on the final grown sequence of sample 0 (fp32 CPU)
+    with torch.no_grad():
+        lg = O.llama_prefill(sd, cfg, seqs[0].float().cpu()[None], [seqs[0].shape[0]])[0]
+    assert rel(ref_logits[-1][0], lg[-1]) < 1.5e-2
+    # public generate(): greedy tokens equal the re-prefill trajectory
+    out = eng.generate(px, ids, mask, grids=grids, max_new_tokens=steps)
+    assert out.shape == (B, steps)
+    assert torch.equal(out, torch.stack(ref_tokens, 1))
