@@ -397,10 +397,18 @@ def main():
     fl = algorithmic_flops(cfg, args.crops * B, lengths, (args.crops - 1) * B * cfg.mm_resampler_dim)
     gemm_tf = pwork[0] / (pms[0] / 1e3) / 1e12 if pms[0] > 0 else 0.0
     step_ms = ms / args.steps
+    traffic, traffic_note = None, None
+    try:  # DRAM bytes per launch of the dominant GEMM from the committed ncu --set full capture (tools/ncu_summary.py)
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tr = json.load(f)["gemm"]
+        traffic, traffic_note = tr["dram_bytes_per_launch"], f"mean over {tr['launches']} captured launches, {tr['source']}"
+    except Exception:
+        pass
     roofline = {
-        "kernel": "gemm_bf16_tn_kernel (tcgen05.mma 128xBNx16 + TMA, slime_b200/csrc/gemm_sm100.cu)",
+        "kernel": "gemm_bf16_tn_2cta_kernel / gemm_bf16_tn_kernel (tcgen05.mma cta_group::2 256x256x16 resp. 128xBNx16, TMA; "
+                  "slime_b200/csrc/gemm2_sm100.cu, gemm_sm100.cu) - every dense contraction of the path",
         "bound": "tensor", "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-        "frac": gemm_tf / peaks["tf_sustained"], "traffic": None,
+        "frac": gemm_tf / peaks["tf_sustained"], "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
         "launches_per_step": pl[0] / args.steps, "gemm_ms_per_step": pms[0] / args.steps,
         "gemm_share_of_step": (pms[0] / args.steps) / step_ms,

@@ -91,7 +91,7 @@ struct slime_ctx {
 
 namespace {
 
-constexpr int VIT_CHUNK_CROPS = 64;  // crops per pass through the ViT (bounds the workspace)
+constexpr int VIT_CHUNK_CROPS = 128;  // crops per pass through the ViT (bounds the workspace to ~1.6 GB)
 
 int find_weight(slime_ctx* c, const std::string& name, int64_t rows, int64_t cols, const bf16** out) {
   auto it = c->w.find(name);
