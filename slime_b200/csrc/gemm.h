@@ -34,6 +34,9 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
 int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                            int num_sms, cudaStream_t stream);
 
+// m-tiles per rasterisation group for a problem with reduction length K (see gemm_sm100.cu)
+int slime_gemm_group_m(int K, int tile_rows);
+
 // Cached 2-D TMA descriptor over a row-major bf16 matrix [rows, cols] with leading dimension ld:
 // box = {64 columns (one 128-byte swizzled row), box_rows rows}, SWIZZLE_128B, zero fill out of bounds.
 int slime_get_tmap(const bf16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out);

@@ -22,7 +22,6 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 6;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr int GROUP_M = 4;        // 256-row tiles per rasterisation group
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KB: this CTA's half of the W tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -35,11 +34,11 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a sha
 struct TileCoord {
   int m_blk, n_blk;
 };
-SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n) {
-  const int per_group = GROUP_M * num_n;
+SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
+  const int per_group = group_m * num_n;
   const int group = t / per_group;
-  const int first_m = group * GROUP_M;
-  const int gsize = min(GROUP_M, num_m - first_m);
+  const int first_m = group * group_m;
+  const int gsize = min(group_m, num_m - first_m);
   const int in = t - group * per_group;
   TileCoord c;
   c.m_blk = first_m + in % gsize;
@@ -100,7 +99,7 @@ SLIME_DEVINL void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmParams p) {
+                         const GemmParams p, const int group_m) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
@@ -149,7 +148,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const TileCoord tc = tile_coord(t, num_m, num_n);
+        const TileCoord tc = tile_coord(t, num_m, num_n, group_m);
         const int m_row = tc.m_blk * 2 * BLOCK_M + rank * BLOCK_M;          // this CTA's 128 rows of A
         const int n_row = tc.n_blk * BLOCK_N + rank * (BLOCK_N / 2);        // this CTA's half of the W tile
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -205,7 +204,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int half = (warp_idx - 2) >> 2;
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-      const TileCoord tc = tile_coord(t, num_m, num_n);
+      const TileCoord tc = tile_coord(t, num_m, num_n, group_m);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -239,7 +238,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, i
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   slime_prof_begin(0, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-  kern<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, slime_gemm_group_m(p.K, 2 * BLOCK_M));
   slime_prof_end(stream);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;

@@ -31,7 +31,6 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // TMA warp + MMA warp + 8 epilogue warps
-constexpr int GROUP_M = 8;  // m-blocks per rasterisation group (L2 reuse of the W tiles)
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -48,11 +47,11 @@ struct TileCoord {
   int m_blk, n_blk;
 };
 
-SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n) {
-  const int per_group = GROUP_M * num_n;
+SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
+  const int per_group = group_m * num_n;
   const int group = t / per_group;
-  const int first_m = group * GROUP_M;
-  const int gsize = min(GROUP_M, num_m - first_m);
+  const int first_m = group * group_m;
+  const int gsize = min(group_m, num_m - first_m);
   const int in = t - group * per_group;
   TileCoord c;
   c.m_blk = first_m + in % gsize;
@@ -65,7 +64,7 @@ SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n) {
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p, const int group_m) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -114,7 +113,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(t, num_m, num_n);
+        const TileCoord tc = tile_coord(t, num_m, num_n, group_m);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -167,7 +166,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int half = (warp_idx - 2) >> 2;   // warps 2..5 take the low half of the columns, 6..9 the high half
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const TileCoord tc = tile_coord(t, num_m, num_n);
+      const TileCoord tc = tile_coord(t, num_m, num_n, group_m);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -285,7 +284,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
   slime_prof_begin(0, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p, slime_gemm_group_m(p.K, BLOCK_M));
   slime_prof_end(stream);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
@@ -310,6 +309,22 @@ int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
 }
 
 }  // namespace
+
+// Rasterisation group: consecutive tiles sweep `group` m-tiles before moving to the next n-tile, so one group's A
+// panel (group * tile_rows x K) stays L2-resident while the whole W matrix streams past it once.  The panel is
+// sized to ~32 MB of the 126 MB L2; a bigger group means fewer DRAM passes over W (SLIME_GEMM_GROUP_ROWS overrides).
+int slime_gemm_group_m(int K, int tile_rows) {
+  static long long env_rows = -1;
+  if (env_rows < 0) {
+    const char* e = getenv("SLIME_GEMM_GROUP_ROWS");
+    env_rows = e != nullptr ? atoll(e) : 0;
+  }
+  long long rows = env_rows > 0 ? env_rows : (32ll << 20) / (2ll * K);
+  long long g = rows / tile_rows;
+  if (g < 1) g = 1;
+  if (g > 64) g = 64;
+  return static_cast<int>(g);
+}
 
 static int g_mode_2cta = -1;  // -1: read SLIME_GEMM_2CTA / the compile-time default on first use
 
