@@ -60,11 +60,19 @@ struct Item {
 template <bool CAUSAL>
 SLIME_DEVINL Item decode_item(const AttnParams& p, int w, int q_tiles) {
   Item it;
-  it.head = w % p.num_heads;
-  const int rest = w / p.num_heads;
-  it.b = rest % p.batch;
-  const int ti = rest / p.batch;
-  it.t = CAUSAL ? (q_tiles - 1 - ti) : ti;  // heavy (late) causal tiles first
+  if (CAUSAL) {
+    // heavy (late) query tiles first for load balance; the q heads of one GQA group are adjacent (shared K/V in L2)
+    it.head = w % p.num_heads;
+    const int rest = w / p.num_heads;
+    it.b = rest % p.batch;
+    it.t = q_tiles - 1 - rest / p.batch;
+  } else {
+    // all query tiles of one (sequence, head) are adjacent, so their common K/V stream is read from DRAM once
+    it.t = w % q_tiles;
+    const int rest = w / q_tiles;
+    it.head = rest % p.num_heads;
+    it.b = rest / p.num_heads;
+  }
   it.kv_head = it.head / (p.num_heads / p.num_kv_heads);
   if (p.cu_q != nullptr) {
     it.q_row0 = p.cu_q[it.b];
