@@ -196,6 +196,8 @@ int slime_op_rope(slime_ctx* ctx, void* qkv, int ld, int rows, const int32_t* po
 /* GEMM kernel selection: 0 = 1-CTA kernel only, 1 = force the 2-CTA (cta_group::2) kernel, 2 = 2-CTA for problems
  * that fill the GPU, -1 = back to the default (SLIME_GEMM_2CTA environment variable / build default). */
 int slime_gemm_set_2cta_mode(int mode);
+/* debug: CTA 0 of the tcgen05 attention kernel stamps clock64() of its first 64 tiles into buf [64][16] (NULL = off) */
+int slime_attention_set_trace(long long* buf);
 long long slime_launch_count(void);
 int slime_profile_enable(int on);
 int slime_profile_collect(double* ms3, double* work3, long long* launches3);

@@ -94,6 +94,7 @@ SIGNATURES = {
     "slime_op_rmsnorm": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
     "slime_op_rope": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "slime_gemm_set_2cta_mode": (_i, [_i]),
+    "slime_attention_set_trace": (_i, [_vp]),
     "slime_launch_count": (C.c_longlong, []),
     "slime_profile_enable": (_i, [_i]),
     "slime_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

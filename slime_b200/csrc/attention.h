@@ -22,6 +22,7 @@ struct AttnParams {
   long long total_q_rows = 0;  // rows of the q matrix (needed for the TMA map when cu_q != nullptr; 0 = derive)
   long long total_k_rows = 0;  // rows of the k / v matrices (same)
   int impl = 0;                // 0 = default (tcgen05), 1 = mma.sync flash kernel, 2 = tcgen05
+  long long* trace = nullptr;  // debug: CTA 0 writes clock64() stamps of its first 64 tiles here ([64][16])
 };
 
 int slime_launch_attention(const AttnParams& p, cudaStream_t stream);

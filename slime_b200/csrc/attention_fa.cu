@@ -303,7 +303,15 @@ int launch(const AttnParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-int slime_launch_attention(const AttnParams& p, cudaStream_t stream) {
+static long long* g_attn_trace = nullptr;
+extern "C" int slime_attention_set_trace(long long* buf) {
+  g_attn_trace = buf;
+  return SLIME_OK;
+}
+
+int slime_launch_attention(const AttnParams& p_in, cudaStream_t stream) {
+  AttnParams p = p_in;
+  p.trace = g_attn_trace;
   SLIME_REQUIRE(p.q && p.k && p.v && p.o, "attention: null tensor");
   SLIME_REQUIRE(p.head_dim == 64 || p.head_dim == 128, "attention: head_dim %d unsupported", p.head_dim);
   SLIME_REQUIRE(p.num_kv_heads > 0 && p.num_heads % p.num_kv_heads == 0, "attention: bad GQA heads %d/%d",

@@ -240,9 +240,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           const int vs = gj % NV;   // V ring stage
           if (j + 1 < it.n_tiles) issue_s(gj + 1, j + 2 == it.n_tiles);
           if (j == 0) mbar_wait(o_free, (item_cnt & 1) ^ 1);  // epilogue of the previous item has drained O
+          const bool tr = p.trace != nullptr && blockIdx.x == 0 && gj < 64;
+          if (tr) p.trace[gj * 16 + 8] = clock64();
           mbar_wait(&p_ready[sb], (gj >> 1) & 1);
+          if (tr) p.trace[gj * 16 + 9] = clock64();
           mbar_wait(&v_full[vs], (gj / NV) & 1);
           tcgen05_fence_after();
+          if (tr) p.trace[gj * 16 + 10] = clock64();
           const uint32_t tmem_p = tmem_base + (sb ? Cfg::S_COL1 : Cfg::S_COL0);
           const uint64_t dv = make_umma_desc_mn_sw128(smem_u32(sV + vs * Cfg::TILE_BYTES), SLAB_BYTES);
 #pragma unroll
@@ -253,6 +257,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           umma_commit(&v_empty[vs]);
           umma_commit(&o_done[gj & 1]);
+          if (tr) p.trace[gj * 16 + 11] = clock64();
         }
         g += it.n_tiles;
         ++item_cnt;
@@ -280,12 +285,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int gj = g + j;
         const int buf = gj & 1;
         const uint32_t s_base = tmem_base + lane_addr + (buf ? Cfg::S_COL1 : Cfg::S_COL0);
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp_idx == 2 && lane == 0 && gj < 64;
+        if (tr) p.trace[gj * 16 + 0] = clock64();
         mbar_wait(&s_full[buf], (gj >> 1) & 1);
         tcgen05_fence_after();
+        if (tr) p.trace[gj * 16 + 1] = clock64();
         uint32_t sr[64];
         tmem_ld_32x32b_x32(s_base + half * 64, sr);
         tmem_ld_32x32b_x32(s_base + half * 64 + 32, sr + 32);
         tmem_ld_wait();
+        if (tr) p.trace[gj * 16 + 2] = clock64();
 
         const int col_base = j * BN + half * 64;
         const bool need_mask = (j * BN + BN > it.len_k) || (CAUSAL && (j * BN + BN - 1 > it.t * BM + it.causal_off));
@@ -307,6 +316,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         xch[((j & 1) * 2 + half) * BM + r_in_tile] = m_half;
         asm volatile("bar.sync %0, 64;\n" ::"r"(pair_bar) : "memory");
         const float m_tile = fmaxf(m_half, xch[((j & 1) * 2 + (half ^ 1)) * BM + r_in_tile]);
+        if (tr) p.trace[gj * 16 + 3] = clock64();
 
         // lazy rescale: only move the reference max when it grew by more than 2^8 (or on the first tile).
         // Both threads of a row see the same m_tile / m_ref, so the two warps take the same branches.
@@ -342,9 +352,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           pk[c] = pack_bf16x2(p0, p1);
         }
         l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+        if (tr) p.trace[gj * 16 + 4] = clock64();
         tmem_st_32x32b_x32(s_base + half * 32, pk);  // P: 64 packed columns per row, this thread's half
         tmem_st_wait();
         tcgen05_fence_before();
+        if (tr) p.trace[gj * 16 + 5] = clock64();
         mbar_arrive(&p_ready[buf]);
       }
       // ---- epilogue: O / l -> bf16 -> HBM (each thread of the pair writes HD/2 columns of its row) ----
