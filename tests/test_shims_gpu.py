@@ -117,3 +117,19 @@ def test_generate_and_encode_images(setup):
     # greedy first token == argmax of the prefill logits
     fast = model._engine().prefill(px[:1], ids[:1], mask[:1], grids=[(2, 2)])
     assert int(toks[0, 0]) == int(fast.logits_last[0].argmax())
+
+
+def test_images_mask_padding_is_ignored(setup):
+    """The training collator pads the crop stack and passes images_mask (reference train.py:913-926,
+    llava_arch.py:228-231,299-302): padded crops must not change the result."""
+    cfg, model, sd, px, ids, mask, ora, gold = setup
+    B = px.shape[0]
+    pad = torch.zeros(B, 2, *px.shape[2:])
+    px_pad = torch.cat([px, pad], 1).cuda().to(torch.bfloat16)
+    images_mask = torch.cat([torch.ones(B, px.shape[1]), torch.zeros(B, 2)], 1).bool().cuda()
+    a = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=px.cuda().to(torch.bfloat16),
+              image_sizes=[(672, 672)] * B)
+    b = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=px_pad, images_mask=images_mask,
+              image_sizes=[(672, 672)] * B)
+    assert a.logits.shape == b.logits.shape
+    assert torch.equal(a.logits, b.logits)
