@@ -328,12 +328,13 @@ int slime_launch_attention(const AttnParams& p_in, cudaStream_t stream) {
   static int num_sms = 0;
   if (env_impl < 0) {
     const char* e = getenv("SLIME_ATTN_IMPL");
-    env_impl = (e != nullptr && (e[0] == 'f' || e[0] == '1')) ? 1 : 2;
+    env_impl = (e == nullptr) ? SLIME_ATTN_DEFAULT_IMPL : ((e[0] == 'f' || e[0] == '1') ? 1 : ((e[0] == 'p' || e[0] == '3') ? 3 : 2));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int impl = p.impl != 0 ? p.impl : env_impl;
+  if (impl == 3) return slime_launch_attention_tc2(p, num_sms, stream);
   if (impl == 2) return slime_launch_attention_tc(p, num_sms, stream);
   if (p.head_dim == 64) {
     return p.causal ? launch<64, true>(p, stream) : launch<64, false>(p, stream);
