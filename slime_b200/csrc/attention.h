@@ -3,7 +3,7 @@
 #include "common.cuh"
 
 // default implementation when neither AttnParams::impl nor SLIME_ATTN_IMPL selects one:
-// 1 = mma.sync kernel, 2 = tcgen05 single-tile kernel, 3 = tcgen05 ping-pong kernel
+// 1 = mma.sync kernel, 2 = tcgen05 kernel
 #ifndef SLIME_ATTN_DEFAULT_IMPL
 #define SLIME_ATTN_DEFAULT_IMPL 2
 #endif
@@ -34,8 +34,6 @@ struct AttnParams {
 int slime_launch_attention(const AttnParams& p, cudaStream_t stream);
 // tcgen05 / TMEM implementation (attention_tc.cu)
 int slime_launch_attention_tc(const AttnParams& p, int num_sms, cudaStream_t stream);
-// tcgen05 / TMEM ping-pong implementation: two query tiles per CTA (attention_tc2.cu); impl == 3
-int slime_launch_attention_tc2(const AttnParams& p, int num_sms, cudaStream_t stream);
 
 // ---- decode step (decode_attn.cu) ----
 // q [batch, heads*head_dim] (row stride q_ld) against the cache k/v [batch, cache_len, kv_heads*head_dim];

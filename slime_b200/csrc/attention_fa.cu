@@ -334,7 +334,6 @@ int slime_launch_attention(const AttnParams& p_in, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int impl = p.impl != 0 ? p.impl : env_impl;
-  if (impl == 3) return slime_launch_attention_tc2(p, num_sms, stream);
   if (impl == 2) return slime_launch_attention_tc(p, num_sms, stream);
   if (p.head_dim == 64) {
     return p.causal ? launch<64, true>(p, stream) : launch<64, false>(p, stream);

@@ -178,7 +178,7 @@ def ref_attention(q, k, v, scale, causal):
     return torch.softmax(s, dim=-1) @ v
 
 
-IMPLS = [pytest.param(3, id="tcgen05_pingpong"), pytest.param(2, id="tcgen05"), pytest.param(1, id="mma_sync")]
+IMPLS = [pytest.param(2, id="tcgen05"), pytest.param(1, id="mma_sync")]
 
 
 @pytest.mark.parametrize("impl", IMPLS)

@@ -18,7 +18,7 @@ def attn(q, k, v, o, impl, **kw):
     torch.cuda.synchronize()
 
 
-def simple_case(d, Sq, Sk, causal=0, impl=3):
+def simple_case(d, Sq, Sk, causal=0, impl=2):
     """single head, single batch; block-wise error report."""
     torch.manual_seed(0)
     q = torch.randn(Sq, d, device="cuda").to(torch.bfloat16)
@@ -70,7 +70,7 @@ if __name__ == "__main__":
     o = torch.empty(B * L_, h * d, device="cuda", dtype=torch.bfloat16)
     cu = torch.arange(0, (B + 1) * L_, L_, device="cuda", dtype=torch.int32)
     fl = 4 * L_ * L_ * d * h * B * 0.5
-    for impl in (1, 2, 3):
+    for impl in (1, 2):
         bench(f"decoder causal impl={impl}", lambda: attn(qkv, qkv[:, h * d:], qkv[:, (h + kvh) * d:], o, impl, q_ld=W, k_ld=W,
               v_ld=W, o_ld=h * d, cu_q=cu, cu_k=cu, seqlen_q=L_, seqlen_k=L_, batch=B, heads=h, kv_heads=kvh, head_dim=d,
               scale=d ** -0.5, causal=1, total_q_rows=B * L_, total_k_rows=B * L_), fl)
@@ -80,7 +80,7 @@ if __name__ == "__main__":
     qkv = torch.randn(B * S, 3 * D, device="cuda").to(torch.bfloat16)
     o = torch.empty(B * S, D, device="cuda", dtype=torch.bfloat16)
     fl = 4 * S * S * d * h * B
-    for impl in (1, 2, 3):
+    for impl in (1, 2):
         bench(f"vit impl={impl}", lambda: attn(qkv, qkv[:, D:], qkv[:, 2 * D:], o, impl, q_ld=3 * D, k_ld=3 * D, v_ld=3 * D, o_ld=D,
               seqlen_q=S, seqlen_k=S, q_batch_rows=S, k_batch_rows=S, o_batch_rows=S, batch=B, heads=h, kv_heads=h,
               head_dim=d, scale=d ** -0.5), fl)
