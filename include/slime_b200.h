@@ -176,6 +176,32 @@ size_t slime_decoder_decode_workspace_bytes(const slime_ctx* ctx, int batch);
 int slime_decoder_decode_fwd(slime_ctx* ctx, const void* x, const int32_t* lens, int batch, float* logits, void* ws,
                              size_t ws_bytes, void* stream);
 
+/* ---- image pre-processing: process_images / process_anyres_image + CLIPImageProcessor.preprocess
+ * (llava/mm_utils.py:99-153,177-210,231-259), bit-exact with Pillow's bicubic `Image.resize`.
+ * One job = one resize of one image placed on a canvas that is then cut into crop x crop tiles:
+ *   source  : RGB bytes [src_h, src_w, 3] at src + src_offset, seen through a padded "virtual" source of
+ *             virt_w x virt_h with the image at (virt_x, virt_y) and `fill` elsewhere (expand2square; no padding:
+ *             virt = src, offsets 0)
+ *   resize  : virtual source -> out_w x out_h (antialiased bicubic, 8-bit intermediate, as PIL)
+ *   canvas  : canvas_w x canvas_h (multiples of crop), black, resized image pasted at (paste_x, paste_y) - negative
+ *             offsets centre-crop; its tiles, row-major, are crops first_crop, first_crop+1, ... of `out`
+ *   out     : [n_crops, 3, crop, crop] in out_dtype (0 bf16, 1 fp32, 2 fp16), value = lut[c][byte]
+ * `jobs` and `lut` ([3][256] floats: the processor's rescale + normalise of every byte value) are HOST arrays;
+ * src / out / ws are device pointers.  Needs no slime_ctx (no weights). */
+typedef struct slime_resize_job {
+  int64_t src_offset;
+  int32_t src_w, src_h;
+  int32_t virt_w, virt_h, virt_x, virt_y;
+  int32_t out_w, out_h;
+  int32_t canvas_w, canvas_h;
+  int32_t paste_x, paste_y;
+  int32_t first_crop;
+  uint8_t fill[4];
+} slime_resize_job;
+size_t slime_preprocess_workspace_bytes(const slime_resize_job* jobs, int n_jobs);
+int slime_preprocess_fwd(const uint8_t* src, const slime_resize_job* jobs, int n_jobs, int crop, const float* lut,
+                         void* out, int out_dtype, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- single-op entry points (unit parity tests of the kernels through the same ABI) ---- */
 int slime_op_gemm(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
                   const void* residual, int res_ld, int res_period, const int32_t* row_map, int epilogue,

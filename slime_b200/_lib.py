@@ -54,6 +54,21 @@ class ModelDesc(C.Structure):
     ]
 
 
+class ResizeJob(C.Structure):
+    """Mirror of `slime_resize_job` (include/slime_b200.h)."""
+
+    _fields_ = [
+        ("src_offset", C.c_int64),
+        ("src_w", C.c_int32), ("src_h", C.c_int32),
+        ("virt_w", C.c_int32), ("virt_h", C.c_int32), ("virt_x", C.c_int32), ("virt_y", C.c_int32),
+        ("out_w", C.c_int32), ("out_h", C.c_int32),
+        ("canvas_w", C.c_int32), ("canvas_h", C.c_int32),
+        ("paste_x", C.c_int32), ("paste_y", C.c_int32),
+        ("first_crop", C.c_int32),
+        ("fill", C.c_uint8 * 4),
+    ]
+
+
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); every symbol declared in include/slime_b200.h
@@ -87,6 +102,8 @@ SIGNATURES = {
     "slime_decoder_set_kv_cache": (_i, [_vp, _vp, _i, _i]),
     "slime_decoder_decode_workspace_bytes": (_sz, [_vp, _i]),
     "slime_decoder_decode_fwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "slime_preprocess_workspace_bytes": (_sz, [_vp, _i]),
+    "slime_preprocess_fwd": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _sz, _vp]),
     "slime_op_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "slime_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i64, _i64, _i64, _i, _i, _i,
                                 _i, _f, _i, _i64, _i64, _i, _vp]),

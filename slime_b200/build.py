@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-ffp-contract=off",  # host double math of preprocess.cu must round like Pillow's C code
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
     "-I", str(REPO / "include"),
