@@ -76,6 +76,9 @@ typedef struct slime_model_desc {
 } slime_model_desc;
 
 int slime_version(void);
+/* 16-bit element type this build computes in: 0 = bfloat16 (libslime_b200.so), 2 = IEEE half (libslime_b200_fp16.so,
+ * the same sources compiled with -DSLIME_FP16).  Every "bf16" tensor in this header is of that type. */
+int slime_elem_dtype(void);
 const char* slime_last_error(void);
 
 int slime_ctx_create(slime_ctx** out, int device, const slime_model_desc* desc);

@@ -12,6 +12,28 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libslime_b200.so"
+# element type -> build of the library (same sources, -DSLIME_FP16 for half; slime_b200/build.py)
+LIB_PATHS = {"bf16": LIB_PATH, "fp16": _PKG / "libslime_b200_fp16.so"}
+ELEM_DTYPE_CODE = {"bf16": 0, "fp16": 2}
+
+
+def variant_of(dtype) -> str:
+    """'bf16' / 'fp16' from a torch dtype or a string (None = bf16)."""
+    if dtype is None:
+        return "bf16"
+    name = str(dtype).replace("torch.", "")
+    if name in ("bf16", "bfloat16"):
+        return "bf16"
+    if name in ("fp16", "float16", "half"):
+        return "fp16"
+    raise ValueError(f"slime_b200 computes in bfloat16 or float16, not {dtype}")
+
+
+def torch_dtype(variant: str):
+    import torch
+
+    return torch.float16 if variant == "fp16" else torch.bfloat16
+
 
 SLIME_FLAG_LEFT_PAD = 1
 SLIME_FLAG_USE_GLOBAL_ONLY = 2
@@ -74,6 +96,7 @@ _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 # name -> (restype, argtypes); every symbol declared in include/slime_b200.h
 SIGNATURES = {
     "slime_version": (_i, []),
+    "slime_elem_dtype": (_i, []),
     "slime_last_error": (C.c_char_p, []),
     "slime_ctx_create": (_i, [C.POINTER(_vp), _i, C.POINTER(ModelDesc)]),
     "slime_ctx_destroy": (None, [_vp]),
@@ -117,36 +140,44 @@ SIGNATURES = {
     "slime_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }
 
-_lib = None
+_libs = {}
 
 
-def load() -> C.CDLL:
-    """dlopen the library and bind every declared symbol (raises if anything is missing)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
+def load(dtype=None) -> C.CDLL:
+    """dlopen the build of the library for `dtype` (default bfloat16) and bind every declared symbol
+    (raises if anything is missing)."""
+    variant = variant_of(dtype)
+    if variant in _libs:
+        return _libs[variant]
+    path = LIB_PATHS[variant]
+    if not path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m slime_b200.build` "
+            f"{path} is missing: build it with `python -m slime_b200.build` "
             "(slime_b200 has no PyTorch/CPU fallback path)")
-    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
+    lib = C.CDLL(str(path))  # RTLD_LOCAL: the two builds export the same names and must not see each other
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
     if lib.slime_version() != 1:
-        raise RuntimeError(f"libslime_b200 ABI version {lib.slime_version()} != 1")
-    _lib = lib
+        raise RuntimeError(f"{path.name} ABI version {lib.slime_version()} != 1")
+    if lib.slime_elem_dtype() != ELEM_DTYPE_CODE[variant]:
+        raise RuntimeError(f"{path.name} was built for element type code {lib.slime_elem_dtype()}")
+    _libs[variant] = lib
     return lib
 
 
-def last_error() -> str:
-    return load().slime_last_error().decode("utf-8", "replace")
+def last_error(lib=None) -> str:
+    """The message of the last failing call on this thread.  Each build keeps its own; without `lib` the
+    non-empty one is returned."""
+    libs = [lib] if lib is not None else list(_libs.values()) or [load()]
+    msgs = [l.slime_last_error().decode("utf-8", "replace") for l in libs]
+    return next((m for m in msgs if m), "")
 
 
-def check(rc: int, what: str = "") -> None:
+def check(rc: int, what: str = "", lib=None) -> None:
     if rc != 0:
-        raise RuntimeError(f"slime_b200 {what} failed (code {rc}): {last_error()}")
+        raise RuntimeError(f"slime_b200 {what} failed (code {rc}): {last_error(lib)}")
 
 
 def ptr(t) -> C.c_void_p:

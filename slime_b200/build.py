@@ -45,38 +45,49 @@ def _needs_rebuild(target: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def _compile_one(src: Path, headers: list[Path], verbose: bool) -> Path:
-    obj = BUILD_DIR / (src.stem + ".o")
+def _compile_one(src: Path, headers: list[Path], verbose: bool, variant: str) -> Path:
+    obj_dir = BUILD_DIR / variant
+    obj = obj_dir / (src.stem + ".o")
     if _needs_rebuild(obj, [src] + headers):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        extra = ["-DSLIME_FP16"] if variant == "fp16" else []
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
-        log = BUILD_DIR / (src.stem + ".log")
+        log = obj_dir / (src.stem + ".log")
         log.write_text(res.stdout + res.stderr)
         if res.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
+            raise RuntimeError(f"nvcc failed for {src.name} ({variant}):\n{res.stdout}\n{res.stderr}")
         if verbose:
-            print(f"[slime_b200.build] compiled {src.name}")
+            print(f"[slime_b200.build] compiled {src.name} ({variant})")
     return obj
 
 
+# element type of the build -> library.  Same sources; -DSLIME_FP16 switches the 16-bit element type (common.cuh).
+VARIANTS = {"bf16": LIB_PATH, "fp16": PKG_DIR / "libslime_b200_fp16.so"}
+
+
 def build(verbose: bool = False, force: bool = False) -> Path:
-    """Compile every .cu under csrc/ for sm_100a and link libslime_b200.so in-tree."""
-    BUILD_DIR.mkdir(parents=True, exist_ok=True)
+    """Compile every .cu under csrc/ for sm_100a and link libslime_b200.so (+ the fp16 build) in-tree."""
     srcs = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((REPO / "include").glob("*.h"))
-    if force:
-        for o in BUILD_DIR.glob("*.o"):
-            o.unlink()
+    for variant in VARIANTS:
+        (BUILD_DIR / variant).mkdir(parents=True, exist_ok=True)
+        if force:
+            for o in (BUILD_DIR / variant).glob("*.o"):
+                o.unlink()
+    jobs = [(s, v) for v in VARIANTS for s in srcs]
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(lambda s: _compile_one(s, headers, verbose), srcs))
-    if _needs_rebuild(LIB_PATH, objs):
-        cmd = [_nvcc(), "-shared", "-o", str(LIB_PATH), *map(str, objs),
-               "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-        if verbose:
-            print(f"[slime_b200.build] linked {LIB_PATH}")
+        objs = list(ex.map(lambda sv: _compile_one(sv[0], headers, verbose, sv[1]), jobs))
+    for variant, lib_path in VARIANTS.items():
+        vobjs = [o for o, (_, v) in zip(objs, jobs) if v == variant]
+        if _needs_rebuild(lib_path, vobjs):
+            # -Bsymbolic: both libraries export the same names; each must bind its internal calls to itself
+            cmd = [_nvcc(), "-shared", "-o", str(lib_path), *map(str, vobjs),
+                   "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic"]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+            if verbose:
+                print(f"[slime_b200.build] linked {lib_path}")
     return LIB_PATH
 
 

@@ -433,6 +433,7 @@ int check_ready(slime_ctx* c, int groups) {
 extern "C" {
 
 int slime_version(void) { return SLIME_ABI_VERSION; }
+int slime_elem_dtype(void) { return SLIME_ELEM_DTYPE; }
 const char* slime_last_error(void) { return slime_get_error(); }
 
 int slime_ctx_create(slime_ctx** out, int device, const slime_model_desc* desc) {

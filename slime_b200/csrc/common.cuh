@@ -3,11 +3,29 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
+// `bf16` is the library's 16-bit element type.  The default build computes in bfloat16 (libslime_b200.so); the
+// same sources compiled with -DSLIME_FP16 compute in IEEE half (libslime_b200_fp16.so) - the reference's
+// inference dtype (llava/model/builder.py:43).  Only the conversions, the UMMA operand-format bits, the TMA
+// element type and the mma.sync type suffix differ; tiles, pipelines and fp32 accumulation are identical.
+#ifdef SLIME_FP16
+typedef __half bf16;
+typedef __half2 bf162;
+#define SLIME_ELEM_DTYPE 2                               /* slime_elem_dtype(): 0 bf16, 2 fp16 */
+#define SLIME_UMMA_AB_FORMAT 0u                          /* kind::f16 operand format: 0 = F16, 1 = BF16 */
+#define SLIME_TMAP_ELEM CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define SLIME_MMA_SYNC_TYPE "f16"
+#else
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
+#define SLIME_ELEM_DTYPE 0
+#define SLIME_UMMA_AB_FORMAT 1u
+#define SLIME_TMAP_ELEM CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define SLIME_MMA_SYNC_TYPE "bf16"
+#endif
 
 #define SLIME_DEVINL __device__ __forceinline__
 
@@ -183,13 +201,27 @@ SLIME_DEVINL uint64_t make_umma_desc_sw128(uint32_t smem_addr) {
 //   c_format [4,6)=1 (F32), a_format [7,10)=1 (BF16), b_format [10,13)=1 (BF16),
 //   a_major bit15 = 0, b_major bit16 = 0, n_dim [17,23) = N>>3, m_dim [24,29) = M>>4.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+  return (1u << 4) | (SLIME_UMMA_AB_FORMAT << 7) | (SLIME_UMMA_AB_FORMAT << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------------------
+#ifdef SLIME_FP16
+SLIME_DEVINL float elem_to_float(bf16 x) { return __half2float(x); }
+SLIME_DEVINL bf16 float_to_elem(float x) { return __float2half_rn(x); }
+SLIME_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
+  bf162 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+SLIME_DEVINL float2 unpack_bf16x2(uint32_t u) {
+  bf162 v = *reinterpret_cast<bf162*>(&u);
+  return __half22float2(v);
+}
+#else
+SLIME_DEVINL float elem_to_float(bf16 x) { return __bfloat162float(x); }
+SLIME_DEVINL bf16 float_to_elem(float x) { return __float2bfloat16_rn(x); }
 SLIME_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   bf162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -198,6 +230,7 @@ SLIME_DEVINL float2 unpack_bf16x2(uint32_t u) {
   bf162 v = *reinterpret_cast<bf162*>(&u);
   return __bfloat1622float2(v);
 }
+#endif
 SLIME_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

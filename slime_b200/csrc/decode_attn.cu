@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(NT) decode_attn_kernel(const bf16* __restrict_
   {
     const bf16* qp = q + static_cast<long long>(b) * q_ld + head * HD + lane * EPL;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) qv[i] = __bfloat162float(qp[i]);
+    for (int i = 0; i < EPL; ++i) qv[i] = elem_to_float(qp[i]);
   }
   float m = -INFINITY, l = 0.f, acc[EPL];
 #pragma unroll
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(NT) decode_attn_kernel(const bf16* __restrict_
     } else {
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        kv[i] = __bfloat162float(kp[i]);
-        vv[i] = __bfloat162float(vp[i]);
+        kv[i] = elem_to_float(kp[i]);
+        vv[i] = elem_to_float(vp[i]);
       }
     }
     float s = 0.f;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NT) decode_attn_kernel(const bf16* __restrict_
     const float inv = lt > 0.f ? 1.0f / lt : 0.f;
     bf16* op = out + static_cast<long long>(b) * out_ld + head * HD + lane * EPL;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) op[i] = __float2bfloat16(o[i] * inv);
+    for (int i = 0; i < EPL; ++i) op[i] = float_to_elem(o[i] * inv);
   }
 }
 

@@ -29,7 +29,7 @@ SLIME_DEVINL void store8(bf16* p, const float* v) {
   u.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
-SLIME_DEVINL float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+SLIME_DEVINL float round_bf16(float x) { return elem_to_float(float_to_elem(x)); }  // round to the element type
 
 // Sum over the TPR threads that share a row.  TPR == 32: one warp per row (4 rows per CTA);
 // TPR == 128: the whole CTA works on one row.
@@ -175,7 +175,7 @@ __global__ void im2col_kernel(const bf16* __restrict__ px, bf16* __restrict__ ou
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int k = static_cast<int>(i % Kpad);
     const long long prow = i / Kpad;
-    bf16 v = __float2bfloat16(0.f);
+    bf16 v = float_to_elem(0.f);
     if (k < K) {
       const int c = k / (patch * patch);
       const int ky = (k / patch) % patch;

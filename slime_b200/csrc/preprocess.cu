@@ -36,6 +36,7 @@ struct DevJob {
   int first_crop;
   int ksize_h, ksize_v;
   int hb_off, hk_off, vb_off, vk_off;  // int32 offsets into the table area: bounds (2 per output) and coefficients
+  int skip_rows_pass;                  // width unchanged and no padding: the vertical pass reads the source itself
   unsigned char fill[4];
 };
 
@@ -84,6 +85,16 @@ void precompute_coeffs(int in_size, int out_size, int ksize, int32_t* bounds, in
       k[x] = (v < 0) ? static_cast<int32_t>(-0.5 + v * (1 << PRECISION_BITS))
                      : static_cast<int32_t>(0.5 + v * (1 << PRECISION_BITS));
     }
+    // taps whose fixed-point coefficient rounded to zero contribute nothing: drop them from both ends (the
+    // identity resize collapses to one tap; Pillow keeps them, the sums are identical)
+    int first = 0;
+    while (xmax - first > 1 && k[first] == 0) ++first;
+    while (xmax - first > 1 && k[xmax - 1] == 0) --xmax;
+    if (first > 0) {
+      for (int x = first; x < xmax; ++x) k[x - first] = k[x];
+      xmin += first;
+      xmax -= first;
+    }
     for (int x = xmax; x < ksize; ++x) k[x] = 0;
     bounds[2 * xx] = xmin;
     bounds[2 * xx + 1] = xmax;
@@ -101,6 +112,7 @@ __global__ void __launch_bounds__(256) resize_rows_kernel(const unsigned char* _
                                                           const int32_t* __restrict__ tables,
                                                           unsigned char* __restrict__ ws) {
   const DevJob jb = jobs[blockIdx.y];
+  if (jb.skip_rows_pass) return;  // ImagingResample: need_horizontal == false
   const long long total = static_cast<long long>(jb.virt_h) * jb.out_w;
   const unsigned char* img = src + jb.src_off;
   unsigned char* tmp = ws + jb.tmp_off;
@@ -146,14 +158,15 @@ __device__ __forceinline__ __half from_float<__half>(float v) { return __float2h
 
 // vertical pass + canvas placement + table lookup: one thread per canvas pixel, all three channels
 template <typename T>
-__global__ void __launch_bounds__(256) resize_cols_kernel(const DevJob* __restrict__ jobs,
+__global__ void __launch_bounds__(256) resize_cols_kernel(const unsigned char* __restrict__ src,
+                                                          const DevJob* __restrict__ jobs,
                                                           const int32_t* __restrict__ tables,
                                                           const float* __restrict__ lut,
                                                           const unsigned char* __restrict__ ws, T* __restrict__ out,
                                                           int crop) {
   const DevJob jb = jobs[blockIdx.y];
   const long long total = static_cast<long long>(jb.canvas_w) * jb.canvas_h;
-  const unsigned char* tmp = ws + jb.tmp_off;
+  const unsigned char* tmp = jb.skip_rows_pass ? src + jb.src_off : ws + jb.tmp_off;
   const int32_t* bounds = tables + jb.vb_off;
   const int32_t* kk = tables + jb.vk_off;
   const int tiles_x = jb.canvas_w / crop;
@@ -275,6 +288,7 @@ extern "C" int slime_preprocess_fwd(const uint8_t* src, const slime_resize_job* 
     d.paste_x = q.paste_x; d.paste_y = q.paste_y;
     d.first_crop = q.first_crop;
     std::memcpy(d.fill, q.fill, 4);
+    d.skip_rows_pass = (q.out_w == q.virt_w && q.virt_w == q.src_w && q.virt_h == q.src_h) ? 1 : 0;
     d.ksize_h = coeff_ksize(q.virt_w, q.out_w);
     d.ksize_v = coeff_ksize(q.virt_h, q.out_h);
     d.hb_off = static_cast<int>(cursor); cursor += 2 * static_cast<size_t>(q.out_w);
@@ -283,7 +297,7 @@ extern "C" int slime_preprocess_fwd(const uint8_t* src, const slime_resize_job* 
     d.vk_off = static_cast<int>(cursor); cursor += static_cast<size_t>(q.out_h) * d.ksize_v;
     precompute_coeffs(q.virt_w, q.out_w, d.ksize_h, tables + d.hb_off, tables + d.hk_off);
     precompute_coeffs(q.virt_h, q.out_h, d.ksize_v, tables + d.vb_off, tables + d.vk_off);
-    const long long rows_px = static_cast<long long>(q.virt_h) * q.out_w;
+    const long long rows_px = d.skip_rows_pass ? 0 : static_cast<long long>(q.virt_h) * q.out_w;
     const long long canvas_px = static_cast<long long>(q.canvas_w) * q.canvas_h;
     if (rows_px > max_rows_px) max_rows_px = rows_px;
     if (canvas_px > max_canvas_px) max_canvas_px = canvas_px;
@@ -299,6 +313,7 @@ extern "C" int slime_preprocess_fwd(const uint8_t* src, const slime_resize_job* 
   {
     long long bx = (max_rows_px + 255) / 256;
     if (bx > 4096) bx = 4096;
+    if (bx < 1) bx = 1;
     dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(n_jobs));
     resize_rows_kernel<<<grid, 256, 0, stream>>>(src, djobs, dtables, wsb);
     SLIME_AFTER_LAUNCH();
@@ -308,12 +323,12 @@ extern "C" int slime_preprocess_fwd(const uint8_t* src, const slime_resize_job* 
     if (bx > 4096) bx = 4096;
     dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(n_jobs));
     if (out_dtype == 0) {
-      resize_cols_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(djobs, dtables, dlut, wsb,
+      resize_cols_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, djobs, dtables, dlut, wsb,
                                                                  static_cast<__nv_bfloat16*>(out), crop);
     } else if (out_dtype == 1) {
-      resize_cols_kernel<float><<<grid, 256, 0, stream>>>(djobs, dtables, dlut, wsb, static_cast<float*>(out), crop);
+      resize_cols_kernel<float><<<grid, 256, 0, stream>>>(src, djobs, dtables, dlut, wsb, static_cast<float*>(out), crop);
     } else {
-      resize_cols_kernel<__half><<<grid, 256, 0, stream>>>(djobs, dtables, dlut, wsb, static_cast<__half*>(out), crop);
+      resize_cols_kernel<__half><<<grid, 256, 0, stream>>>(src, djobs, dtables, dlut, wsb, static_cast<__half*>(out), crop);
     }
     SLIME_AFTER_LAUNCH();
   }

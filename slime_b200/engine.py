@@ -53,13 +53,18 @@ class PrefillResult:
 
 
 class SlimeEngine:
-    def __init__(self, cfg: SlimeConfig, device: int | str | torch.device = 0, max_pos: Optional[int] = None):
+    def __init__(self, cfg: SlimeConfig, device: int | str | torch.device = 0, max_pos: Optional[int] = None,
+                 dtype=torch.bfloat16):
         cfg.validate()
         self.cfg = cfg
         self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         if self.device.type != "cuda":
             raise RuntimeError("SlimeEngine needs a CUDA (B200) device: there is no CPU path")
-        self.lib = L.load()
+        # 16-bit element type of every activation / weight: bfloat16 (default) or float16, the reference's
+        # inference dtype (llava/model/builder.py:43) - each has its own build of the library
+        self.dtype = L.torch_dtype(L.variant_of(dtype))
+        self.lib = L.load(self.dtype)
+        self._check = lambda rc, what="": L.check(rc, what, self.lib)
         self._lock = threading.RLock()  # a slime_ctx is not re-entrant (serve/model_worker.py runs generate on threads)
         self._ws: Optional[torch.Tensor] = None
         self._row_maps: Dict[tuple, torch.Tensor] = {}
@@ -82,7 +87,7 @@ class SlimeEngine:
         self._desc = d
         self._ctx = C.c_void_p()
         with torch.cuda.device(self.device):
-            L.check(self.lib.slime_ctx_create(C.byref(self._ctx), self.device.index or 0, C.byref(d)), "ctx_create")
+            self._check(self.lib.slime_ctx_create(C.byref(self._ctx), self.device.index or 0, C.byref(d)), "ctx_create")
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -104,12 +109,12 @@ class SlimeEngine:
         """groups: which weight groups to register ("vit", "rs_local", "rs_global", "proj", "llm"); a stage
         whose group is absent fails loudly (used by the stand-alone module shims of slime_b200/model)."""
         with self._lock, torch.cuda.device(self.device):
-            self.weights = pack_weights(self.cfg, get, self.device, groups)
+            self.weights = pack_weights(self.cfg, get, self.device, groups, self.dtype)
             for name, t in self.weights.items():
-                L.check(self.lib.slime_ctx_set_weight(self._ctx, name.encode(), L.ptr(t), t.shape[0], t.shape[1]),
+                self._check(self.lib.slime_ctx_set_weight(self._ctx, name.encode(), L.ptr(t), t.shape[0], t.shape[1]),
                         f"set_weight({name})")
             ws = self._workspace(self.lib.slime_finalize_workspace_bytes(self._ctx))
-            L.check(self.lib.slime_ctx_finalize_weights(self._ctx, L.ptr(ws), ws.numel(), L.stream_ptr()), "finalize")
+            self._check(self.lib.slime_ctx_finalize_weights(self._ctx, L.ptr(ws), ws.numel(), L.stream_ptr()), "finalize")
             torch.cuda.current_stream().synchronize()
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
@@ -119,19 +124,19 @@ class SlimeEngine:
         return self._ws
 
     def _bf16(self, *shape) -> torch.Tensor:
-        return torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+        return torch.empty(shape, dtype=self.dtype, device=self.device)
 
     # ------------------------------------------------------------------ stages
     @_locked
     def vision_tower(self, pixels: torch.Tensor) -> torch.Tensor:
         """CLIPVisionTower.forward (reference multimodal_encoder/clip_encoder.py:46-58): [N,3,S,S] -> [N,576,D]."""
-        px = pixels.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        px = pixels.to(device=self.device, dtype=self.dtype).contiguous()
         n = px.shape[0]
         feats = self._bf16(n, self.cfg.vit_patches, self.cfg.vit_hidden)
         if n == 0:
             return feats
         ws = self._workspace(self.lib.slime_vision_tower_workspace_bytes(self._ctx, n))
-        L.check(self.lib.slime_vision_tower_fwd(self._ctx, L.ptr(px), n, L.ptr(feats), L.ptr(ws), ws.numel(),
+        self._check(self.lib.slime_vision_tower_fwd(self._ctx, L.ptr(px), n, L.ptr(feats), L.ptr(ws), ws.numel(),
                                                 L.stream_ptr()), "vision_tower_fwd")
         return feats
 
@@ -139,14 +144,14 @@ class SlimeEngine:
     def resampler(self, which: int, x: torch.Tensor) -> torch.Tensor:
         """Resampler.forward (reference multimodal_resampler/sampler.py:140-170); which 0 = local 144-query
         compression (sampler.post_qformer), 1 = the projector's 576-query resampler.  [n,576,D] -> [n,nq,D]."""
-        x = x.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        x = x.to(device=self.device, dtype=self.dtype).contiguous()
         n = x.shape[0]
         nq = self.cfg.mm_resampler_dim if which == 0 else 576
         out = self._bf16(n, nq, self.cfg.vit_hidden)
         if n == 0:
             return out
         ws = self._workspace(self.lib.slime_resampler_workspace_bytes(self._ctx, which, n))
-        L.check(self.lib.slime_resampler_fwd(self._ctx, which, L.ptr(x), n, L.ptr(out), L.ptr(ws), ws.numel(),
+        self._check(self.lib.slime_resampler_fwd(self._ctx, which, L.ptr(x), n, L.ptr(out), L.ptr(ws), ws.numel(),
                                              L.stream_ptr()), "resampler_fwd")
         return out
 
@@ -155,27 +160,27 @@ class SlimeEngine:
                   ) -> torch.Tensor:
         """GatedBlock.projection (reference multimodal_projector/builder.py:53-57,180-181): [rows,D] -> [rows,H];
         row_map scatters output rows (the spatial merge of llava_arch.py:240-244 folded into the store)."""
-        x2 = x.to(device=self.device, dtype=torch.bfloat16).reshape(-1, self.cfg.vit_hidden).contiguous()
+        x2 = x.to(device=self.device, dtype=self.dtype).reshape(-1, self.cfg.vit_hidden).contiguous()
         rows = x2.shape[0]
         if out is None:
             out = self._bf16(rows, self.cfg.hidden_size)
         if rows == 0:
             return out
         ws = self._workspace(self.lib.slime_projector_workspace_bytes(self._ctx, rows))
-        L.check(self.lib.slime_projector_fwd(self._ctx, L.ptr(x2), rows, L.ptr(row_map), L.ptr(out), L.ptr(ws),
+        self._check(self.lib.slime_projector_fwd(self._ctx, L.ptr(x2), rows, L.ptr(row_map), L.ptr(out), L.ptr(ws),
                                              ws.numel(), L.stream_ptr()), "projector_fwd")
         return out
 
     @_locked
     def gated_projector(self, x: torch.Tensor) -> torch.Tensor:
         """GatedBlock.forward on global crops (reference multimodal_projector/builder.py:179-209): [n,576,D] -> [n,576,H]."""
-        x = x.to(device=self.device, dtype=torch.bfloat16).reshape(-1, 576, self.cfg.vit_hidden).contiguous()
+        x = x.to(device=self.device, dtype=self.dtype).reshape(-1, 576, self.cfg.vit_hidden).contiguous()
         n = x.shape[0]
         out = self._bf16(n, 576, self.cfg.hidden_size)
         if n == 0:
             return out
         ws = self._workspace(self.lib.slime_gated_projector_workspace_bytes(self._ctx, n))
-        L.check(self.lib.slime_gated_projector_fwd(self._ctx, L.ptr(x), n, L.ptr(out), L.ptr(ws), ws.numel(),
+        self._check(self.lib.slime_gated_projector_fwd(self._ctx, L.ptr(x), n, L.ptr(out), L.ptr(ws), ws.numel(),
                                                    L.stream_ptr()), "gated_projector_fwd")
         return out
 
@@ -185,7 +190,7 @@ class SlimeEngine:
         """TextGuidedSampler.forward + cosine selector + get_pure_text_embedding (reference
         multimodal_resampler/builder.py:189-201,248-281; llava_arch.py:162-210).
         local [B, n_per, H] -> (sel_idx [B,n_per] int32, sel_count [B] int32, probs or None)."""
-        local = local.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        local = local.to(device=self.device, dtype=self.dtype).contiguous()
         B, n_per = local.shape[0], local.shape[1]
         T = ids.shape[1]
         ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
@@ -194,7 +199,7 @@ class SlimeEngine:
         sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
         probs = torch.zeros(B, max(n_per, 1), dtype=torch.float32, device=self.device) if want_probs else None
         ws = self._workspace(self.lib.slime_router_workspace_bytes(self._ctx, B, n_per, T))
-        L.check(self.lib.slime_router_fwd(self._ctx, L.ptr(local), n_per, L.ptr(n_valid), L.ptr(ids),
+        self._check(self.lib.slime_router_fwd(self._ctx, L.ptr(local), n_per, L.ptr(n_valid), L.ptr(ids),
                                           L.ptr(m8), B, T, L.ptr(probs), L.ptr(sel_idx), L.ptr(sel_count), L.ptr(ws),
                                           ws.numel(), L.stream_ptr()), "router_fwd")
         return sel_idx, sel_count, probs
@@ -204,8 +209,8 @@ class SlimeEngine:
                       want_probs: bool = False):
         """The reference's module-level signature TextGuidedSampler.forward(local_f, text_embedding, attn_mask)
         (multimodal_resampler/builder.py:248): the prompt arrives as embeddings [B,T,H], not ids."""
-        local = local.to(device=self.device, dtype=torch.bfloat16).contiguous()
-        text = text_embeds.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        local = local.to(device=self.device, dtype=self.dtype).contiguous()
+        text = text_embeds.to(device=self.device, dtype=self.dtype).contiguous()
         B, n_per = local.shape[0], local.shape[1]
         T = text.shape[1]
         m8 = None if mask is None else (mask != 0).to(device=self.device, dtype=torch.uint8).contiguous()
@@ -213,7 +218,7 @@ class SlimeEngine:
         sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
         probs = torch.zeros(B, max(n_per, 1), dtype=torch.float32, device=self.device) if want_probs else None
         ws = self._workspace(self.lib.slime_router_workspace_bytes(self._ctx, B, n_per, T))
-        L.check(self.lib.slime_router_fwd_embeds(self._ctx, L.ptr(local), n_per, None, L.ptr(text), L.ptr(m8), B, T,
+        self._check(self.lib.slime_router_fwd_embeds(self._ctx, L.ptr(local), n_per, None, L.ptr(text), L.ptr(m8), B, T,
                                                  L.ptr(probs), L.ptr(sel_idx), L.ptr(sel_count), L.ptr(ws), ws.numel(),
                                                  L.stream_ptr()), "router_fwd_embeds")
         return sel_idx, sel_count, probs
@@ -225,7 +230,7 @@ class SlimeEngine:
         B, n_per = probs.shape
         sel_idx = torch.zeros(B, n_per, dtype=torch.int32, device=self.device)
         sel_count = torch.zeros(B, dtype=torch.int32, device=self.device)
-        L.check(self.lib.slime_router_select(self._ctx, L.ptr(probs), B, n_per, L.ptr(n_valid), L.ptr(sel_idx),
+        self._check(self.lib.slime_router_select(self._ctx, L.ptr(probs), B, n_per, L.ptr(n_valid), L.ptr(sel_idx),
                                              L.ptr(sel_count), L.stream_ptr()), "router_select")
         return sel_idx, sel_count
 
@@ -241,7 +246,7 @@ class SlimeEngine:
         m8 = None if mask is None else (mask != 0).to(device=self.device, dtype=torch.uint8).contiguous()
         plan = torch.empty(int(self.lib.slime_splice_plan_ints(B, T)), dtype=torch.int32, device=self.device)
         host_cu = (C.c_int32 * (B + 1))()
-        L.check(self.lib.slime_splice_plan(self._ctx, L.ptr(ids), L.ptr(m8), B, T, n_global, int(has_sep),
+        self._check(self.lib.slime_splice_plan(self._ctx, L.ptr(ids), L.ptr(m8), B, T, n_global, int(has_sep),
                                            L.ptr(sel_count), L.ptr(plan), host_cu, L.stream_ptr()), "splice_plan")
         cu_host = list(host_cu)
         lengths = [cu_host[i + 1] - cu_host[i] for i in range(B)]
@@ -251,19 +256,19 @@ class SlimeEngine:
         g_rows = glob.shape[1] if glob is not None and glob.dim() == 3 else 0
         l_rows = local.shape[1] if local is not None and local.dim() == 3 else 0
         sel_stride = sel_idx.shape[1] if sel_idx is not None else 0
-        L.check(self.lib.slime_splice_gather(self._ctx, L.ptr(ids), B, T, L.ptr(plan), L.ptr(glob), n_global, g_rows,
+        self._check(self.lib.slime_splice_gather(self._ctx, L.ptr(ids), B, T, L.ptr(plan), L.ptr(glob), n_global, g_rows,
                                              L.ptr(local), l_rows, L.ptr(sel_idx), sel_stride, int(has_sep),
                                              L.ptr(embeds), L.ptr(pos_ids), total, L.stream_ptr()), "splice_gather")
         cu_dev = plan[B * T + B * 8: B * T + B * 8 + B + 1]
         out = dict(embeds=embeds, pos_ids=pos_ids, cu_seqlens=cu_dev, lengths=lengths, plan=plan)
         if padded:
             lmax = max(lengths) if lengths else 0
-            pe = torch.empty(B, lmax, H, dtype=torch.bfloat16, device=self.device)
+            pe = torch.empty(B, lmax, H, dtype=self.dtype, device=self.device)
             pm = torch.empty(B, lmax, dtype=torch.uint8, device=self.device)
             pp = torch.empty(B, lmax, dtype=torch.int64, device=self.device)
             pl = torch.empty(B, lmax, dtype=torch.int64, device=self.device)
             lab = None if labels is None else labels.to(device=self.device, dtype=torch.int64).contiguous()
-            L.check(self.lib.slime_splice_pad(self._ctx, L.ptr(plan), L.ptr(embeds), L.ptr(lab), B, T, lmax, L.ptr(pe),
+            self._check(self.lib.slime_splice_pad(self._ctx, L.ptr(plan), L.ptr(embeds), L.ptr(lab), B, T, lmax, L.ptr(pe),
                                               L.ptr(pm), L.ptr(pp), L.ptr(pl), L.stream_ptr()), "splice_pad")
             out.update(inputs_embeds=pe, attention_mask=pm.bool(), position_ids=pp, labels=pl)
         return out
@@ -279,7 +284,7 @@ class SlimeEngine:
         allv = self._bf16(total, V) if want_all else None
         hid = self._bf16(total, self.cfg.hidden_size) if want_hidden else None
         ws = self._workspace(self.lib.slime_decoder_workspace_bytes(self._ctx, total, B))
-        L.check(self.lib.slime_decoder_prefill_fwd(self._ctx, L.ptr(embeds), L.ptr(cu_seqlens), L.ptr(pos_ids), B, total,
+        self._check(self.lib.slime_decoder_prefill_fwd(self._ctx, L.ptr(embeds), L.ptr(cu_seqlens), L.ptr(pos_ids), B, total,
                                                    max(lengths) if lengths else 0, L.ptr(last), L.ptr(allv), L.ptr(hid),
                                                    L.ptr(ws), ws.numel(), L.stream_ptr()), "decoder_prefill_fwd")
         return last, allv, hid
@@ -325,25 +330,25 @@ class SlimeEngine:
         decoder_prefill stores K (post-RoPE) / V of its sequences into it (sequence b -> cache slot b)."""
         cfg = self.cfg
         cache = torch.zeros(cfg.num_hidden_layers, 2, batch, cache_len, cfg.num_key_value_heads * cfg.head_dim,
-                            dtype=torch.bfloat16, device=self.device)
-        L.check(self.lib.slime_decoder_set_kv_cache(self._ctx, L.ptr(cache), batch, cache_len), "set_kv_cache")
+                            dtype=self.dtype, device=self.device)
+        self._check(self.lib.slime_decoder_set_kv_cache(self._ctx, L.ptr(cache), batch, cache_len), "set_kv_cache")
         self._kv_cache = cache
         return cache
 
     @_locked
     def detach_kv_cache(self) -> None:
-        L.check(self.lib.slime_decoder_set_kv_cache(self._ctx, None, 0, 0), "set_kv_cache")
+        self._check(self.lib.slime_decoder_set_kv_cache(self._ctx, None, 0, 0), "set_kv_cache")
         self._kv_cache = None
 
     @_locked
     def decode_step(self, x: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
         """One decode step: x [B, H] embeddings of the tokens to append, lens [B] int32 (device) tokens already cached
         -> logits [B, V] fp32 (HF generation loop step after the prefill; reference llava_llama.py:139)."""
-        x = x.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        x = x.to(device=self.device, dtype=self.dtype).contiguous()
         B = x.shape[0]
         logits = torch.empty(B, self.cfg.vocab_size, dtype=torch.float32, device=self.device)
         ws = self._workspace(self.lib.slime_decoder_decode_workspace_bytes(self._ctx, B))
-        L.check(self.lib.slime_decoder_decode_fwd(self._ctx, L.ptr(x), L.ptr(lens), B, L.ptr(logits), L.ptr(ws),
+        self._check(self.lib.slime_decoder_decode_fwd(self._ctx, L.ptr(x), L.ptr(lens), B, L.ptr(logits), L.ptr(ws),
                                                   ws.numel(), L.stream_ptr()), "decode_fwd")
         return logits
 
@@ -443,7 +448,7 @@ class SlimeEngine:
                 px = pixels.reshape(-1, *pixels.shape[2:])
             B = len(counts)
             assert input_ids.shape[0] == B, "one image (stack of crops) per sample"
-            px = px.to(device=self.device, dtype=torch.bfloat16, non_blocking=True)
+            px = px.to(device=self.device, dtype=self.dtype, non_blocking=True)
             ids = input_ids.to(device=self.device, dtype=torch.int64, non_blocking=True)
             mask = None if attention_mask is None else attention_mask.to(device=self.device, non_blocking=True)
             stages = {} if keep_stages else None
@@ -473,7 +478,7 @@ class SlimeEngine:
             q = cfg.mm_resampler_dim
             n_per = max(n_local) * q if n_local else 0
             if not cfg.use_global_only:
-                local = torch.zeros(B, max(n_per, 1), cfg.hidden_size, dtype=torch.bfloat16, device=self.device) \
+                local = torch.zeros(B, max(n_per, 1), cfg.hidden_size, dtype=self.dtype, device=self.device) \
                     if not uniform else self._bf16(B, max(n_per, 1), cfg.hidden_size)
                 if n_per > 0:
                     if grids is None and cfg.mm_patch_merge_type == "spatial":

@@ -47,8 +47,13 @@ class EngineBinding:
             raise RuntimeError("slime_b200 modules run on a CUDA (B200) device only: move the model with .to('cuda') "
                                "or pass CUDA inputs; there is no CPU/PyTorch fallback path")
         stamp = self._current_stamp(owner)
-        if self._engine is None or self._engine.device != dev:
-            self._engine = SlimeEngine(self.cfg, dev, max_pos=max(self.cfg.max_position_embeddings, 4096))
+        # compute dtype follows the parameters, as in the reference: model.half() / torch_dtype=float16
+        # (llava/model/builder.py:43) -> the float16 build; anything else (bf16, fp32 masters) -> bfloat16
+        big = max(params, key=lambda p: p.numel(), default=None)
+        dtype = torch.float16 if big is not None and big.dtype == torch.float16 else torch.bfloat16
+        if self._engine is None or self._engine.device != dev or self._engine.dtype != dtype:
+            self._engine = SlimeEngine(self.cfg, dev, max_pos=max(self.cfg.max_position_embeddings, 4096),
+                                       dtype=dtype)
             self._stamp = None
         if stamp != self._stamp:
             sd = owner.state_dict()

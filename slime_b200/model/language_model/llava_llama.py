@@ -180,7 +180,7 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         am = torch.ones(B, Lm, dtype=torch.bool, device=inputs_embeds.device) if attention_mask is None \
             else attention_mask.bool()
         lengths = am.sum(1).tolist()
-        rows = inputs_embeds[am].to(device=eng.device, dtype=torch.bfloat16).contiguous()
+        rows = inputs_embeds[am].to(device=eng.device, dtype=eng.dtype).contiguous()
         cu = torch.tensor([0] + list(torch.tensor(lengths).cumsum(0)), dtype=torch.int32, device=eng.device)
         pos = torch.cat([torch.arange(L) for L in lengths]).to(device=eng.device, dtype=torch.int32)
         if position_ids is not None:

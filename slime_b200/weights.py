@@ -38,11 +38,11 @@ ALL_GROUPS = ("vit", "rs_local", "rs_global", "proj", "llm")
 
 
 def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device,
-                 groups=ALL_GROUPS) -> Dict[str, torch.Tensor]:
+                 groups=ALL_GROUPS, dtype: torch.dtype = torch.bfloat16) -> Dict[str, torch.Tensor]:
     """get(name) returns the reference tensor `name` (any dtype/device); returns canonical-name ->
-    contiguous bf16 CUDA tensor (2-D).  Tensors are pulled one at a time so a lazy source (e.g. the
+    contiguous CUDA tensor (2-D) in the engine's 16-bit element type.  Tensors are pulled one at a time so a lazy source (e.g. the
     on-GPU synthetic generator) never holds two copies of the model."""
-    bf = torch.bfloat16
+    bf = dtype
 
     def g(name: str) -> torch.Tensor:
         return get(name).to(device=device, dtype=bf)
@@ -52,7 +52,7 @@ def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device,
     v = CLIP_PREFIX
     if "vit" in groups:
         _pack_vit(cfg, g, out)
-    _pack_adapter(cfg, g, out, device, groups)
+    _pack_adapter(cfg, g, out, device, groups, bf)
     if "llm" in groups:
         _pack_llm(cfg, g, out)
     for k, t in out.items():
@@ -85,8 +85,7 @@ def _pack_vit(cfg, g, out):
         out[c + "fc2_b"] = g(p + "mlp.fc2.bias").reshape(1, -1)
 
 
-def _pack_adapter(cfg, g, out, device, groups):
-    bf = torch.bfloat16
+def _pack_adapter(cfg, g, out, device, groups, bf):
     D = cfg.vit_hidden
     side = int(math.sqrt(cfg.vit_patches))
     for ref_prefix, c, nq in (("model.sampler.post_qformer.", "rs_local.", cfg.mm_resampler_dim),

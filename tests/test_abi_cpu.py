@@ -15,13 +15,14 @@ def test_library_exports_every_declared_symbol():
     from slime_b200 import _lib, build
 
     build.build()
-    lib = _lib.load()
     declared = _declared_symbols()
     assert len(declared) >= 25
-    for name in declared:
-        assert hasattr(lib, name), f"{name} declared in include/slime_b200.h but not exported"
-        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in slime_b200/_lib.py"
-    assert lib.slime_version() == 1
+    for dtype, code in (("bf16", 0), ("fp16", 2)):  # the two builds of the same sources export the same ABI
+        lib = _lib.load(dtype)
+        for name in declared:
+            assert hasattr(lib, name), f"{name} declared in include/slime_b200.h but not exported ({dtype} build)"
+            assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in slime_b200/_lib.py"
+        assert lib.slime_version() == 1 and lib.slime_elem_dtype() == code
 
 
 def test_ctx_create_fails_loudly_without_gpu():

@@ -26,9 +26,9 @@ def rel(a, b):
 _cache = {}
 
 
-def build(name, layers=None):
+def build(name, layers=None, dtype=torch.bfloat16):
     """Engine with on-GPU synthetic weights of the named architecture (+ an accessor for the same tensors)."""
-    key = (name, layers)
+    key = (name, layers, dtype)
     if key in _cache:
         return _cache[key]
     from slime_b200.config import preset
@@ -44,7 +44,7 @@ def build(name, layers=None):
     def get(n):
         return synth_tensor(n, specs[n][0], specs[n][1], 3407, device=dev, dtype=torch.bfloat16)
 
-    eng = SlimeEngine(cfg, 0, max_pos=4096)
+    eng = SlimeEngine(cfg, 0, max_pos=4096, dtype=dtype)
     eng.load_weights(get)
     _cache[key] = (cfg, eng, get, specs)
     return _cache[key]
@@ -61,14 +61,23 @@ class LazyFp32Dict(dict):
         return self._get(k).float()
 
 
-@pytest.mark.parametrize("name,T", [("vicuna-7b", 128), ("llama3-8b", 256)])
-def test_fullsize_against_fp32_oracle_on_gpu(name, T):
+# tolerances (rel-L2 vs the fp32 oracle): bf16 keeps 8 significand bits per rounding, fp16 11 -> 8x tighter.
+# north_star asks for 1e-3 "bf16/fp16 tolerance": the fp16 build is what gets the 32-layer logits to that order;
+# in bf16 the reference's own bf16 execution is ~1e-2 away from fp32 as well (tolerances).
+TOL = {torch.bfloat16: dict(stage=2e-2, logits=5e-2), torch.float16: dict(stage=2.5e-3, logits=6e-3)}
+
+
+@pytest.mark.parametrize("name,T,dtype", [("vicuna-7b", 128, torch.bfloat16), ("llama3-8b", 256, torch.bfloat16),
+                                          ("llama3-8b", 256, torch.float16)],
+                         ids=["vicuna-7b-bf16", "llama3-8b-bf16", "llama3-8b-fp16"])
+def test_fullsize_against_fp32_oracle_on_gpu(name, T, dtype):
     from oracle import slime_oracle as O
     from slime_b200.synth import synth_inputs
 
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    cfg, eng, get, specs = build(name)
+    cfg, eng, get, specs = build(name, dtype=dtype)
+    tol = TOL[dtype]
     B, n = 2, 5
     px, ids, mask = synth_inputs(cfg, B, n, T, seed=11, ragged=True)
     px, ids, mask = px.cuda(), ids.cuda(), mask.cuda()
@@ -80,13 +89,13 @@ def test_fullsize_against_fp32_oracle_on_gpu(name, T):
         e_vit = rel(res.stages["vit"], torch.cat(enc["vit"]))
         e_glob = rel(res.stages["glob"], torch.stack(enc["glob"]))
         e_loc = rel(res.stages["local_m"], torch.stack(enc["local_m"]))
-        print(f"[{name}] full-size rel-L2: vit {e_vit:.3e}  gated-global {e_glob:.3e}  local {e_loc:.3e}")
-        assert e_vit < 2e-2 and e_glob < 2e-2 and e_loc < 2e-2
+        print(f"[{name} {dtype}] full-size rel-L2: vit {e_vit:.3e}  gated-global {e_glob:.3e}  local {e_loc:.3e}")
+        assert e_vit < tol["stage"] and e_glob < tol["stage"] and e_loc < tol["stage"]
         # router probabilities on the CUDA path's own features, then the exact selection rule on them
         r2 = eng.prefill(px, ids, mask, grids=grids, want_probs=True, want_last=False, run_decoder=False)
         for b in range(B):
             e_p = rel(r2.probs[b], enc["probs"][b])
-            assert e_p < 2e-2, e_p
+            assert e_p < tol["stage"], e_p
             expect = O.top_p_select(r2.probs[b].cpu(), cfg.mm_resampler_topp)
             k = int(r2.sel_count[b])
             assert r2.sel_idx[b, :k].cpu().tolist() == expect.tolist()
@@ -100,8 +109,8 @@ def test_fullsize_against_fp32_oracle_on_gpu(name, T):
             lg = _oracle_last_logits(O, sd, cfg, emb[b, :L].cuda())
             last.append(lg)
         e_log = rel(res.logits_last, torch.stack(last))
-        print(f"[{name}] full-size last-token logits rel-L2 vs fp32 oracle: {e_log:.3e}")
-        assert e_log < 5e-2
+        print(f"[{name} {dtype}] full-size last-token logits rel-L2 vs fp32 oracle: {e_log:.3e}")
+        assert e_log < tol["logits"]
 
 
 def _oracle_last_logits(O, sd, cfg, x):

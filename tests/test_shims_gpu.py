@@ -133,3 +133,29 @@ def test_images_mask_padding_is_ignored(setup):
               image_sizes=[(672, 672)] * B)
     assert a.logits.shape == b.logits.shape
     assert torch.equal(a.logits, b.logits)
+
+
+def test_half_model_runs_the_float16_build():
+    """model.half() (the reference's inference dtype, llava/model/builder.py:43) selects libslime_b200_fp16.so;
+    the logits agree with the bf16 run of the same model to bf16 accuracy and are fp16-finite."""
+    from slime_b200.synth import synth_inputs, synth_state_dict
+    from tests.test_shims_cpu import make_model
+
+    cfg, model = make_model("tiny")
+    sd = synth_state_dict(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(device="cuda", dtype=torch.float16).eval()
+    px, ids, mask = synth_inputs(cfg, 2, 5, 24, image_pos=5, ragged=True)
+    res = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=px.cuda().half(), image_sizes=[(672, 672)] * 2)
+    eng = model._engine()
+    assert eng.dtype == torch.float16 and eng.lib.slime_elem_dtype() == 2
+    assert torch.isfinite(res.logits.float()).all()
+    fast = eng.prefill(px, ids, mask, grids=[(2, 2)] * 2)
+    lens = fast.lengths
+    for b in range(2):
+        assert rel(res.logits[b, lens[b] - 1], fast.logits_last[b]) < 2e-3
+    model = model.to(dtype=torch.bfloat16)          # back to bf16: the binding re-creates a bf16 engine
+    res2 = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=px.cuda().bfloat16(),
+                 image_sizes=[(672, 672)] * 2)
+    assert model._engine().dtype == torch.bfloat16
+    assert res2.logits.shape[2] == cfg.vocab_size
