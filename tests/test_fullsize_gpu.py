@@ -64,7 +64,7 @@ class LazyFp32Dict(dict):
 # tolerances (rel-L2 vs the fp32 oracle): bf16 keeps 8 significand bits per rounding, fp16 11 -> 8x tighter.
 # north_star asks for 1e-3 "bf16/fp16 tolerance": the fp16 build is what gets the 32-layer logits to that order;
 # in bf16 the reference's own bf16 execution is ~1e-2 away from fp32 as well (tolerances).
-TOL = {torch.bfloat16: dict(stage=2e-2, logits=5e-2), torch.float16: dict(stage=2.5e-3, logits=6e-3)}
+TOL = {torch.bfloat16: dict(stage=2e-2, logits=5e-2), torch.float16: dict(stage=2.5e-3, logits=3e-3)}
 
 
 @pytest.mark.parametrize("name,T,dtype", [("vicuna-7b", 128, torch.bfloat16), ("llama3-8b", 256, torch.bfloat16),
