@@ -36,10 +36,13 @@ struct TcCfg {
   // >= 120 KB so that two CTAs can never share an SM (each allocates all 512 TMEM columns)
   static constexpr int NK = HD == 128 ? 3 : 4;  // K ring depth (TMA latency must be covered by ~2 tile times)
   static constexpr int NV = HD == 128 ? 2 : 3;  // V ring depth
-  static constexpr int SMEM_RAW = 1024 + TILE_BYTES * (1 + NK + NV) + 256 + 6 * 128 * 4;
+  static constexpr int STAGE_BYTES = 8 * 32 * 64;  // epilogue: per softmax warp 32 rows x 64 B (one 32-column chunk)
+  static constexpr int SMEM_RAW = 1024 + TILE_BYTES * (1 + NK + NV) + 256 + 6 * 128 * 4 + STAGE_BYTES;
   static constexpr int SMEM_BYTES = SMEM_RAW > 120 * 1024 ? SMEM_RAW : 120 * 1024;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;
+  // S double-buffered per kv tile, O double-buffered per ITEM (the epilogue of item i is deferred until the first
+  // score tile of item i+1 has been handed to the tensor pipe, so PV of item i+1 must not touch O of item i)
+  static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256, O_STRIDE = 128;
 };
 
 // MUFU.EX2 without the denormal/range fix-up code exp2f() adds (inputs here are <= 8, -inf -> 0)
@@ -100,6 +103,45 @@ SLIME_DEVINL Item decode_item(const AttnParams& p, int w, int q_tiles) {
   return it;
 }
 
+// Epilogue of one item for one softmax warp: O / l -> bf16 -> HBM.  Each thread owns HD/2 columns of one row in
+// TMEM; writing those straight to HBM makes every store instruction touch 32 different rows (32 L1 wavefronts per
+// instruction, ~2 k cycles per item with the tensor pipe idle - the gap between items in
+// profiles/r01_attention_clock_trace.txt).  Instead each warp transposes one 32-column chunk at a time through its
+// own 2 KB of shared memory (16-byte slots XOR-swizzled by row pair: conflict-free both ways) and writes 8 rows x 64
+// contiguous bytes per instruction.
+template <int HD>
+SLIME_DEVINL void epilogue_tile(uint64_t* o_done_bar, uint32_t o_done_parity, uint64_t* o_free_bar, uint32_t o_addr,
+                                uint8_t* stage, int lane, int quad, float inv_l, int rows_valid, bf16* out, int o_ld) {
+  mbar_wait(o_done_bar, o_done_parity);
+  tcgen05_fence_after();
+#pragma unroll
+  for (int c = 0; c < HD / 64; ++c) {
+    uint32_t orow[32];
+    tmem_ld_32x32b_x32(o_addr + c * 32, orow);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 pkv;
+      pkv.x = pack_bf16x2(__uint_as_float(orow[q * 8 + 0]) * inv_l, __uint_as_float(orow[q * 8 + 1]) * inv_l);
+      pkv.y = pack_bf16x2(__uint_as_float(orow[q * 8 + 2]) * inv_l, __uint_as_float(orow[q * 8 + 3]) * inv_l);
+      pkv.z = pack_bf16x2(__uint_as_float(orow[q * 8 + 4]) * inv_l, __uint_as_float(orow[q * 8 + 5]) * inv_l);
+      pkv.w = pack_bf16x2(__uint_as_float(orow[q * 8 + 6]) * inv_l, __uint_as_float(orow[q * 8 + 7]) * inv_l);
+      *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = pkv;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + (lane >> 2), q = lane & 3;  // 8 rows x 4 slots per instruction
+      const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+      if (quad * 32 + r < rows_valid)
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * o_ld + c * 32 + q * 8) = v;
+    }
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  mbar_arrive(o_free_bar);
+}
+
 template <int HD, bool CAUSAL>
 __global__ void __launch_bounds__(NT, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -123,9 +165,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* p_ready = bars + 20;  // [2]
   uint64_t* o_done = bars + 22;   // [2]: PV with global index g commits o_done[g & 1] (phase g >> 1), so a waiter is
                                  // never more than one phase behind and parity waits stay unambiguous
-  uint64_t* o_free = bars + 24;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 25);
-  float* xch = reinterpret_cast<float*>(bars + 26);  // [6][128]: per-tile half-row max (2 slots x 2 halves), item sums (2 halves)
+  uint64_t* o_free = bars + 24;   // [2] per O buffer
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
+  float* xch = reinterpret_cast<float*>(bars + 27);  // [6][128]: per-tile half-row max (2 slots x 2 halves), item sums (2 halves)
+  uint8_t* stage_all = reinterpret_cast<uint8_t*>(bars) + 256 + 6 * 128 * 4;  // [8 warps][32 rows][64 B]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,7 +193,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
     mbar_init(&o_done[0], 1);
     mbar_init(&o_done[1], 1);
-    mbar_init(o_free, 256);
+    mbar_init(&o_free[0], 256);
+    mbar_init(&o_free[1], 256);
     fence_barrier_init();
   } else if (warp_idx == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
@@ -239,7 +283,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           const int sb = gj & 1;    // S / P buffer
           const int vs = gj % NV;   // V ring stage
           if (j + 1 < it.n_tiles) issue_s(gj + 1, j + 2 == it.n_tiles);
-          if (j == 0) mbar_wait(o_free, (item_cnt & 1) ^ 1);  // epilogue of the previous item has drained O
+          // the epilogue of the item before last has drained this O buffer
+          if (j == 0) mbar_wait(&o_free[item_cnt & 1], ((item_cnt >> 1) & 1) ^ 1);
           const bool tr = p.trace != nullptr && blockIdx.x == 0 && gj < 64;
           if (tr) p.trace[gj * 16 + 8] = clock64();
           mbar_wait(&p_ready[sb], (gj >> 1) & 1);
@@ -252,7 +297,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk) {
             // A: 16 kv positions = 8 TMEM columns of packed bf16 pairs;  B: 16 kv rows = 2048 bytes further down
-            umma_bf16_ts(tmem_base + Cfg::O_COL, tmem_p + kk * 8, dv + static_cast<uint64_t>(kk * (2048 >> 4)),
+            umma_bf16_ts(tmem_base + Cfg::O_COL + (item_cnt & 1) * Cfg::O_STRIDE, tmem_p + kk * 8,
+                         dv + static_cast<uint64_t>(kk * (2048 >> 4)),
                          idesc_pv, (j | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&v_empty[vs]);
@@ -275,6 +321,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const float scale_log2 = p.scale * 1.4426950408889634f;
     const int pair_bar = 1 + quad;  // named barrier id (0 is __syncthreads)
     int item_cnt = 0, g = 0;
+
+    // state of the deferred epilogue of the previous item (kept small: the work index is re-decoded)
+    float pend_inv_l = 0.f;
+    int pend_w = -1, pend_g_last = 0;
+    auto run_epilogue = [&](int obuf) {
+      const Item pi = decode_item<CAUSAL>(p, pend_w, q_tiles);
+      epilogue_tile<HD>(&o_done[pend_g_last & 1], (pend_g_last >> 1) & 1, &o_free[obuf],
+                        tmem_base + lane_addr + Cfg::O_COL + obuf * Cfg::O_STRIDE + half * (HD / 2),
+                        stage_all + (warp_idx - 2) * (32 * 64), lane, quad, pend_inv_l, pi.len_q - pi.t * BM,
+                        p.o + (pi.o_row0 + pi.t * BM + quad * 32) * p.o_ld + pi.head * HD + half * (HD / 2), p.o_ld);
+    };
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
       const Item it = decode_item<CAUSAL>(p, w, q_tiles);
       if (!it.valid) continue;
@@ -327,7 +384,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           l_sum *= alpha;
           mbar_wait(&o_done[(gj - 1) & 1], ((gj - 1) >> 1) & 1);  // PV_{j-1} finished: O is stable until PV_j
           tcgen05_fence_after();
-          const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + half * (HD / 2);
+          const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + (item_cnt & 1) * Cfg::O_STRIDE + half * (HD / 2);
 #pragma unroll
           for (int c = 0; c < HD / 64; ++c) {
             uint32_t orow[32];
@@ -358,41 +415,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         tcgen05_fence_before();
         if (tr) p.trace[gj * 16 + 5] = clock64();
         mbar_arrive(&p_ready[buf]);
+        if (j == 0 && pend_w >= 0) {  // previous item's O: its last PV finished long ago, S(1)/PV(0) keep the pipe busy
+          run_epilogue((item_cnt - 1) & 1);
+          pend_w = -1;
+        }
       }
-      // ---- epilogue: O / l -> bf16 -> HBM (each thread of the pair writes HD/2 columns of its row) ----
+      // ---- item end: total row sum now (the exchange slots are reused by the next item); the epilogue itself is
+      //      deferred until the first score tile of the next item is with the tensor pipe ----
       xch[(4 + half) * BM + r_in_tile] = l_sum;
       asm volatile("bar.sync %0, 64;\n" ::"r"(pair_bar) : "memory");
       const float l_tot = l_sum + xch[(4 + (half ^ 1)) * BM + r_in_tile];
-      const int g_last = g + it.n_tiles - 1;
-      mbar_wait(&o_done[g_last & 1], (g_last >> 1) & 1);
-      tcgen05_fence_after();
-      const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-      const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + half * (HD / 2);
-      bf16* orow_ptr = p.o + (it.o_row0 + row) * p.o_ld + it.head * HD + half * (HD / 2);
-#pragma unroll
-      for (int c = 0; c < HD / 64; ++c) {
-        uint32_t orow[32];
-        tmem_ld_32x32b_x32(o_addr + c * 32, orow);
-        tmem_ld_wait();
-        if (row < it.len_q) {
-#pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            uint4 pkv;
-            pkv.x = pack_bf16x2(__uint_as_float(orow[v8 * 8 + 0]) * inv_l, __uint_as_float(orow[v8 * 8 + 1]) * inv_l);
-            pkv.y = pack_bf16x2(__uint_as_float(orow[v8 * 8 + 2]) * inv_l, __uint_as_float(orow[v8 * 8 + 3]) * inv_l);
-            pkv.z = pack_bf16x2(__uint_as_float(orow[v8 * 8 + 4]) * inv_l, __uint_as_float(orow[v8 * 8 + 5]) * inv_l);
-            pkv.w = pack_bf16x2(__uint_as_float(orow[v8 * 8 + 6]) * inv_l, __uint_as_float(orow[v8 * 8 + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(orow_ptr + c * 32 + v8 * 8) = pkv;
-          }
-        }
-      }
-      tcgen05_fence_before();
-      mbar_arrive(o_free);
-      // the sum slots are rewritten by the next item only after both threads passed this item's barrier and
-      // the next item's first per-tile barrier orders the max slots
+      pend_inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      pend_g_last = g + it.n_tiles - 1;
+      pend_w = w;
       g += it.n_tiles;
       ++item_cnt;
     }
+    if (pend_w >= 0) run_epilogue((item_cnt - 1) & 1);
   }
 
   tcgen05_fence_before();
