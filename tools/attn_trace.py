@@ -32,3 +32,8 @@ for g in range(2, 30):
     nxt = int(t[g + 1, 0])
     print(g, a[1] - a[0], a[2] - a[1], a[3] - a[2], a[4] - a[3], a[5] - a[4], nxt - a[5], "| mma: p_ready-wait", int(t[g, 9]) - int(t[g, 8]),
           "v", int(t[g, 10]) - int(t[g, 9]), "issue", int(t[g, 11]) - int(t[g, 10]), "| period", int(t[g + 1, 1]) - a[1])
+print("deferred epilogues (row = first tile of the next item): start->o_done wait, ->first tcgen05.ld, ->first chunk stored, ->end")
+for g in range(1, 40):
+    if int(t[g, 6]):
+        e = [int(t[g, k]) for k in (6, 7, 12, 13, 14)]
+        print(g, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], "total", e[4] - e[0], "| st_done->epi start", e[0] - int(t[g, 5]))
