@@ -22,6 +22,12 @@ def _has_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
+    # a hung kernel blocks inside cudaDeviceSynchronize where no Python signal handler runs: the "thread" method
+    # kills the process from a timer thread instead, so a deadlock fails the run instead of wedging the GPU box
+    for item in items:
+        if "gpu" in item.keywords:
+            own = item.get_closest_marker("timeout")
+            item.add_marker(pytest.mark.timeout(own.args[0] if own and own.args else 900, method="thread"))
     if _has_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")

@@ -239,6 +239,65 @@ def test_attention_decoder_causal_varlen_gqa(impl):
         off += L_
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("causal,d", [(1, 128), (0, 128), (0, 64), (1, 64)])
+def test_attention_many_ragged_items(impl, causal, d):
+    """Scheduling stress for the persistent kernel: 96 sequences of random length 0..400 x 8 heads = hundreds of
+    work items per CTA, most of them one or two kv tiles long (the item hand-over, the Q / O double buffers and the
+    deferred epilogue are exercised on every boundary), empty sequences in the list, GQA when causal."""
+    g = torch.Generator().manual_seed(10 + d + causal)
+    h, kvh = (8, 2) if causal else (8, 8)
+    lens = torch.randint(0, 401, (96,), generator=g).tolist()
+    lens[3] = 0
+    lens[50] = 0
+    lens[-1] = 1
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device="cuda", dtype=torch.int32)
+    total = sum(lens)
+    W = (h + 2 * kvh) * d
+    torch.manual_seed(11)
+    qkv = rnd(total, W)
+    for rep in range(3):  # back-to-back launches: barrier state / TMEM are per launch, results must not change
+        o = attention(qkv, qkv[:, h * d:], qkv[:, (h + kvh) * d:], total, h * d, q_ld=W, k_ld=W, v_ld=W, cu_q=cu,
+                      cu_k=cu, seqlen_q=max(lens), seqlen_k=max(lens), batch=len(lens), heads=h, kv_heads=kvh,
+                      head_dim=d, scale=d ** -0.5, causal=causal, total_q_rows=total, total_k_rows=total, impl=impl)
+        if rep == 0:
+            first = o.clone()
+        else:
+            assert torch.equal(o, first), "attention is not deterministic across launches"
+    off = 0
+    worst = 0.0
+    for L_ in lens:
+        if L_ == 0:
+            continue
+        blk = qkv[off:off + L_].float()
+        q = blk[:, :h * d].view(L_, h, d).permute(1, 0, 2)[None]
+        k = blk[:, h * d:(h + kvh) * d].view(L_, kvh, d).permute(1, 0, 2)[None].repeat_interleave(h // kvh, dim=1)
+        v = blk[:, (h + kvh) * d:].view(L_, kvh, d).permute(1, 0, 2)[None].repeat_interleave(h // kvh, dim=1)
+        ref = ref_attention(q, k, v, d ** -0.5, bool(causal))[0].permute(1, 0, 2).reshape(L_, h * d)
+        worst = max(worst, rel_l2(o[off:off + L_], ref))
+        off += L_
+    assert worst <= BF16_REL_L2, f"worst per-sequence rel-L2 {worst:.3e}"
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("impl", IMPLS)
+def test_attention_cross_lengths_causal_offset(impl):
+    """Sq != Sk with the causal diagonal anchored at the END of the keys (query i sees keys <= i + Sk - Sq), several
+    batches, so a CTA walks items with different tile counts."""
+    torch.manual_seed(12)
+    B, h, d, Sq, Sk = 5, 4, 128, 200, 520
+    q, kv = rnd(B * Sq, h * d), rnd(B * Sk, 2 * h * d)
+    o = attention(q, kv, kv[:, h * d:], B * Sq, h * d, q_ld=h * d, k_ld=2 * h * d, v_ld=2 * h * d, seqlen_q=Sq,
+                  seqlen_k=Sk, q_batch_rows=Sq, k_batch_rows=Sk, o_batch_rows=Sq, batch=B, heads=h, kv_heads=h,
+                  head_dim=d, scale=d ** -0.5, causal=1, impl=impl)
+    qf = q.float().view(B, Sq, h, d).permute(0, 2, 1, 3)
+    kf = kv[:, :h * d].float().view(B, Sk, h, d).permute(0, 2, 1, 3)
+    vf = kv[:, h * d:].float().view(B, Sk, h, d).permute(0, 2, 1, 3)
+    ref = ref_attention(qf, kf, vf, d ** -0.5, True).permute(0, 2, 1, 3).reshape(B * Sq, h * d)
+    assert_close_bf16(o, ref, "attention Sq != Sk causal")
+
+
 @pytest.mark.parametrize("D", [128, 1024, 4096, 5120])
 def test_layernorm_rmsnorm(D):
     L = _lib()
