@@ -190,7 +190,10 @@ int slime_decoder_decode_fwd(slime_ctx* ctx, const void* x, const int32_t* lens,
  *             offsets centre-crop; its tiles, row-major, are crops first_crop, first_crop+1, ... of `out`
  *   out     : [n_crops, 3, crop, crop] in out_dtype (0 bf16, 1 fp32, 2 fp16), value = lut[c][byte]
  * `jobs` and `lut` ([3][256] floats: the processor's rescale + normalise of every byte value) are HOST arrays;
- * src / out / ws are device pointers.  Needs no slime_ctx (no weights). */
+ * src / out / ws are device pointers.  Needs no slime_ctx (no weights).
+ * Alignment: src 4 bytes, every src_offset a multiple of 4 and the buffer readable up to the next multiple of 4 past
+ * each image (the kernels fetch the interleaved bytes as aligned 32-bit words); out 16 bytes; ws 256 bytes;
+ * crop a multiple of 4. */
 typedef struct slime_resize_job {
   int64_t src_offset;
   int32_t src_w, src_h;
