@@ -37,6 +37,10 @@ extern "C" {
 #define SLIME_FLAG_LEFT_PAD 1u         /* config.tokenizer_padding_side == "left" */
 #define SLIME_FLAG_USE_GLOBAL_ONLY 2u  /* config.use_global_only */
 #define SLIME_FLAG_USE_LOCAL_ONLY 4u   /* config.use_local_only */
+/* llm.layers.N.qkv_w was registered with the q / k rows of every head interleaved - row 2i = q_proj row i, row
+ * 2i+1 = q_proj row i + head_dim/2 (same for k_proj) - so the rotary embedding (HF llama/modeling_llama.py:152-176)
+ * is applied in the epilogue of the QKV GEMM instead of by a separate pass over q and k. */
+#define SLIME_FLAG_ROPE_INTERLEAVED 8u
 
 typedef struct slime_ctx slime_ctx;
 
@@ -222,14 +226,29 @@ int slime_op_layernorm(const void* x, const void* w, const void* b, void* y, int
                        void* stream);
 int slime_op_rmsnorm(const void* x, const void* w, void* y, int rows, int dim, float eps, void* stream);
 int slime_op_rope(slime_ctx* ctx, void* qkv, int ld, int rows, const int32_t* pos_ids, void* stream);
+/* Packed Llama QKV projection + RoPE of the q / k heads exactly as the decoder stage runs it: x [rows, hidden] times
+ * qkv_w [(heads + 2 kv_heads) * head_dim, hidden]^T -> qkv [rows, (heads + 2 kv_heads) * head_dim].  With
+ * SLIME_FLAG_ROPE_INTERLEAVED in the ctx's desc, qkv_w must hold the interleaved q / k rows and the q / k columns of the
+ * result come out in that interleaved feature order (rotation fused into the GEMM epilogue); without it the plain
+ * layout is used (GEMM, then the in-place rotation pass). */
+int slime_op_qkv_rope(slime_ctx* ctx, const void* x, const void* qkv_w, int rows, const int32_t* pos_ids, void* qkv,
+                      void* stream);
 
 /* ---- accounting: kernels launched by the library since load; optional CUDA-event profiling of the
  * library's own launches (class 0 = tcgen05 GEMM [work = FLOPs], 1 = attention, 2 = other) ---- */
 /* GEMM kernel selection: 0 = 1-CTA kernel only, 1 = force the 2-CTA (cta_group::2) kernel, 2 = 2-CTA for problems
  * that fill the GPU, -1 = back to the default (SLIME_GEMM_2CTA environment variable / build default). */
 int slime_gemm_set_2cta_mode(int mode);
+/* GEMM epilogue HBM access pattern: 0 = every thread stores its own row, 1 = chunks transposed through shared memory
+ * (stores and residual loads of 8 rows x 64 contiguous bytes per instruction).  Never called: SLIME_GEMM_EPI_MODE
+ * environment variable, else the build default. */
+int slime_gemm_set_epi_mode(int mode);
 /* debug: CTA 0 of the tcgen05 attention kernel stamps clock64() of its first 64 tiles into buf [64][16] (NULL = off) */
 int slime_attention_set_trace(long long* buf);
+/* softmax arithmetic of the tcgen05 attention kernel: 0 = scalar FFMA + MUFU.EX2; 1 + 2*P = packed fp32 pairs
+ * (FFMA2 / FADD2) with P of every 8 pairs exponentiated by a polynomial on the FMA pipe instead of the SFU
+ * (P = 0, 2, 3, 4 -> 1, 5, 7, 9); -1 = back to the default (SLIME_ATTN_VARIANT / build default). */
+int slime_attention_set_variant(int variant);
 long long slime_launch_count(void);
 int slime_profile_enable(int on);
 int slime_profile_collect(double* ms3, double* work3, long long* launches3);

@@ -38,6 +38,7 @@ def torch_dtype(variant: str):
 SLIME_FLAG_LEFT_PAD = 1
 SLIME_FLAG_USE_GLOBAL_ONLY = 2
 SLIME_FLAG_USE_LOCAL_ONLY = 4
+SLIME_FLAG_ROPE_INTERLEAVED = 8
 
 EPI_NONE, EPI_QUICK_GELU, EPI_GELU_ERF, EPI_SWIGLU = 0, 1, 2, 3
 
@@ -133,8 +134,11 @@ SIGNATURES = {
     "slime_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "slime_op_rmsnorm": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
     "slime_op_rope": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "slime_op_qkv_rope": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "slime_gemm_set_2cta_mode": (_i, [_i]),
+    "slime_gemm_set_epi_mode": (_i, [_i]),
     "slime_attention_set_trace": (_i, [_vp]),
+    "slime_attention_set_variant": (_i, [_i]),
     "slime_launch_count": (C.c_longlong, []),
     "slime_profile_enable": (_i, [_i]),
     "slime_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -129,6 +129,37 @@ int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, in
   return slime_launch_gemm(A, lda, W, ldw, p, epi, c->num_sms, s);
 }
 
+// Packed Llama QKV projection + rotary embedding of the q / k heads (HF llama/modeling_llama.py:152-176, 262-288).
+// With SLIME_FLAG_ROPE_INTERLEAVED the q / k weight rows of every head were interleaved at load so a feature pair
+// (i, i + hd/2) sits in adjacent accumulator columns and the rotation happens in the GEMM epilogue on the fp32
+// accumulators (q and k stay in that permuted feature order: q.k is invariant under a common permutation, and
+// the KV cache / decode step use the same order).  Without the flag: plain GEMM, then rope_kernel in place.
+int qkv_rope(slime_ctx* c, const bf16* x, const bf16* qkv_w, int rows, const int* pos, bf16* qkv, cudaStream_t s) {
+  const slime_model_desc& d = c->d;
+  const int H = d.hidden, hd = d.head_dim, QKV = (d.heads + 2 * d.kv_heads) * hd;
+  if ((d.flags & SLIME_FLAG_ROPE_INTERLEAVED) == 0) {
+    SLIME_PROPAGATE(gemm(c, x, H, qkv_w, H, rows, QKV, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, qkv, nullptr,
+                         QKV, s));
+    return slime_launch_rope(qkv, QKV, rows, d.heads, d.kv_heads, hd, pos, c->rope_table, d.max_pos, s);
+  }
+  GemmParams p;
+  p.M = rows; p.N = QKV; p.K = H;
+  p.bias = nullptr;
+  p.residual = nullptr;
+  p.res_ld = 0;
+  p.res_period = 0;
+  p.row_map = nullptr;
+  p.out = qkv;
+  p.out_f32 = nullptr;
+  p.out_ld = QKV;
+  p.rope_pos = pos;
+  p.rope_table = reinterpret_cast<const float2*>(c->rope_table);
+  p.rope_half = hd / 2;
+  p.rope_cols = (d.heads + d.kv_heads) * hd;
+  p.rope_max_pos = d.max_pos;
+  return slime_launch_gemm(x, H, qkv_w, H, p, GEMM_EPI_ROPE, c->num_sms, s);
+}
+
 // ------------------------------------------------------------------------------------------
 // stage bodies (dry == true: only account for workspace)
 // ------------------------------------------------------------------------------------------
@@ -295,9 +326,7 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
   for (int l = 0; l < d.layers; ++l) {
     const LlmLayer& L = c->llm[l];
     SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.in_norm_w, t, H, total, H, d.rms_eps, nullptr, s));
-    SLIME_PROPAGATE(gemm(c, t, H, L.qkv_w, H, total, QKV, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, qkv,
-                         nullptr, QKV, s));
-    SLIME_PROPAGATE(slime_launch_rope(qkv, QKV, total, d.heads, d.kv_heads, hd, pos_ids, c->rope_table, d.max_pos, s));
+    SLIME_PROPAGATE(qkv_rope(c, t, L.qkv_w, total, pos_ids, qkv, s));
     if (c->kv_cache != nullptr) {
       // keep K (post-RoPE) and V of every real token for the decode steps that follow the prefill
       if (l == 0) SLIME_PROPAGATE(slime_launch_cache_rows(cu, pos_ids, B, total, c->kv_cache_len, cache_rows, s));
@@ -361,9 +390,7 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
     bf16* kc = c->kv_cache + (static_cast<size_t>(l) * 2 + 0) * plane;
     bf16* vc = c->kv_cache + (static_cast<size_t>(l) * 2 + 1) * plane;
     SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.in_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
-    SLIME_PROPAGATE(gemm(c, t, H, L.qkv_w, H, B, QKV, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, qkv, nullptr,
-                         QKV, s));
-    SLIME_PROPAGATE(slime_launch_rope(qkv, QKV, B, d.heads, d.kv_heads, hd, lens, c->rope_table, d.max_pos, s));
+    SLIME_PROPAGATE(qkv_rope(c, t, L.qkv_w, B, lens, qkv, s));
     SLIME_PROPAGATE(slime_launch_scatter_rows(qkv + QD, QKV, kc, KD, B, KD, rows, s));
     SLIME_PROPAGATE(slime_launch_scatter_rows(qkv + QD + KD, QKV, vc, KD, B, KD, rows, s));
     SLIME_PROPAGATE(slime_launch_decode_attention(qkv, QKV, kc, vc, c->kv_cache_len, lens, B, d.heads, d.kv_heads, hd,
@@ -886,6 +913,14 @@ int slime_op_rope(slime_ctx* ctx, void* qkv, int ld, int rows, const int32_t* po
   SLIME_REQUIRE(ctx != nullptr, "rope: null context");
   return slime_launch_rope(static_cast<bf16*>(qkv), ld, rows, ctx->d.heads, ctx->d.kv_heads, ctx->d.head_dim, pos_ids,
                            ctx->rope_table, ctx->d.max_pos, static_cast<cudaStream_t>(stream));
+}
+int slime_op_qkv_rope(slime_ctx* ctx, const void* x, const void* qkv_w, int rows, const int32_t* pos_ids, void* qkv,
+                      void* stream) {
+  SLIME_REQUIRE(ctx != nullptr && x != nullptr && qkv_w != nullptr && qkv != nullptr && pos_ids != nullptr,
+                "qkv_rope: null argument");
+  if (rows <= 0) return SLIME_OK;
+  return qkv_rope(ctx, static_cast<const bf16*>(x), static_cast<const bf16*>(qkv_w), rows, pos_ids,
+                  static_cast<bf16*>(qkv), static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

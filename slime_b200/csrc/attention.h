@@ -8,6 +8,12 @@
 #define SLIME_ATTN_DEFAULT_IMPL 2
 #endif
 
+// softmax arithmetic variant of the tcgen05 kernel (attention_tc.cu: 0 scalar MUFU, 1 + 2*P packed pairs with P of
+// every 8 pairs exponentiated on the FMA pipe)
+#ifndef SLIME_ATTN_VARIANT_DEFAULT
+#define SLIME_ATTN_VARIANT_DEFAULT 5
+#endif
+
 struct AttnParams {
   const bf16* q;
   const bf16* k;

@@ -22,6 +22,8 @@
 // 144/576 shared queries x 576 keys), Llama decoder (h x 128, causal, GQA, packed variable-length rows).
 #include "attention.h"
 #include "errors.h"
+#include <cstdlib>
+
 #include "gemm.h"
 
 namespace {
@@ -42,7 +44,10 @@ struct TcCfg {
   static constexpr int NK = HD == 128 ? 2 : 4;
   static constexpr int NV = HD == 128 ? 2 : 3;
   static constexpr int BAR_BYTES = 256;            // 28 mbarriers + the TMEM base address
-  static constexpr int XCH_BYTES = 6 * 128 * 4;    // half-row max (2 slots x 2 halves) and item sums (2 halves)
+  // exchange area between the two softmax warps of a row.  column split: half-row max (2 slots x 2 halves) and item
+  // sums (2 halves) = 6 x 128 floats;  kv split: the reference max handed from tile to tile (128 floats), the
+  // per-item (sum, max) of both groups for 2 items in flight (2 x 2 x 128 float2) and the ring head counter
+  static constexpr int XCH_BYTES = 128 * 4 + 2 * 2 * 128 * 8 + 64;
   static constexpr int STAGE_BYTES = 8 * 32 * 64;  // epilogue: per softmax warp 32 rows x 64 B (one 32-column chunk)
   static constexpr int RING_BYTES = 8 * 64;        // decoded work items, written by the producer
   static constexpr int SMEM_RAW = 1024 + TILE_BYTES * (2 + NK + NV) + BAR_BYTES + XCH_BYTES + STAGE_BYTES + RING_BYTES;
@@ -59,6 +64,140 @@ SLIME_DEVINL float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// ---- packed fp32 pairs (FFMA2 / FADD2: one issue slot for two lanes of work) ----
+SLIME_DEVINL float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+SLIME_DEVINL float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
+// 2^x for a pair WITHOUT the SFU: Cody-Waite split x = n + f, n = round(x), f in [-0.5, 0.5], minimax polynomial
+// for 2^f on the FMA pipe (relative error 1.0e-4 at degree 3 - far below the bf16 rounding of P at 3.9e-3 - and
+// 2.9e-6 at degree 4 for the fp16 build), n added into the exponent field.  The SFUs retire 16 ex2 per clock per
+// SM, which makes a 128 x 128 score tile cost as much SFU time as tensor time (profiles/r01_attention_clock_trace_v2.txt);
+// moving a fraction of the exponentials onto the FMA pipe shortens that phase.  Inputs are <= 8 (lazy rescale)
+// and clamped at -126 so the exponent arithmetic cannot wrap.
+SLIME_DEVINL float2 exp2_poly2(float2 x) {
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23: x + MAGIC holds round(x) in its low mantissa bits
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 xr = fadd2(x, make_float2(MAGIC, MAGIC));
+  const float2 n = fadd2(xr, make_float2(-MAGIC, -MAGIC));
+  const float2 f = ffma2(n, make_float2(-1.0f, -1.0f), x);
+#ifdef SLIME_FP16
+  float2 q = ffma2(make_float2(0.009582850150763988f, 0.009582850150763988f), f,
+                   make_float2(0.055906426161527634f, 0.055906426161527634f));
+  q = ffma2(q, f, make_float2(0.24024099111557007f, 0.24024099111557007f));
+  q = ffma2(q, f, make_float2(0.6931241750717163f, 0.6931241750717163f));
+#else
+  float2 q = ffma2(make_float2(0.05500892549753189f, 0.05500892549753189f), f,
+                   make_float2(0.2422109693288803f, 0.2422109693288803f));
+  q = ffma2(q, f, make_float2(0.6932829022407532f, 0.6932829022407532f));
+#endif
+  q = ffma2(q, f, make_float2(1.0f, 1.0f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(xr.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(xr.y) << 23));
+  return r;
+}
+
+// Softmax arithmetic variant of attn_tc_kernel (template parameter VAR; SLIME_ATTN_VARIANT / slime_attention_set_variant):
+//   0        : scalar FFMA + MUFU.EX2 per element
+//   1 + 2*P  : packed pairs (FFMA2 scale, FADD2 row sums) with P of every 8 pairs exponentiated by exp2_poly2 on
+//              the FMA pipe instead of the SFU (P = 0, 2, 3, 4); tiles that need masking keep the scalar path
+//              (masked scores are -inf, which the polynomial path would turn into 2^-126 instead of 0)
+SLIME_DEVINL constexpr bool pair_is_poly(int c, int P) {
+  // spread the polynomial pairs evenly over each group of 8 so SFU and FMA work interleave
+  return P == 2 ? ((c & 3) == 1) : P == 3 ? ((c & 7) == 1 || (c & 7) == 4 || (c & 7) == 6) : P == 4 ? ((c & 1) == 1) : false;
+}
+
+// ---- named barriers (id 0 is __syncthreads) ----
+SLIME_DEVINL void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+SLIME_DEVINL void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+SLIME_DEVINL int ld_acquire_cta(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];\n" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+SLIME_DEVINL void st_release_cta(int* p, int v) {
+  asm volatile("st.release.cta.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// max over 64 score columns held in registers; with `need_mask` columns beyond `limit` are set to -inf in place
+SLIME_DEVINL float rowmax64(uint32_t (&sr)[64], bool need_mask, int col_base, int limit) {
+  float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains
+  if (need_mask) {
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      float v = __uint_as_float(sr[c]);
+      if (col_base + c > limit) v = -INFINITY;
+      sr[c] = __float_as_uint(v);
+      mx4[c & 3] = fmaxf(mx4[c & 3], v);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 64; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(sr[c]));
+  }
+  return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+}
+
+// P = 2^(s * scale_log2 - m_scaled) for 64 columns -> 32 packed bf16 pairs; returns the fp32 row sum of the 64 values.
+// `packed_ok` = the tile needs no masking (no -inf inputs), so the packed / polynomial arithmetic of VAR may be used.
+template <int VAR>
+SLIME_DEVINL float softmax_exp64(const uint32_t (&sr)[64], bool packed_ok, float scale_log2, float m_scaled,
+                                 uint32_t (&pk)[32]) {
+  if (VAR != 0 && packed_ok) {
+    constexpr int P = VAR >> 1;
+    const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_scaled, -m_scaled);
+    float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), sc2, nm2);
+      float2 pv;
+      if (pair_is_poly(c, P)) {
+        pv = exp2_poly2(x);
+      } else {
+        pv.x = fast_exp2(x.x);
+        pv.y = fast_exp2(x.y);
+      }
+      acc[c & 1] = fadd2(acc[c & 1], pv);
+      pk[c] = pack_bf16x2(pv.x, pv.y);
+    }
+    return (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
+  }
+  float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_scaled));
+    const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_scaled));
+    ps4[c & 3] += p0 + p1;
+    pk[c] = pack_bf16x2(p0, p1);
+  }
+  return (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
 }
 
 // One unit of work: a 128-row query tile of one (sequence, head).  Decoded once by the producer warp and handed to
@@ -133,7 +272,7 @@ SLIME_DEVINL void epilogue_tile(uint64_t* o_done_bar, uint32_t o_done_parity, ui
                                 uint8_t* stage, int lane, int quad, float inv_l, int rows_valid, bf16* out, int o_ld,
                                 long long* tr) {
   if (tr) tr[6] = clock64();
-  mbar_wait(o_done_bar, o_done_parity);
+  if (o_done_bar != nullptr) mbar_wait(o_done_bar, o_done_parity);  // nullptr: the caller has already waited
   tcgen05_fence_after();
   if (tr) tr[7] = clock64();
 #pragma unroll
@@ -167,7 +306,7 @@ SLIME_DEVINL void epilogue_tile(uint64_t* o_done_bar, uint32_t o_done_parity, ui
   if (tr) tr[14] = clock64();
 }
 
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, int VAR, bool SPLIT>
 __global__ void __launch_bounds__(NT, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p, int q_tiles, int total_items) {
@@ -195,6 +334,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   float* xch = reinterpret_cast<float*>(aux + Cfg::BAR_BYTES);
   uint8_t* stage_all = aux + Cfg::BAR_BYTES + Cfg::XCH_BYTES;  // [8 warps][32 rows][64 B]
   Item* ring = reinterpret_cast<Item*>(aux + Cfg::BAR_BYTES + Cfg::XCH_BYTES + Cfg::STAGE_BYTES);  // [8] x 64 B
+  int* ring_head = reinterpret_cast<int*>(aux + Cfg::BAR_BYTES + Cfg::XCH_BYTES - 64);  // items posted so far
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -207,7 +347,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 256);
+      mbar_init(&p_ready[s], SPLIT ? 128 : 256);  // kv split: only the 4 warps of the tile's group arrive
       mbar_init(&o_done[s], 1);
       mbar_init(&o_free[s], 256);
     }
@@ -219,6 +359,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
+    *ring_head = 0;
     fence_barrier_init();
   } else if (warp_idx == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
@@ -250,6 +391,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int qb = k & 1;
         mbar_wait(&q_empty[qb], ((k >> 1) & 1) ^ 1);  // last S MMA of item k-2 done (its ring slot is long dead)
         ring[k & 7] = it;
+        st_release_cta(ring_head, k + 1);  // kv-split softmax warps learn about item k from this counter
         if (it.n_tiles > 0) {
           mbar_arrive_expect_tx(&q_full[qb], Cfg::TILE_BYTES);
 #pragma unroll
@@ -381,6 +523,173 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         more = more_next;
       }
     }
+  } else if constexpr (SPLIT) {
+    // ================================ softmax + epilogue, kv-split (2 groups x 4 warps) ================
+    // Group G = warps {2..5} / {6..9} handles the kv tiles with global index gj & 1 == G - i.e. S / P buffer G -
+    // with ONE thread per query row (TMEM lane r belongs to warp quadrant r / 32 of both groups).  While one group
+    // exponentiates tile gj the other finds the row max of tile gj+1, and the 1024 tensor-pipe cycles a group waits
+    // for its next S (PV of its last tile, then the S MMA into the same buffer) are filled by the other group's
+    // softmax - the column-split version leaves SFU and FMA pipes idle in exactly those phases
+    // (profiles/r01_attention_clock_trace_v2.txt: ~900 of 2150 cycles per tile).
+    //   * the reference max of a row travels from tile to tile through shared memory (mail[r]) with a named-barrier
+    //     hand-off per tile (arrive by the publisher, sync by the next tile's warp): tile gj's warp decides whether
+    //     the max grows (lazy rescale, as before) after it has seen the decision of tile gj-1;
+    //   * each group keeps its own partial row sum, relative to the last reference max it has seen; both post
+    //     (sum, max) per item and combine them in the deferred epilogue;
+    //   * O is rescaled (rare) by the deciding thread over all HD columns after PV(gj-1) has completed.
+    const int quad = warp_idx & 3;
+    const int G = (warp_idx - 2) >> 2;
+    const int r_in_tile = quad * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const float scale_log2 = p.scale * 1.4426950408889634f;
+    const int pair_bar = 1 + quad;            // both warps of a row, blocking (deferred epilogue)
+    const int hand_in = 5 + (1 - G) * 4 + quad;   // published by the other group
+    const int hand_out = 5 + G * 4 + quad;        // published by this group
+    float* mail = xch;                                             // [128] reference max after the latest decision
+    float2* post = reinterpret_cast<float2*>(xch + 128);           // [2 items][2 groups][128] (sum, max)
+    const uint32_t s_base = tmem_base + lane_addr + (G ? Cfg::S_COL1 : Cfg::S_COL0);
+    int g = 0;
+    int pend_k = -1, pend_g_last = -1;
+    // The last PV of the pending item (global tile pend_g_last) commits o_done[pend_g_last & 1]; the NEXT commit on that
+    // barrier is PV(pend_g_last + 2).  A parity wait must not fall two phases behind, so each group waits for the
+    // pending item's O BEFORE it releases its own first tile of the following item (PV(pend_g_last + 2) needs that
+    // tile's P, or - in-order issue - the P of pend_g_last + 1), never afterwards.
+    auto wait_pending_o = [&]() { mbar_wait(&o_done[pend_g_last & 1], (pend_g_last >> 1) & 1); };
+    auto run_epilogue = [&](long long* tr) {
+      // both groups have posted their (sum, max) of item pend_k once both are here
+      named_bar_sync(pair_bar, 64);
+      const float2 a = post[((pend_k & 1) * 2 + 0) * 128 + r_in_tile];
+      const float2 b = post[((pend_k & 1) * 2 + 1) * 128 + r_in_tile];
+      const float m_fin = fmaxf(a.y, b.y);
+      float l_tot = 0.f;
+      if (a.y != -INFINITY) l_tot += a.x * fast_exp2((a.y - m_fin) * scale_log2);
+      if (b.y != -INFINITY) l_tot += b.x * fast_exp2((b.y - m_fin) * scale_log2);
+      const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      const Item* pi = &ring[pend_k & 7];
+      const int obuf = pend_k & 1;
+      epilogue_tile<HD>(nullptr, 0, &o_free[obuf],
+                        tmem_base + lane_addr + Cfg::O_COL + obuf * Cfg::O_STRIDE + G * (HD / 2),
+                        stage_all + (warp_idx - 2) * (32 * 64), lane, quad, inv_l, pi->len_q - pi->t * BM,
+                        p.o + (pi->o_row0 + pi->t * BM + quad * 32) * p.o_ld + pi->head * HD + G * (HD / 2), p.o_ld, tr);
+      pend_k = -1;
+    };
+    for (int k = 0;; ++k) {
+      while (ld_acquire_cta(ring_head) <= k) {
+      }
+      const int n_tiles = ring[k & 7].n_tiles;
+      if (n_tiles == 0) break;
+      const int more = ring[k & 7].more;
+      const int it_t = ring[k & 7].t, len_k = ring[k & 7].len_k, causal_off = ring[k & 7].causal_off;
+      const int row = it_t * BM + r_in_tile;  // query index inside the sequence
+      const int limit = CAUSAL ? min(len_k - 1, row + causal_off) : len_k - 1;  // last visible column of this row
+      float m_cur = -INFINITY;  // reference max this thread's partial sum is relative to
+      float l_part = 0.f;       // sum over the tiles of THIS group
+      bool first_done = false;
+      for (int j = (g & 1) == G ? 0 : 1; j < n_tiles; j += 2) {
+        const int gj = g + j;
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp_idx == 2 + 4 * G && lane == 0 && gj < 64;
+        if (tr) p.trace[gj * 16 + 0] = clock64();
+        mbar_wait(&s_full[G], (gj >> 1) & 1);
+        tcgen05_fence_after();
+        if (tr) p.trace[gj * 16 + 1] = clock64();
+        const bool need_mask = (j * BN + BN > len_k) || (CAUSAL && (j * BN + BN - 1 > it_t * BM + causal_off));
+        // ---- pass 1: row max over the 128 columns
+        float m_tile;
+        {
+          uint32_t sr[64];
+          tmem_ld_32x32b_x32(s_base, sr);
+          tmem_ld_32x32b_x32(s_base + 32, sr + 32);
+          tmem_ld_wait();
+          if (tr) p.trace[gj * 16 + 2] = clock64();
+          m_tile = rowmax64(sr, need_mask, j * BN, limit);
+          tmem_ld_32x32b_x32(s_base + 64, sr);
+          tmem_ld_32x32b_x32(s_base + 96, sr + 32);
+          tmem_ld_wait();
+          m_tile = fmaxf(m_tile, rowmax64(sr, need_mask, j * BN + 64, limit));
+        }
+        // ---- the decision of the previous tile (made by the other group; every tile takes part in the chain so the
+        //      barrier use stays uniform - the value only matters inside an item)
+        if (gj > 0) {
+          named_bar_sync(hand_in, 64);
+          if (j > 0) {
+            const float m_prev = mail[r_in_tile];
+            if (m_prev != m_cur) {  // the other group moved the reference: bring this group's partial sum along
+              l_part = (m_cur == -INFINITY) ? 0.f : l_part * fast_exp2((m_cur - m_prev) * scale_log2);
+              m_cur = m_prev;
+            }
+          }
+        }
+        if (tr) p.trace[gj * 16 + 3] = clock64();
+        // ---- lazy rescale: only move the reference max when it grew by more than 2^8 (or on the first tile)
+        bool grow = (m_tile - m_cur) * scale_log2 > RESCALE_THRESHOLD;
+        if (m_tile == -INFINITY) grow = false;
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2((m_cur - m_tile) * scale_log2) : 1.0f;  // m_cur == -inf -> 0
+          l_part *= alpha;
+          mbar_wait(&o_done[(gj - 1) & 1], ((gj - 1) >> 1) & 1);  // PV(gj-1) finished: O is stable until PV(gj)
+          tcgen05_fence_after();
+          const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + (k & 1) * Cfg::O_STRIDE;
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t orow[32];
+            tmem_ld_32x32b_x32(o_addr + c * 32, orow);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr + c * 32, orow);
+          }
+          tmem_st_wait();
+        }
+        if (grow) m_cur = m_tile;
+        mail[r_in_tile] = m_cur;
+        __threadfence_block();
+        named_bar_arrive(hand_out, 64);
+        const float m_scaled = (m_cur == -INFINITY) ? 0.f : m_cur * scale_log2;
+        // ---- pass 2: exponentials, 64 columns at a time; P (bf16 pairs) overwrites the S columns just consumed
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t sr[64];
+          tmem_ld_32x32b_x32(s_base + hh * 64, sr);
+          tmem_ld_32x32b_x32(s_base + hh * 64 + 32, sr + 32);
+          tmem_ld_wait();
+          if (need_mask) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (j * BN + hh * 64 + c > limit) sr[c] = __float_as_uint(-INFINITY);
+          }
+          uint32_t pk[32];
+          l_part += softmax_exp64<VAR>(sr, !need_mask, scale_log2, m_scaled, pk);
+          tmem_st_32x32b_x32(s_base + hh * 32, pk);
+        }
+        if (tr) p.trace[gj * 16 + 4] = clock64();
+        tmem_st_wait();
+        tcgen05_fence_before();
+        if (tr) p.trace[gj * 16 + 5] = clock64();
+        if (!first_done && pend_k >= 0) wait_pending_o();
+        mbar_arrive(&p_ready[G]);
+        if (!first_done) {
+          first_done = true;
+          // previous item's O: its last PV finished long ago; the other group and the tensor pipe keep going
+          if (pend_k >= 0) run_epilogue(tr ? p.trace + gj * 16 : nullptr);
+        }
+      }
+      if (!first_done && pend_k >= 0) {  // this group has no tile in a one-tile item
+        wait_pending_o();
+        run_epilogue(nullptr);
+      }
+      // ---- item end: post this group's (sum, max); combined in the deferred epilogue
+      post[((k & 1) * 2 + G) * 128 + r_in_tile] = make_float2(l_part, m_cur);
+      pend_k = k;
+      pend_g_last = g + n_tiles - 1;
+      g += n_tiles;
+      if (!more) break;
+    }
+    if (pend_k >= 0) {
+      wait_pending_o();
+      run_epilogue(nullptr);
+    }
+    // the last tile's publisher arrived on a hand-off barrier nobody synchronises on: complete it
+    if (g > 0 && (g & 1) == G) named_bar_sync(hand_in, 64);
   } else {
     // ================================ softmax + epilogue (8 warps) ================
     // Two threads per query row: warps w and w+4 share TMEM lane quadrant w % 4 and split the 128 score
@@ -481,15 +790,35 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * scale_log2;
 
         uint32_t pk[32];
-        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (VAR != 0 && !need_mask) {
+          constexpr int P = VAR >> 1;
+          const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_scaled, -m_scaled);
+          float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_scaled));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_scaled));
-          ps4[c & 3] += p0 + p1;
-          pk[c] = pack_bf16x2(p0, p1);
+          for (int c = 0; c < 32; ++c) {
+            const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), sc2, nm2);
+            float2 pv;
+            if (pair_is_poly(c, P)) {
+              pv = exp2_poly2(x);
+            } else {
+              pv.x = fast_exp2(x.x);
+              pv.y = fast_exp2(x.y);
+            }
+            acc[c & 1] = fadd2(acc[c & 1], pv);
+            pk[c] = pack_bf16x2(pv.x, pv.y);
+          }
+          l_sum += (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
+        } else {
+          float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_scaled));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_scaled));
+            ps4[c & 3] += p0 + p1;
+            pk[c] = pack_bf16x2(p0, p1);
+          }
+          l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         }
-        l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         if (tr) p.trace[gj * 16 + 4] = clock64();
         tmem_st_32x32b_x32(s_base + half * 32, pk);  // P: 64 packed columns per row, this thread's half
         tmem_st_wait();
@@ -523,10 +852,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   }
 }
 
-template <int HD, bool CAUSAL>
-int launch_tc(const AttnParams& p, int num_sms, cudaStream_t stream) {
+template <int HD, bool CAUSAL, int VAR, bool SPLIT>
+int launch_tc_var(const AttnParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = TcCfg<HD>;
-  auto kern = attn_tc_kernel<HD, CAUSAL>;
+  auto kern = attn_tc_kernel<HD, CAUSAL, VAR, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
     SLIME_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -555,7 +884,42 @@ int launch_tc(const AttnParams& p, int num_sms, cudaStream_t stream) {
   return SLIME_OK;
 }
 
+int g_attn_variant = -1;  // -1: read SLIME_ATTN_VARIANT / the compile-time default on first use
+
+template <int HD, bool CAUSAL>
+int launch_tc(const AttnParams& p, int num_sms, cudaStream_t stream) {
+  if (g_attn_variant < 0) {
+    const char* e = getenv("SLIME_ATTN_VARIANT");
+    g_attn_variant = e != nullptr ? atoi(e) : SLIME_ATTN_VARIANT_DEFAULT;
+  }
+  switch (g_attn_variant) {
+    case 0: return launch_tc_var<HD, CAUSAL, 0, false>(p, num_sms, stream);
+    case 1: return launch_tc_var<HD, CAUSAL, 1, false>(p, num_sms, stream);
+    case 5: return launch_tc_var<HD, CAUSAL, 5, false>(p, num_sms, stream);
+    case 7: return launch_tc_var<HD, CAUSAL, 7, false>(p, num_sms, stream);
+    case 9: return launch_tc_var<HD, CAUSAL, 9, false>(p, num_sms, stream);
+    case 16: return launch_tc_var<HD, CAUSAL, 0, true>(p, num_sms, stream);
+    case 21: return launch_tc_var<HD, CAUSAL, 5, true>(p, num_sms, stream);
+    case 23: return launch_tc_var<HD, CAUSAL, 7, true>(p, num_sms, stream);
+    case 25: return launch_tc_var<HD, CAUSAL, 9, true>(p, num_sms, stream);
+    default:
+      slime_set_error("attention: unknown softmax variant %d (0, 1, 5, 7, 9; +16 = kv-split)", g_attn_variant);
+      return SLIME_EINVAL;
+  }
+}
+
 }  // namespace
+
+extern "C" int slime_attention_set_variant(int variant) {
+  const bool known = variant == -1 || variant == 0 || variant == 1 || variant == 5 || variant == 7 || variant == 9 ||
+                     variant == 16 || variant == 21 || variant == 23 || variant == 25;
+  if (!known) {
+    slime_set_error("attention: unknown softmax variant %d (0, 1, 5, 7, 9; +16 = kv-split; -1 = default)", variant);
+    return SLIME_EINVAL;
+  }
+  g_attn_variant = variant;
+  return SLIME_OK;
+}
 
 int slime_launch_attention_tc(const AttnParams& p, int num_sms, cudaStream_t stream) {
   if (p.batch <= 0 || p.seqlen_q <= 0 || p.seqlen_k <= 0) return SLIME_OK;

@@ -7,6 +7,9 @@ enum GemmEpilogue : int {
   GEMM_EPI_QUICK_GELU = 1,  // out = qgelu(acc + bias)          x*sigmoid(1.702x)  (CLIP MLP)
   GEMM_EPI_GELU_ERF = 2,    // out = gelu(acc + bias)           exact erf GELU     (mm_projector)
   GEMM_EPI_SWIGLU = 3,      // out[:, j] = silu(acc[:, 2j]) * acc[:, 2j+1]          (Llama MLP)
+  GEMM_EPI_ROPE = 4,        // rotary embedding on the fp32 accumulators of the packed Llama QKV projection: columns
+                            // < rope_cols hold the (i, i + hd/2) feature pairs of every head ADJACENT (weight rows
+                            // interleaved at load, slime_b200/weights.py), rotated by the row's position
 };
 
 struct GemmParams {
@@ -19,6 +22,14 @@ struct GemmParams {
   bf16* out;           // bf16 output (may alias residual) or nullptr
   float* out_f32;      // optional fp32 output (used for logits) or nullptr
   int out_ld;          // leading dimension of the output (elements)
+  // GEMM_EPI_ROPE only (HF llama/modeling_llama.py:152-176 apply_rotary_pos_emb, rotate_half)
+  const int* rope_pos = nullptr;       // [M] position id of every row
+  const float2* rope_table = nullptr;  // [rope_max_pos][rope_half] (cos, sin) fp32
+  int rope_half = 0;                   // head_dim / 2
+  int rope_cols = 0;                   // columns [0, rope_cols) are rotated (q and k heads), the rest (v) is not
+  int rope_max_pos = 0;
+  int epi_mode = 0;    // HBM access pattern of the epilogue (gemm_epilogue.cuh): 0 direct, 1 staged through shared
+                       // memory (coalesced stores and residual loads); filled in by slime_launch_gemm
 };
 
 // 0 = 1-CTA kernel only, 1 = always the 2-CTA kernel, 2 = 2-CTA for problems that fill the GPU.
@@ -33,6 +44,11 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
 // cta_group::2 variant (256 x 256 cluster tiles); arguments already validated by slime_launch_gemm.
 int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                            int num_sms, cudaStream_t stream);
+
+// Epilogue access pattern used by slime_launch_gemm (SLIME_GEMM_EPI_MODE overrides the compile-time default).
+#ifndef SLIME_GEMM_EPI_MODE_DEFAULT
+#define SLIME_GEMM_EPI_MODE_DEFAULT 0
+#endif
 
 // m-tiles per rasterisation group for a problem with reduction length K (see gemm_sm100.cu)
 int slime_gemm_group_m(int K, int tile_rows);

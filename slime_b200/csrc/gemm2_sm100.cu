@@ -26,7 +26,8 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
 constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KB: this CTA's half of the W tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 2 * BLOCK_N;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;  // barriers + TMEM holder live in the 256 bytes before it
+constexpr int SMEM_BYTES = 1024 + EPI_OFF + NUM_EPI_WARPS * 4096;  // + the epilogue staging tiles
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0
 
 #include "gemm_epilogue.cuh"
@@ -96,7 +97,7 @@ SLIME_DEVINL void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int EPI>
+template <int EPI, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p, const int group_m) {
@@ -109,6 +110,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_stage = smem + EPI_OFF;  // [NUM_EPI_WARPS][EPI_STAGE_BYTES]
+  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block");
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -209,8 +212,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<BLOCK_N, EPI>(p, tmem_base + acc * BLOCK_N, tc.m_blk * 2 * BLOCK_M + rank * BLOCK_M,
-                                  tc.n_blk * BLOCK_N, quad, half, lane);
+      epilogue_tile<BLOCK_N, EPI, STAGED>(p, tmem_base + acc * BLOCK_N, tc.m_blk * 2 * BLOCK_M + rank * BLOCK_M,
+                                  tc.n_blk * BLOCK_N, quad, half, lane,
+                                  epi_stage + (warp_idx - 2) * EPI_STAGE_BYTES);
       tcgen05_fence_before();
       mbar_arrive_leader(&tmem_empty_bar[acc]);
     }
@@ -224,9 +228,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
-template <int EPI>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_tn_2cta_kernel<EPI>;
+template <int EPI, bool STAGED>
+int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = gemm_bf16_tn_2cta_kernel<EPI, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     SLIME_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -242,6 +246,12 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, i
   slime_prof_end(stream);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
+}
+
+template <int EPI>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  if (p.epi_mode != 0 && p.out_f32 == nullptr) return launch2s<EPI, true>(ta, tb, p, num_sms, stream);
+  return launch2s<EPI, false>(ta, tb, p, num_sms, stream);
 }
 
 }  // namespace
@@ -260,6 +270,8 @@ int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const
       return launch2<GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
     case GEMM_EPI_SWIGLU:
       return launch2<GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_ROPE:
+      return launch2<GEMM_EPI_ROPE>(ta, tb, p, num_sms, stream);
     default:
       slime_set_error("unknown GEMM epilogue %d", epi);
       return SLIME_EINVAL;

@@ -40,7 +40,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES + ((BAR_BYTES + 127) / 128) * 128;  // epilogue staging tiles
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + EPI_OFF + NUM_EPI_WARPS * 4096;
 };
 
 struct TileCoord {
@@ -61,7 +62,7 @@ SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
 
 #include "gemm_epilogue.cuh"
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmParams p, const int group_m) {
@@ -78,6 +79,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* epi_stage = smem + Cfg::EPI_OFF;  // [NUM_EPI_WARPS][EPI_STAGE_BYTES]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,8 +173,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<BLOCK_N, EPI>(p, tmem_base + acc * BLOCK_N, tc.m_blk * BLOCK_M, tc.n_blk * BLOCK_N, quad, half,
-                                  lane);
+      epilogue_tile<BLOCK_N, EPI, STAGED>(p, tmem_base + acc * BLOCK_N, tc.m_blk * BLOCK_M, tc.n_blk * BLOCK_N, quad, half,
+                                  lane, epi_stage + (warp_idx - 2) * EPI_STAGE_BYTES);
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
     }
@@ -268,11 +270,11 @@ int get_tmap(const bf16* ptr, int rows, int cols, int ld, int box_rows, CUtensor
   return SLIME_OK;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool STAGED>
 int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     SLIME_CHECK_CUDA(
@@ -290,18 +292,20 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
   return SLIME_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool STAGED>
 int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi,
                int num_sms, cudaStream_t stream) {
   switch (epi) {
     case GEMM_EPI_NONE:
-      return launch_cfg<BLOCK_N, GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
+      return launch_cfg<BLOCK_N, GEMM_EPI_NONE, STAGED>(ta, tb, p, num_sms, stream);
     case GEMM_EPI_QUICK_GELU:
-      return launch_cfg<BLOCK_N, GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
+      return launch_cfg<BLOCK_N, GEMM_EPI_QUICK_GELU, STAGED>(ta, tb, p, num_sms, stream);
     case GEMM_EPI_GELU_ERF:
-      return launch_cfg<BLOCK_N, GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
+      return launch_cfg<BLOCK_N, GEMM_EPI_GELU_ERF, STAGED>(ta, tb, p, num_sms, stream);
     case GEMM_EPI_SWIGLU:
-      return launch_cfg<BLOCK_N, GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
+      return launch_cfg<BLOCK_N, GEMM_EPI_SWIGLU, STAGED>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_ROPE:
+      return launch_cfg<BLOCK_N, GEMM_EPI_ROPE, STAGED>(ta, tb, p, num_sms, stream);
     default:
       slime_set_error("unknown GEMM epilogue %d", epi);
       return SLIME_EINVAL;
@@ -327,6 +331,16 @@ int slime_gemm_group_m(int K, int tile_rows) {
 }
 
 static int g_mode_2cta = -1;  // -1: read SLIME_GEMM_2CTA / the compile-time default on first use
+static int g_epi_mode = -1;   // -1: read SLIME_GEMM_EPI_MODE / the compile-time default on first use
+
+extern "C" int slime_gemm_set_epi_mode(int mode) {
+  if (mode < 0 || mode > 1) {
+    slime_set_error("gemm epilogue mode %d not in {0,1}", mode);
+    return SLIME_EINVAL;
+  }
+  g_epi_mode = mode;
+  return SLIME_OK;
+}
 
 extern "C" int slime_gemm_set_2cta_mode(int mode) {
   g_mode_2cta = mode;
@@ -337,8 +351,14 @@ int slime_get_tmap(const bf16* ptr, int rows, int cols, int ld, int box_rows, CU
   return get_tmap(ptr, rows, cols, ld, box_rows, out);
 }
 
-int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
+int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p_in, int epi,
                       int num_sms, cudaStream_t stream) {
+  if (g_epi_mode < 0) {
+    const char* e = getenv("SLIME_GEMM_EPI_MODE");
+    g_epi_mode = (e != nullptr && e[0] >= '0' && e[0] <= '1') ? e[0] - '0' : SLIME_GEMM_EPI_MODE_DEFAULT;
+  }
+  GemmParams p = p_in;
+  p.epi_mode = p.out_f32 != nullptr ? 0 : g_epi_mode;  // fp32 outputs always go direct
   SLIME_REQUIRE(A != nullptr && W != nullptr, "gemm: null operand");
   SLIME_REQUIRE(p.out != nullptr || p.out_f32 != nullptr, "gemm: no output pointer");
   SLIME_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
@@ -356,6 +376,11 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
     SLIME_REQUIRE(p.res_ld % 8 == 0 && epi != GEMM_EPI_SWIGLU, "gemm: bad residual configuration");
   if (epi == GEMM_EPI_SWIGLU)
     SLIME_REQUIRE(p.bias == nullptr && p.out != nullptr, "gemm: SwiGLU epilogue takes no bias");
+  if (epi == GEMM_EPI_ROPE)
+    SLIME_REQUIRE(p.rope_pos != nullptr && p.rope_table != nullptr && p.rope_half > 0 && p.rope_half % 16 == 0 &&
+                      (p.rope_half & (p.rope_half - 1)) == 0 && p.rope_cols % (2 * p.rope_half) == 0 &&
+                      p.rope_max_pos > 0 && p.residual == nullptr,
+                  "gemm: bad RoPE epilogue configuration (half=%d cols=%d)", p.rope_half, p.rope_cols);
 
   // BLOCK_N = 256 halves the A re-reads; fall back to 128 when the 256-wide grid cannot fill the GPU.
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -376,6 +401,10 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
   CUtensorMap ta, tb;
   SLIME_PROPAGATE(get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
   SLIME_PROPAGATE(get_tmap(W, p.N, p.K, ldw, block_n, &tb));
-  if (use256) return launch_epi<256>(ta, tb, p, epi, num_sms, stream);
-  return launch_epi<128>(ta, tb, p, epi, num_sms, stream);
+  if (p.epi_mode != 0) {
+    if (use256) return launch_epi<256, true>(ta, tb, p, epi, num_sms, stream);
+    return launch_epi<128, true>(ta, tb, p, epi, num_sms, stream);
+  }
+  if (use256) return launch_epi<256, false>(ta, tb, p, epi, num_sms, stream);
+  return launch_epi<128, false>(ta, tb, p, epi, num_sms, stream);
 }

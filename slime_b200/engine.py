@@ -11,6 +11,7 @@ chains them for a whole batch:  pixels + prompt ids -> last-token logits, with t
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
@@ -21,6 +22,9 @@ from . import _lib as L
 from .config import IGNORE_INDEX, IMAGE_TOKEN_INDEX, SlimeConfig
 from .mm_utils import get_anyres_image_grid_shape
 from .weights import ALL_GROUPS, pack_weights
+
+
+FUSED_ROPE_DEFAULT = "1"  # RoPE in the QKV GEMM epilogue (SLIME_FUSED_ROPE=0: separate in-place pass)
 
 
 def _locked(fn):
@@ -54,7 +58,7 @@ class PrefillResult:
 
 class SlimeEngine:
     def __init__(self, cfg: SlimeConfig, device: int | str | torch.device = 0, max_pos: Optional[int] = None,
-                 dtype=torch.bfloat16):
+                 dtype=torch.bfloat16, fused_rope: Optional[bool] = None):
         cfg.validate()
         self.cfg = cfg
         self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
@@ -81,9 +85,15 @@ class SlimeEngine:
         d.top_p, d.temp = cfg.mm_resampler_topp, cfg.mm_resampler_temp
         d.image_token, d.sep_token = IMAGE_TOKEN_INDEX, cfg.seperator
         d.max_len = int(cfg.tokenizer_model_max_length or 0)
+        # RoPE inside the QKV GEMM's epilogue (q / k weight rows interleaved at load) instead of a separate pass;
+        # SLIME_FUSED_ROPE=0/1 overrides the default
+        if fused_rope is None:
+            fused_rope = os.environ.get("SLIME_FUSED_ROPE", FUSED_ROPE_DEFAULT) not in ("0", "")
+        self.fused_rope = bool(fused_rope)
         d.flags = ((L.SLIME_FLAG_LEFT_PAD if cfg.tokenizer_padding_side == "left" else 0)
                    | (L.SLIME_FLAG_USE_GLOBAL_ONLY if cfg.use_global_only else 0)
-                   | (L.SLIME_FLAG_USE_LOCAL_ONLY if cfg.use_local_only else 0))
+                   | (L.SLIME_FLAG_USE_LOCAL_ONLY if cfg.use_local_only else 0)
+                   | (L.SLIME_FLAG_ROPE_INTERLEAVED if self.fused_rope else 0))
         self._desc = d
         self._ctx = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -109,7 +119,7 @@ class SlimeEngine:
         """groups: which weight groups to register ("vit", "rs_local", "rs_global", "proj", "llm"); a stage
         whose group is absent fails loudly (used by the stand-alone module shims of slime_b200/model)."""
         with self._lock, torch.cuda.device(self.device):
-            self.weights = pack_weights(self.cfg, get, self.device, groups, self.dtype)
+            self.weights = pack_weights(self.cfg, get, self.device, groups, self.dtype, rope_interleaved=self.fused_rope)
             for name, t in self.weights.items():
                 self._check(self.lib.slime_ctx_set_weight(self._ctx, name.encode(), L.ptr(t), t.shape[0], t.shape[1]),
                         f"set_weight({name})")

@@ -5,6 +5,9 @@ Packing = one-time, load-time layout work done with torch tensor ops (plumbing):
   * CLIP q/k/v -> one [3D, D] weight + [3D] bias;  Llama q/k/v -> one [(h+2kv)*hd, H] weight
   * Llama gate/up -> rows interleaved (g0,u0,g1,u1,...) so the SwiGLU epilogue sees both halves of
     a pair in one accumulator tile
+  * Llama q/k (rope_interleaved): inside every head, rows (i, i + hd/2) made adjacent so the RoPE pair of
+    HF's rotate_half (llama/modeling_llama.py:152-176) sits in adjacent accumulator columns and the rotation
+    runs in the QKV GEMM's epilogue (SLIME_FLAG_ROPE_INTERLEAVED); q.k is invariant under the common permutation
   * CLIP patch conv [D,3,14,14] -> [D, 588] zero-padded to K = 640 (TMA needs 16-byte row strides)
   * Resampler key positions: the bicubic 12x12 -> 24x24 resize of the constant sincos table
     (reference multimodal_resampler/sampler.py:27-36,149-155) is input independent -> done here once
@@ -37,8 +40,15 @@ def resize_pos_table(pos: torch.Tensor, tgt: int) -> torch.Tensor:
 ALL_GROUPS = ("vit", "rs_local", "rs_global", "proj", "llm")
 
 
+def rope_interleave_rows(w: torch.Tensor, head_dim: int) -> torch.Tensor:
+    """[heads*hd, H] -> same shape with rows (i, i + hd/2) of every head adjacent: new row 2i = old i, 2i+1 = old i + hd/2."""
+    heads = w.shape[0] // head_dim
+    return w.reshape(heads, 2, head_dim // 2, w.shape[1]).transpose(1, 2).reshape(w.shape)
+
+
 def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device,
-                 groups=ALL_GROUPS, dtype: torch.dtype = torch.bfloat16) -> Dict[str, torch.Tensor]:
+                 groups=ALL_GROUPS, dtype: torch.dtype = torch.bfloat16,
+                 rope_interleaved: bool = False) -> Dict[str, torch.Tensor]:
     """get(name) returns the reference tensor `name` (any dtype/device); returns canonical-name ->
     contiguous CUDA tensor (2-D) in the engine's 16-bit element type.  Tensors are pulled one at a time so a lazy source (e.g. the
     on-GPU synthetic generator) never holds two copies of the model."""
@@ -54,7 +64,7 @@ def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device,
         _pack_vit(cfg, g, out)
     _pack_adapter(cfg, g, out, device, groups, bf)
     if "llm" in groups:
-        _pack_llm(cfg, g, out)
+        _pack_llm(cfg, g, out, rope_interleaved)
     for k, t in out.items():
         assert t.dim() == 2 and t.is_contiguous() and t.dtype == bf, k
     return out
@@ -115,14 +125,16 @@ def _pack_adapter(cfg, g, out, device, groups, bf):
     out["proj.w_gate"] = g(m + "w_gate").contiguous()
 
 
-def _pack_llm(cfg, g, out):
+def _pack_llm(cfg, g, out, rope_interleaved=False):
     H = cfg.hidden_size
+    perm = (lambda w: rope_interleave_rows(w, cfg.head_dim)) if rope_interleaved else (lambda w: w)
     out["llm.embed"] = g("model.embed_tokens.weight").contiguous()
     out["llm.norm_w"] = g("model.norm.weight").reshape(1, -1)
     out["llm.lm_head"] = g("lm_head.weight").contiguous()
     for l in range(cfg.num_hidden_layers):
         p, c = f"model.layers.{l}.", f"llm.layers.{l}."
-        out[c + "qkv_w"] = torch.cat([g(p + f"self_attn.{n}.weight") for n in ("q_proj", "k_proj", "v_proj")]).contiguous()
+        out[c + "qkv_w"] = torch.cat([perm(g(p + "self_attn.q_proj.weight")), perm(g(p + "self_attn.k_proj.weight")),
+                                      g(p + "self_attn.v_proj.weight")]).contiguous()
         out[c + "o_w"] = g(p + "self_attn.o_proj.weight").contiguous()
         gate, up = g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")
         out[c + "gate_up_w"] = torch.stack([gate, up], dim=1).reshape(2 * cfg.intermediate_size, H).contiguous()

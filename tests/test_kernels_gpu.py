@@ -352,3 +352,127 @@ def test_gemm_2cta_epilogues(force_2cta):
     out = gemm(x, inter, epi=L.EPI_SWIGLU)
     ref = torch.nn.functional.silu(x.float() @ gate.float().t()) * (x.float() @ up.float().t())
     assert_close_bf16(out, ref, "gemm 2cta + swiglu")
+
+
+# ------------------------------------------------------------------------------------------------
+# opt-in / alternative code paths: staged GEMM epilogue, softmax variants, RoPE in the QKV epilogue
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("two_cta", [0, 1])
+def test_gemm_staged_epilogue_bit_identical(two_cta):
+    """GemmParams::epi_mode 1 (chunks transposed through shared memory, coalesced stores and residual loads) only
+    changes the HBM access pattern: every epilogue must produce the same bits as the direct path, including ragged
+    M, N not a multiple of 32, the row-scatter map with dropped rows and the row-periodic residual table."""
+    L = _lib()
+    lib = L.load()
+    torch.manual_seed(5)
+    M, N, K = 1000, 1064, 256
+    a, w, bias, h = rnd(M, K), rnd(N, K, scale=0.05), rnd(N), rnd(M, N)
+    table = rnd(37, N)
+    row_map = torch.randperm(M, device="cuda").to(torch.int32)
+    row_map[::7] = -1
+    gu = rnd(2048, K, scale=0.05)
+    res = {}
+    lib.slime_gemm_set_2cta_mode(two_cta)
+    try:
+        for mode in (0, 1):
+            L.check(lib.slime_gemm_set_epi_mode(mode), "set_epi_mode")
+            res[mode] = [
+                gemm(a, w, bias=bias),
+                gemm(a, w, bias=bias, residual=h),
+                gemm(a, w, residual=table, res_period=37),
+                gemm(a, w, bias=bias, epi=L.EPI_QUICK_GELU),
+                gemm(a, w, bias=bias, epi=L.EPI_GELU_ERF),
+                gemm(a, w, bias=bias, row_map=row_map),
+                gemm(a, gu, epi=L.EPI_SWIGLU),
+                gemm(a, w, bias=bias, f32=True),
+            ]
+    finally:
+        lib.slime_gemm_set_epi_mode(0)
+        lib.slime_gemm_set_2cta_mode(-1)
+    for i, (x, y) in enumerate(zip(res[0], res[1])):
+        assert torch.equal(x, y), f"staged epilogue differs from direct in case {i} (2cta={two_cta})"
+    assert_close_bf16(res[1][1], a.float() @ w.float().t() + bias.float() + h.float(), "staged gemm + residual")
+
+
+@pytest.mark.parametrize("variant", [1, 5, 7, 9, 16, 21, 25])
+@pytest.mark.parametrize("causal,d", [(1, 128), (0, 64)])
+def test_attention_softmax_variants(variant, causal, d):
+    """Packed-pair / polynomial-exp2 softmax variants of the tcgen05 kernel against fp32 math, incl. peaked scores
+    (large logits: very negative exponents, lazy rescale) and ragged lengths (masked tiles keep the scalar path)."""
+    L = _lib()
+    lib = L.load()
+    torch.manual_seed(variant * 10 + d)
+    lens = [700, 130, 1, 577, 129]
+    h, kvh = (8, 2) if d == 128 else (4, 4)
+    total = sum(lens)
+    W = (h + 2 * kvh) * d
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device="cuda", dtype=torch.int32)
+    try:
+        for scale in (1.0, 3.0):
+            qkv = (torch.randn(total, W, device="cuda") * scale).to(torch.bfloat16)
+            o = torch.zeros(total, h * d, device="cuda", dtype=torch.bfloat16)
+            L.check(lib.slime_attention_set_variant(variant), "set_variant")
+            rc = lib.slime_op_attention(L.ptr(qkv), L.ptr(qkv[:, h * d:]), L.ptr(qkv[:, (h + kvh) * d:]), L.ptr(o), W, W, W,
+                                        h * d, L.ptr(cu), L.ptr(cu), max(lens), max(lens), 0, 0, 0, len(lens), h, kvh, d,
+                                        d ** -0.5, causal, total, total, 2, L.stream_ptr())
+            L.check(rc, "op_attention")
+            torch.cuda.synchronize()
+            ref = torch.zeros(total, h * d, device="cuda")
+            for b, n in enumerate(lens):
+                r0 = int(cu[b])
+                q = qkv[r0:r0 + n, :h * d].float().reshape(n, h, d).transpose(0, 1)
+                k = qkv[r0:r0 + n, h * d:(h + kvh) * d].float().reshape(n, kvh, d).transpose(0, 1)
+                v = qkv[r0:r0 + n, (h + kvh) * d:].float().reshape(n, kvh, d).transpose(0, 1)
+                k, v = k.repeat_interleave(h // kvh, 0), v.repeat_interleave(h // kvh, 0)
+                s = (q @ k.transpose(1, 2)) * d ** -0.5
+                if causal:
+                    s = s.masked_fill(torch.triu(torch.ones(n, n, device="cuda", dtype=torch.bool), 1), float("-inf"))
+                ref[r0:r0 + n] = (s.softmax(-1) @ v).transpose(0, 1).reshape(n, h * d)
+            assert_close_bf16(o, ref, f"attention variant {variant} causal={causal} d={d} scale={scale}", tol=6e-3)
+    finally:
+        lib.slime_attention_set_variant(-1)
+
+
+@pytest.mark.parametrize("rows,two_cta", [(1, -1), (8, -1), (700, -1), (700, 1), (333, 1)])
+def test_qkv_rope_fused_epilogue(rows, two_cta):
+    """RoPE fused into the QKV GEMM epilogue (SLIME_FLAG_ROPE_INTERLEAVED: q / k weight rows of every head interleaved
+    at load) against fp32 math of HF apply_rotary_pos_emb, and against the unfused path (GEMM + in-place pass) after
+    undoing the feature permutation.  Covers the 1-CTA kernels (decode-sized M) and the 2-CTA kernel."""
+    from slime_b200.config import preset
+    from slime_b200.engine import SlimeEngine
+    from slime_b200.weights import rope_interleave_rows
+
+    L = _lib()
+    cfg = preset("small")
+    hd, nh, nkv, H = cfg.head_dim, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.hidden_size
+    torch.manual_seed(rows)
+    x = rnd(rows, H)
+    wq, wk, wv = rnd(nh * hd, H, scale=0.05), rnd(nkv * hd, H, scale=0.05), rnd(nkv * hd, H, scale=0.05)
+    pos = torch.randint(0, 900, (rows,), device="cuda", dtype=torch.int32)
+    outs = {}
+    L.load().slime_gemm_set_2cta_mode(two_cta)
+    for fused in (False, True):
+        eng = SlimeEngine(cfg, 0, max_pos=1024, fused_rope=fused)
+        perm = (lambda w: rope_interleave_rows(w, hd)) if fused else (lambda w: w)
+        w = torch.cat([perm(wq), perm(wk), wv]).contiguous()
+        out = torch.zeros(rows, (nh + 2 * nkv) * hd, device="cuda", dtype=torch.bfloat16)
+        L.check(eng.lib.slime_op_qkv_rope(eng._ctx, L.ptr(x), L.ptr(w), rows, L.ptr(pos), L.ptr(out), L.stream_ptr()),
+                "op_qkv_rope")
+        torch.cuda.synchronize()
+        if fused:  # undo the interleave of the q / k feature order: column 2i <- feature i, 2i+1 <- feature i + hd/2
+            qk = out[:, :(nh + nkv) * hd].reshape(rows, nh + nkv, hd // 2, 2).transpose(2, 3).reshape(rows, -1)
+            out = torch.cat([qk, out[:, (nh + nkv) * hd:]], dim=1)
+        outs[fused] = out
+        eng.close()
+    L.load().slime_gemm_set_2cta_mode(-1)
+    # fp32 reference (HF llama/modeling_llama.py:152-176)
+    y = x.float() @ torch.cat([wq, wk, wv]).float().t()
+    inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, device="cuda", dtype=torch.float32) / hd))
+    ang = pos.float()[:, None] * inv[None, :]
+    cos, sin = torch.cat([ang.cos(), ang.cos()], -1), torch.cat([ang.sin(), ang.sin()], -1)
+    qk = y[:, :(nh + nkv) * hd].reshape(rows, nh + nkv, hd)
+    rot = torch.cat([-qk[..., hd // 2:], qk[..., :hd // 2]], -1)
+    ref = torch.cat([(qk * cos[:, None, :] + rot * sin[:, None, :]).reshape(rows, -1), y[:, (nh + nkv) * hd:]], dim=1)
+    assert_close_bf16(outs[True], ref, f"fused qkv+rope rows={rows}")
+    assert_close_bf16(outs[False], ref, f"unfused qkv+rope rows={rows}", tol=6e-3)
+    assert torch.equal(outs[True][:, (nh + nkv) * hd:], outs[False][:, (nh + nkv) * hd:]), "v columns must not change"
