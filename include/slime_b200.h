@@ -245,9 +245,10 @@ int slime_gemm_set_2cta_mode(int mode);
 int slime_gemm_set_epi_mode(int mode);
 /* debug: CTA 0 of the tcgen05 attention kernel stamps clock64() of its first 64 tiles into buf [64][16] (NULL = off) */
 int slime_attention_set_trace(long long* buf);
-/* softmax arithmetic of the tcgen05 attention kernel: 0 = scalar FFMA + MUFU.EX2; 1 + 2*P = packed fp32 pairs
- * (FFMA2 / FADD2) with P of every 8 pairs exponentiated by a polynomial on the FMA pipe instead of the SFU
- * (P = 0, 2, 3, 4 -> 1, 5, 7, 9); -1 = back to the default (SLIME_ATTN_VARIANT / build default). */
+/* softmax arithmetic of the tcgen05 attention kernel: 0 = scalar FFMA + MUFU.EX2; 5 / 9 = packed fp32 pairs
+ * (FFMA2 / FADD2) with 2 / 4 of every 8 pairs exponentiated by a polynomial on the FMA pipe instead of the SFU
+ * (5 is the default); 21 = variant 5 with the kv tiles alternating between two softmax warp groups; 32 = measurement
+ * only (no softmax, garbage output); -1 = back to the default (SLIME_ATTN_VARIANT / build default). */
 int slime_attention_set_variant(int variant);
 long long slime_launch_count(void);
 int slime_profile_enable(int on);

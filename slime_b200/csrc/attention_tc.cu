@@ -124,8 +124,12 @@ SLIME_DEVINL float2 exp2_poly2(float2 x) {
 // Softmax arithmetic variant of attn_tc_kernel (template parameter VAR; SLIME_ATTN_VARIANT / slime_attention_set_variant):
 //   0        : scalar FFMA + MUFU.EX2 per element
 //   1 + 2*P  : packed pairs (FFMA2 scale, FADD2 row sums) with P of every 8 pairs exponentiated by exp2_poly2 on
-//              the FMA pipe instead of the SFU (P = 0, 2, 3, 4); tiles that need masking keep the scalar path
-//              (masked scores are -inf, which the polynomial path would turn into 2^-126 instead of 0)
+//              the FMA pipe instead of the SFU (P = 2 -> variant 5, the default; P = 4 -> 9); tiles that need
+//              masking keep the scalar path (masked scores are -inf, which the polynomial path would turn into
+//              2^-126 instead of 0)
+//   16 + v   : kv-split softmax (template parameter SPLIT) with arithmetic v; built: 21
+//   32       : MEASUREMENT ONLY, garbage output: no softmax at all (floor of the TMA + tcgen05.mma side)
+// Measured on B200 (profiles/r01_attention_experiments.txt): decoder shape 0.376 ms (0) -> 0.367 (5); kv-split 0.386.
 SLIME_DEVINL constexpr bool pair_is_poly(int c, int P) {
   // spread the polynomial pairs evenly over each group of 8 so SFU and FMA work interleave
   return P == 2 ? ((c & 3) == 1) : P == 3 ? ((c & 7) == 1 || (c & 7) == 4 || (c & 7) == 6) : P == 4 ? ((c & 1) == 1) : false;
@@ -737,6 +741,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         mbar_wait(&s_full[buf], (gj >> 1) & 1);
         tcgen05_fence_after();
         if (tr) p.trace[gj * 16 + 1] = clock64();
+        if (VAR == 32) {
+          // DEBUG / measurement only (garbage output): no softmax at all - P is whatever S left in TMEM.  The tile
+          // period of this variant is the floor set by the TMA + tcgen05.mma side alone.
+          l_sum = 1.f;
+          tcgen05_fence_before();
+          mbar_arrive(&p_ready[buf]);
+          if (j == 0 && pend_g_last >= 0) {
+            run_epilogue(k - 1, nullptr);
+            pend_g_last = -1;
+          }
+          continue;
+        }
         uint32_t sr[64];
         tmem_ld_32x32b_x32(s_base + half * 64, sr);
         tmem_ld_32x32b_x32(s_base + half * 64 + 32, sr + 32);
@@ -894,16 +910,12 @@ int launch_tc(const AttnParams& p, int num_sms, cudaStream_t stream) {
   }
   switch (g_attn_variant) {
     case 0: return launch_tc_var<HD, CAUSAL, 0, false>(p, num_sms, stream);
-    case 1: return launch_tc_var<HD, CAUSAL, 1, false>(p, num_sms, stream);
     case 5: return launch_tc_var<HD, CAUSAL, 5, false>(p, num_sms, stream);
-    case 7: return launch_tc_var<HD, CAUSAL, 7, false>(p, num_sms, stream);
     case 9: return launch_tc_var<HD, CAUSAL, 9, false>(p, num_sms, stream);
-    case 16: return launch_tc_var<HD, CAUSAL, 0, true>(p, num_sms, stream);
+    case 32: return launch_tc_var<HD, CAUSAL, 32, false>(p, num_sms, stream);  // measurement only: no softmax
     case 21: return launch_tc_var<HD, CAUSAL, 5, true>(p, num_sms, stream);
-    case 23: return launch_tc_var<HD, CAUSAL, 7, true>(p, num_sms, stream);
-    case 25: return launch_tc_var<HD, CAUSAL, 9, true>(p, num_sms, stream);
     default:
-      slime_set_error("attention: unknown softmax variant %d (0, 1, 5, 7, 9; +16 = kv-split)", g_attn_variant);
+      slime_set_error("attention: unknown softmax variant %d (0, 5, 9, 21, 32)", g_attn_variant);
       return SLIME_EINVAL;
   }
 }
@@ -911,10 +923,9 @@ int launch_tc(const AttnParams& p, int num_sms, cudaStream_t stream) {
 }  // namespace
 
 extern "C" int slime_attention_set_variant(int variant) {
-  const bool known = variant == -1 || variant == 0 || variant == 1 || variant == 5 || variant == 7 || variant == 9 ||
-                     variant == 16 || variant == 21 || variant == 23 || variant == 25;
+  const bool known = variant == -1 || variant == 0 || variant == 5 || variant == 9 || variant == 21 || variant == 32;
   if (!known) {
-    slime_set_error("attention: unknown softmax variant %d (0, 1, 5, 7, 9; +16 = kv-split; -1 = default)", variant);
+    slime_set_error("attention: unknown softmax variant %d (0, 5, 9, 21 = kv-split, 32 = no softmax; -1 = default)", variant);
     return SLIME_EINVAL;
   }
   g_attn_variant = variant;

@@ -394,7 +394,7 @@ def test_gemm_staged_epilogue_bit_identical(two_cta):
     assert_close_bf16(res[1][1], a.float() @ w.float().t() + bias.float() + h.float(), "staged gemm + residual")
 
 
-@pytest.mark.parametrize("variant", [1, 5, 7, 9, 16, 21, 25])
+@pytest.mark.parametrize("variant", [0, 5, 9, 21])
 @pytest.mark.parametrize("causal,d", [(1, 128), (0, 64)])
 def test_attention_softmax_variants(variant, causal, d):
     """Packed-pair / polynomial-exp2 softmax variants of the tcgen05 kernel against fp32 math, incl. peaked scores

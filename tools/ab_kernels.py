@@ -107,7 +107,7 @@ def attn_ab():
                    L.ptr(cu), L_, L_, 0, 0, 0, B, h, kvh, d, d ** -0.5, 1, B * L_, B * L_, 2, L.stream_ptr()), (qkv3, cu)))
     for name, out, fl, args, _keep in cases:
         base = None
-        for var in (0, 5, 16, 21, 23, 25):
+        for var in [int(v) for v in os.environ.get("AB_VARIANTS", "0,5,9,21,32").split(",")]:
             assert lib.slime_attention_set_variant(var) == 0
 
             def f():
