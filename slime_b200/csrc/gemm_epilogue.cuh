@@ -99,10 +99,21 @@ SLIME_DEVINL void epi_issue_residual(const GemmParams& p, const EpiRow& er, cons
   }
 }
 
+// ---- bias fetch of one chunk (32 columns, the same for every row), issued one chunk ahead like the residual: the
+//      ncu source view of the K = 1024 ViT fc1 GEMM had 55 % of all stall samples on the first use of these loads
+//      (the 227 KB shared-memory carve-out leaves almost no L1, so each is an L2 round trip) ----
+SLIME_DEVINL void epi_issue_bias(const GemmParams& p, int col0, uint4 (&b)[4]) {
+  if (p.bias == nullptr) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (col0 + g * 8 < p.N) b[g] = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + g * 8));
+  }
+}
+
 // bias / activation / residual on 8 accumulator columns -> 8 floats
 template <int EPI>
 SLIME_DEVINL void epi_math8(const GemmParams& p, const EpiRow& er, int col, const uint32_t* r8, const uint4& resq,
-                            float (&v)[8]) {
+                            const uint4& b, float (&v)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r8[j]);
   if constexpr (EPI == GEMM_EPI_ROPE) {
@@ -122,7 +133,6 @@ SLIME_DEVINL void epi_math8(const GemmParams& p, const EpiRow& er, int col, cons
     }
   }
   if (p.bias != nullptr) {
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
     const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
     v[0] += b0.x; v[1] += b0.y; v[2] += b1.x; v[3] += b1.y;
     v[4] += b2.x; v[5] += b2.y; v[6] += b3.x; v[7] += b3.y;
@@ -162,7 +172,7 @@ SLIME_DEVINL uint4 epi_swiglu8(const uint32_t* r16) {
 // ---- mode 0: every thread stores its own row ----
 template <int EPI>
 SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, const EpiRow& er, int col0, const uint32_t (&r)[32],
-                                           const uint4 (&res)[4]) {
+                                           const uint4 (&res)[4], const uint4 (&bia)[4]) {
   if (!er.store_ok || col0 >= p.N) return;
   if constexpr (EPI == GEMM_EPI_SWIGLU) {
     // columns are (gate_j, up_j) interleaved -> 16 outputs per 32 accumulator columns
@@ -178,7 +188,7 @@ SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, const EpiRow& er
       const int col = col0 + g * 8;
       if (col >= p.N) break;
       float v[8];
-      epi_math8<EPI>(p, er, col, r + g * 8, res[g], v);
+      epi_math8<EPI>(p, er, col, r + g * 8, res[g], bia[g], v);
       if (p.out_f32 != nullptr) {
         float4* dst = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(er.out_row) * p.out_ld + col);
         dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -193,7 +203,8 @@ SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, const EpiRow& er
 // ---- modes 1 / 2: transpose through the warp's staging tile, coalesced stores (and residual loads) ----
 template <int EPI>
 SLIME_DEVINL void epi_process_chunk_staged(const GemmParams& p, const EpiRow& er, const EpiCoal& ec, int lane, int col0,
-                                           const uint32_t (&r)[32], const uint4 (&res)[4], uint8_t* stage) {
+                                           const uint32_t (&r)[32], const uint4 (&res)[4], const uint4 (&bia)[4],
+                                           uint8_t* stage) {
   if (col0 >= p.N) return;  // warp-uniform
   constexpr int SLOTS = EPI == GEMM_EPI_SWIGLU ? 2 : 4;
   uint8_t* stage_out = stage;
@@ -220,7 +231,7 @@ SLIME_DEVINL void epi_process_chunk_staged(const GemmParams& p, const EpiRow& er
       const int col = col0 + g * 8;
       float v[8];
       if (col < p.N) {
-        epi_math8<EPI>(p, er, col, r + g * 8, own[g], v);
+        epi_math8<EPI>(p, er, col, r + g * 8, own[g], bia[g], v);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -269,19 +280,22 @@ SLIME_DEVINL void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m0, 
 
   uint32_t acc[2][32];
   uint4 res[2][4];
+  uint4 bia[2][4];
   tmem_ld_32x32b_x32(taddr, acc[0]);
+  if constexpr (EPI != GEMM_EPI_SWIGLU) epi_issue_bias(p, col_begin, bia[0]);
   epi_issue_residual<EPI, STAGED>(p, er, ec, lane, col_begin, res[0]);
   tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     if (i + 1 < NCH) {
       tmem_ld_32x32b_x32(taddr + (i + 1) * 32, acc[(i + 1) & 1]);
+      if constexpr (EPI != GEMM_EPI_SWIGLU) epi_issue_bias(p, col_begin + (i + 1) * 32, bia[(i + 1) & 1]);
       epi_issue_residual<EPI, STAGED>(p, er, ec, lane, col_begin + (i + 1) * 32, res[(i + 1) & 1]);
     }
     if constexpr (STAGED) {
-      epi_process_chunk_staged<EPI>(p, er, ec, lane, col_begin + i * 32, acc[i & 1], res[i & 1], stage);
+      epi_process_chunk_staged<EPI>(p, er, ec, lane, col_begin + i * 32, acc[i & 1], res[i & 1], bia[i & 1], stage);
     } else {
-      epi_process_chunk_direct<EPI>(p, er, col_begin + i * 32, acc[i & 1], res[i & 1]);
+      epi_process_chunk_direct<EPI>(p, er, col_begin + i * 32, acc[i & 1], res[i & 1], bia[i & 1]);
     }
     if (i + 1 < NCH) tmem_ld_wait();
   }

@@ -59,7 +59,8 @@ def gemm_ab():
         n_out = N // 2 if epi == L.EPI_SWIGLU else N
         res0 = torch.randn(M, n_out, device=dev).to(torch.bfloat16) if use_res else None
         outs, times = [], []
-        for mode in (0, 1):
+        order = (1, 0) if os.environ.get("AB_REVERSE") else (0, 1)
+        for mode in order:
             assert lib.slime_gemm_set_epi_mode(mode) == 0
             out = res0.clone() if use_res else torch.full((M, n_out), 7.0, device=dev, dtype=torch.bfloat16)
 
@@ -72,7 +73,10 @@ def gemm_ab():
             f()  # one application on the fresh residual: this is the output that is compared
             torch.cuda.synchronize()
             outs.append(out.clone())
-            times.append(timeit(f))
+            times.append(timeit(f, n=30))
+        if order[0] == 1:
+            outs.reverse()
+            times.reverse()
         same = torch.equal(outs[0], outs[1])
         fl = 2.0 * M * N * K
         print(f"gemm {name:22s} M={M:6d} N={N:6d} K={K:6d}  direct {times[0]:7.3f} ms ({fl / times[0] / 1e9:6.0f} TF/s)  "
