@@ -216,6 +216,20 @@ int slime_preprocess_fwd(const uint8_t* src, const slime_resize_job* jobs, int n
 int slime_op_gemm(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
                   const void* residual, int res_ld, int res_period, const int32_t* row_map, int epilogue,
                   void* out, float* out_f32, int out_ld, void* stream);
+/* Weight-streaming GEMM of the decode step (M <= 32 rows, K % 32 == 0; csrc/gemm_skinny.cu) with an explicit number
+ * of k-splits: splits > 1 (or norm_w != NULL) needs ws with splits * m * n floats.  norm_w / norm_out: RMSNorm of the
+ * output rows fused into the split-K finishing kernel (epilogue 0, bf16 out).  rope_*: epilogue 4 only. */
+int slime_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
+                         const void* residual, int res_ld, int epilogue, void* out, float* out_f32, int out_ld,
+                         int splits, float* ws, size_t ws_floats, const void* norm_w, void* norm_out, float norm_eps,
+                         const int32_t* rope_pos, const float* rope_table, int rope_half, int rope_cols, int rope_max_pos,
+                         void* stream);
+/* Single-query attention over a KV cache [batch, cache_len, kv_heads * head_dim]: sequence b attends its first
+ * lens[b] + 1 positions.  splits >= 1: split-KV kernel (ws = batch * heads * splits * (head_dim + 2) floats when
+ * splits > 1); splits == 0: one CTA per (q head, sequence). */
+int slime_op_decode_attention(const void* q, int q_ld, const void* kcache, const void* vcache, int cache_len,
+                              const int32_t* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
+                              void* out, int out_ld, int splits, float* ws, void* stream);
 int slime_op_attention(const void* q, const void* k, const void* v, void* o, int q_ld, int k_ld, int v_ld,
                        int o_ld, const int32_t* cu_q, const int32_t* cu_k, int seqlen_q, int seqlen_k,
                        int64_t q_batch_rows, int64_t k_batch_rows, int64_t o_batch_rows, int batch,
@@ -243,6 +257,14 @@ int slime_gemm_set_2cta_mode(int mode);
  * (stores and residual loads of 8 rows x 64 contiguous bytes per instruction).  Never called: SLIME_GEMM_EPI_MODE
  * environment variable, else the build default. */
 int slime_gemm_set_epi_mode(int mode);
+/* Decode-step kernel selection (A/B measurements): weight-streaming GEMM for M <= 32 rows (1, default) or the tcgen05
+ * tile kernels (0); split-KV decode attention (1, default) or one CTA per (q head, sequence) (0); -1 = back to the
+ * SLIME_GEMM_SKINNY / SLIME_DECODE_ATTN environment variables. */
+int slime_gemm_set_skinny_mode(int mode);
+int slime_decode_attention_set_mode(int mode);
+/* Programmatic dependent launch of the decode-step kernels (their weight prefetch / prologue overlaps the previous
+ * kernel's tail): 1 on (default), 0 ordinary stream-ordered launches, -1 = back to the SLIME_PDL environment variable. */
+int slime_set_pdl_mode(int mode);
 /* debug: CTA 0 of the tcgen05 attention kernel stamps clock64() of its first 64 tiles into buf [64][16] (NULL = off) */
 int slime_attention_set_trace(long long* buf);
 /* softmax arithmetic of the tcgen05 attention kernel: 0 = scalar FFMA + MUFU.EX2; 5 / 9 = packed fp32 pairs

@@ -40,7 +40,7 @@ SLIME_FLAG_USE_GLOBAL_ONLY = 2
 SLIME_FLAG_USE_LOCAL_ONLY = 4
 SLIME_FLAG_ROPE_INTERLEAVED = 8
 
-EPI_NONE, EPI_QUICK_GELU, EPI_GELU_ERF, EPI_SWIGLU = 0, 1, 2, 3
+EPI_NONE, EPI_QUICK_GELU, EPI_GELU_ERF, EPI_SWIGLU, EPI_ROPE = 0, 1, 2, 3, 4
 
 
 class ModelDesc(C.Structure):
@@ -129,6 +129,9 @@ SIGNATURES = {
     "slime_preprocess_workspace_bytes": (_sz, [_vp, _i]),
     "slime_preprocess_fwd": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _sz, _vp]),
     "slime_op_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    "slime_op_gemm_skinny": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _f,
+                                  _vp, _vp, _i, _i, _i, _vp]),
+    "slime_op_decode_attention": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _i, _vp, _vp]),
     "slime_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i64, _i64, _i64, _i, _i, _i,
                                 _i, _f, _i, _i64, _i64, _i, _vp]),
     "slime_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
@@ -137,6 +140,9 @@ SIGNATURES = {
     "slime_op_qkv_rope": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "slime_gemm_set_2cta_mode": (_i, [_i]),
     "slime_gemm_set_epi_mode": (_i, [_i]),
+    "slime_gemm_set_skinny_mode": (_i, [_i]),
+    "slime_decode_attention_set_mode": (_i, [_i]),
+    "slime_set_pdl_mode": (_i, [_i]),
     "slime_attention_set_trace": (_i, [_vp]),
     "slime_attention_set_variant": (_i, [_i]),
     "slime_launch_count": (C.c_longlong, []),

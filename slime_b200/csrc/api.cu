@@ -113,10 +113,33 @@ int find_weight(slime_ctx* c, const std::string& name, int64_t rows, int64_t col
   return SLIME_OK;
 }
 
+// Optional arguments of the decode-step GEMMs (M <= 32 rows, gemm_skinny.cu): split-K scratch and the RMSNorm that
+// follows the projection (fused into the split-K finishing kernel when possible).
+struct GemmExtra {
+  float* splitk_ws = nullptr;
+  size_t splitk_ws_floats = 0;
+  bf16* kv_k = nullptr;  // qkv_rope only: append this step's K / V rows to the cache (slot kv_lens[row] of sequence row)
+  bf16* kv_v = nullptr;
+  const int* kv_lens = nullptr;
+  int kv_cache_len = 0;
+  const bf16* norm_w = nullptr;
+  bf16* norm_out = nullptr;
+  int norm_ld = 0;
+  float norm_eps = 0.f;
+};
+
 int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
          const bf16* bias, const bf16* residual, int res_ld, int res_period, const int* row_map, int epi,
-         bf16* out, float* out_f32, int out_ld, cudaStream_t s) {
+         bf16* out, float* out_f32, int out_ld, cudaStream_t s, const GemmExtra* ex = nullptr) {
   GemmParams p;
+  if (ex != nullptr) {
+    p.splitk_ws = ex->splitk_ws;
+    p.splitk_ws_floats = ex->splitk_ws_floats;
+    p.norm_w = ex->norm_w;
+    p.norm_out = ex->norm_out;
+    p.norm_ld = ex->norm_ld;
+    p.norm_eps = ex->norm_eps;
+  }
   p.M = M; p.N = N; p.K = K;
   p.bias = bias;
   p.residual = residual;
@@ -134,15 +157,30 @@ int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, in
 // (i, i + hd/2) sits in adjacent accumulator columns and the rotation happens in the GEMM epilogue on the fp32
 // accumulators (q and k stay in that permuted feature order: q.k is invariant under a common permutation, and
 // the KV cache / decode step use the same order).  Without the flag: plain GEMM, then rope_kernel in place.
-int qkv_rope(slime_ctx* c, const bf16* x, const bf16* qkv_w, int rows, const int* pos, bf16* qkv, cudaStream_t s) {
+int qkv_rope(slime_ctx* c, const bf16* x, const bf16* qkv_w, int rows, const int* pos, bf16* qkv, cudaStream_t s,
+             const GemmExtra* ex = nullptr) {
   const slime_model_desc& d = c->d;
   const int H = d.hidden, hd = d.head_dim, QKV = (d.heads + 2 * d.kv_heads) * hd;
   if ((d.flags & SLIME_FLAG_ROPE_INTERLEAVED) == 0) {
     SLIME_PROPAGATE(gemm(c, x, H, qkv_w, H, rows, QKV, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, qkv, nullptr,
-                         QKV, s));
-    return slime_launch_rope(qkv, QKV, rows, d.heads, d.kv_heads, hd, pos, c->rope_table, d.max_pos, s);
+                         QKV, s, ex));
+    SLIME_PROPAGATE(slime_launch_rope(qkv, QKV, rows, d.heads, d.kv_heads, hd, pos, c->rope_table, d.max_pos, s));
+    if (ex != nullptr && ex->kv_k != nullptr)
+      return slime_launch_kv_append(qkv + d.heads * hd, qkv + (d.heads + d.kv_heads) * hd, QKV, ex->kv_k, ex->kv_v,
+                                    d.kv_heads * hd, ex->kv_lens, rows, ex->kv_cache_len, s);
+    return SLIME_OK;
   }
   GemmParams p;
+  if (ex != nullptr) {
+    p.splitk_ws = ex->splitk_ws;
+    p.splitk_ws_floats = ex->splitk_ws_floats;
+    p.kv_k = ex->kv_k;
+    p.kv_v = ex->kv_v;
+    p.kv_lens = ex->kv_lens;
+    p.kv_cache_len = ex->kv_cache_len;
+    p.kv_dim = d.kv_heads * hd;
+    p.kv_q_cols = d.heads * hd;
+  }
   p.M = rows; p.N = QKV; p.K = H;
   p.bias = nullptr;
   p.residual = nullptr;
@@ -370,6 +408,10 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
 }
 
 // One decode step for B sequences: x [B, H] = embeddings of the tokens to append; lens[b] = tokens already cached.
+// HBM-bound (every weight byte is read once per step): the projections run on the weight-streaming kernel of
+// gemm_skinny.cu for B <= 32, attention on the split-KV kernel of decode_attn.cu; 7-8 launches per layer -
+//   qkv (+RoPE, K/V append) [+ split-K finish] | attention [+ split merge] | o-proj + finish(residual, RMSNorm) |
+//   gate/up (SwiGLU) | down-proj + finish(residual, next layer's RMSNorm).
 int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B, float* logits, cudaStream_t s) {
   const slime_model_desc& d = c->d;
   const int H = d.hidden, I = d.mlp, hd = d.head_dim;
@@ -379,31 +421,49 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
   bf16* qkv = a.get<bf16>(static_cast<size_t>(B) * QKV);
   bf16* att = a.get<bf16>(static_cast<size_t>(B) * QD);
   bf16* act = a.get<bf16>(static_cast<size_t>(B) * I);
-  int* rows = a.get<int>(B);
+  // split-K scratch of the projections: up to 8 splits of the [B, <= max(QKV, H)] outputs, 2 of the wide ones
+  const size_t wide = static_cast<size_t>(2 * I > d.vocab ? 2 * I : d.vocab);
+  const size_t narrow = static_cast<size_t>(QKV > H ? QKV : H);
+  const size_t sk_floats = static_cast<size_t>(B) * (8 * narrow > 2 * wide ? 8 * narrow : 2 * wide);
+  float* skws = a.get<float>(sk_floats);
+  // kv splits of the attention: sized for the attached cache (the dry run has none: assume the worst case)
+  const int cache_len = c->kv_cache != nullptr ? c->kv_cache_len : d.max_pos;
+  const int asplits = slime_decode_attention_splits(B, d.heads, d.kv_heads, hd, cache_len, c->num_sms);
+  const int asplits_max = slime_decode_attention_splits(B, d.heads, d.kv_heads, hd, d.max_pos, c->num_sms);
+  float* aws = a.get<float>(slime_decode_attention_ws_floats(B, d.heads, asplits_max > asplits ? asplits_max : asplits));
   ARENA_CHECK(a, "decode");
   if (a.dry || B <= 0) return SLIME_OK;
   SLIME_CHECK_CUDA(cudaMemcpyAsync(h, x_in, static_cast<size_t>(B) * H * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
-  SLIME_PROPAGATE(slime_launch_append_rows(lens, B, c->kv_cache_len, rows, s));
   const size_t plane = static_cast<size_t>(c->kv_cache_batch) * c->kv_cache_len * KD;
+  GemmExtra ex;
+  ex.splitk_ws = skws;
+  ex.splitk_ws_floats = sk_floats;
+  SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, c->llm[0].in_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
   for (int l = 0; l < d.layers; ++l) {
     const LlmLayer& L = c->llm[l];
     bf16* kc = c->kv_cache + (static_cast<size_t>(l) * 2 + 0) * plane;
     bf16* vc = c->kv_cache + (static_cast<size_t>(l) * 2 + 1) * plane;
-    SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.in_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
-    SLIME_PROPAGATE(qkv_rope(c, t, L.qkv_w, B, lens, qkv, s));
-    SLIME_PROPAGATE(slime_launch_scatter_rows(qkv + QD, QKV, kc, KD, B, KD, rows, s));
-    SLIME_PROPAGATE(slime_launch_scatter_rows(qkv + QD + KD, QKV, vc, KD, B, KD, rows, s));
+    GemmExtra exq = ex;  // QKV projection + RoPE; K / V of the new token go straight into the cache
+    exq.kv_k = kc;
+    exq.kv_v = vc;
+    exq.kv_lens = lens;
+    exq.kv_cache_len = c->kv_cache_len;
+    SLIME_PROPAGATE(qkv_rope(c, t, L.qkv_w, B, lens, qkv, s, &exq));
     SLIME_PROPAGATE(slime_launch_decode_attention(qkv, QKV, kc, vc, c->kv_cache_len, lens, B, d.heads, d.kv_heads, hd,
-                                                  1.0f / sqrtf(static_cast<float>(hd)), att, QD, s));
-    SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, B, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s));
-    SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.post_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
+                                                  1.0f / sqrtf(static_cast<float>(hd)), att, QD, asplits, aws, s));
+    GemmExtra exn = ex;  // projection + residual, then the RMSNorm that feeds the next GEMM
+    exn.norm_out = t;
+    exn.norm_ld = H;
+    exn.norm_eps = d.rms_eps;
+    exn.norm_w = L.post_norm_w;
+    SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, B, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s, &exn));
     SLIME_PROPAGATE(gemm(c, t, H, L.gate_up_w, H, B, 2 * I, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_SWIGLU, act,
-                         nullptr, I, s));
-    SLIME_PROPAGATE(gemm(c, act, I, L.down_w, I, B, H, I, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s));
+                         nullptr, I, s, &ex));
+    exn.norm_w = (l + 1 < d.layers) ? c->llm[l + 1].in_norm_w : c->llm_norm_w;
+    SLIME_PROPAGATE(gemm(c, act, I, L.down_w, I, B, H, I, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s, &exn));
   }
-  SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, c->llm_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
   SLIME_PROPAGATE(gemm(c, t, H, c->llm_lm_head, H, B, d.vocab, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, nullptr,
-                       logits, d.vocab, s));
+                       logits, d.vocab, s, &ex));
   return SLIME_OK;
 }
 
@@ -878,6 +938,50 @@ int slime_op_gemm(const void* a, int lda, const void* w, int ldw, int m, int n, 
   SLIME_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   return slime_launch_gemm(static_cast<const bf16*>(a), lda, static_cast<const bf16*>(w), ldw, p, epilogue, sms,
                            static_cast<cudaStream_t>(stream));
+}
+
+int slime_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
+                         const void* residual, int res_ld, int epilogue, void* out, float* out_f32, int out_ld,
+                         int splits, float* ws, size_t ws_floats, const void* norm_w, void* norm_out, float norm_eps,
+                         const int32_t* rope_pos, const float* rope_table, int rope_half, int rope_cols, int rope_max_pos,
+                         void* stream) {
+  GemmParams p;
+  p.M = m; p.N = n; p.K = k;
+  p.bias = static_cast<const bf16*>(bias);
+  p.residual = static_cast<const bf16*>(residual);
+  p.res_ld = res_ld;
+  p.res_period = 0;
+  p.row_map = nullptr;
+  p.out = static_cast<bf16*>(out);
+  p.out_f32 = out_f32;
+  p.out_ld = out_ld;
+  p.force_splits = splits;
+  p.splitk_ws = ws;
+  p.splitk_ws_floats = ws_floats;
+  p.norm_w = static_cast<const bf16*>(norm_w);
+  p.norm_out = static_cast<bf16*>(norm_out);
+  p.norm_ld = out_ld;
+  p.norm_eps = norm_eps;
+  p.rope_pos = rope_pos;
+  p.rope_table = reinterpret_cast<const float2*>(rope_table);
+  p.rope_half = rope_half;
+  p.rope_cols = rope_cols;
+  p.rope_max_pos = rope_max_pos;
+  SLIME_REQUIRE(splits >= 1, "gemm_skinny: splits must be >= 1");
+  int dev = 0, sms = 148;
+  SLIME_CHECK_CUDA(cudaGetDevice(&dev));
+  SLIME_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return slime_launch_gemm_skinny(static_cast<const bf16*>(a), lda, static_cast<const bf16*>(w), ldw, p, epilogue, sms,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int slime_op_decode_attention(const void* q, int q_ld, const void* kcache, const void* vcache, int cache_len,
+                              const int32_t* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
+                              void* out, int out_ld, int splits, float* ws, void* stream) {
+  return slime_launch_decode_attention(static_cast<const bf16*>(q), q_ld, static_cast<const bf16*>(kcache),
+                                       static_cast<const bf16*>(vcache), cache_len, lens, batch, heads, kv_heads,
+                                       head_dim, scale, static_cast<bf16*>(out), out_ld, splits, ws,
+                                       static_cast<cudaStream_t>(stream));
 }
 
 int slime_op_attention(const void* q, const void* k, const void* v, void* o, int q_ld, int k_ld, int v_ld, int o_ld,

@@ -43,12 +43,20 @@ int slime_launch_attention_tc(const AttnParams& p, int num_sms, cudaStream_t str
 
 // ---- decode step (decode_attn.cu) ----
 // q [batch, heads*head_dim] (row stride q_ld) against the cache k/v [batch, cache_len, kv_heads*head_dim];
-// sequence b attends its first lens[b] + 1 cached positions.
+// sequence b attends its first lens[b] + 1 cached positions.  splits >= 1 selects the split-KV kernel (one CTA per
+// kv head x sequence x split; ws = slime_decode_attention_ws_floats() floats when splits > 1); splits == 0, or a
+// shape the split kernel does not cover, runs the one-CTA-per-(q head, sequence) kernel.
 int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, const bf16* vcache, int cache_len,
                                   const int* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
-                                  bf16* out, int out_ld, cudaStream_t stream);
+                                  bf16* out, int out_ld, int splits, float* ws, cudaStream_t stream);
+// kv splits that fill the GPU for this problem (0: the split kernel does not apply / is switched off)
+int slime_decode_attention_splits(int batch, int heads, int kv_heads, int head_dim, int cache_len, int num_sms);
+size_t slime_decode_attention_ws_floats(int batch, int heads, int splits);
 // rows[i] = sample(i) * cache_len + pos_ids[i] for the packed prefill rows (-1 when pos >= cache_len)
 int slime_launch_cache_rows(const int* cu, const int* pos_ids, int B, int total, int cache_len, int* rows,
                             cudaStream_t stream);
+// cache[b, lens[b]] = this step's K / V rows (k, v: [B, KD] slices with row stride ld), both planes in one launch
+int slime_launch_kv_append(const bf16* k, const bf16* v, int ld, bf16* kcache, bf16* vcache, int KD, const int* lens,
+                           int B, int cache_len, cudaStream_t stream);
 // rows[b] = b * cache_len + lens[b]
 int slime_launch_append_rows(const int* lens, int B, int cache_len, int* rows, cudaStream_t stream);

@@ -231,6 +231,15 @@ SLIME_DEVINL float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 #endif
+// ---- programmatic dependent launch (PDL): a kernel launched with the attribute may become resident while its
+// predecessor in the stream is still running; it must execute pdl_wait() before touching anything the predecessor
+// (or, transitively, anything earlier) writes or reads-then-overwrites.  What comes BEFORE the wait - in the decode
+// GEMM the first 8 KB per warp of the (immutable) weight stream - overlaps the predecessor's tail and the launch
+// latency.  pdl_trigger() lets the NEXT kernel in the stream do the same with this one.  Both are no-ops for a
+// kernel launched without the attribute.
+SLIME_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+SLIME_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 SLIME_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

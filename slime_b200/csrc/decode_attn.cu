@@ -2,6 +2,8 @@
 // prefill in generate() (reference llava_llama.py:139 -> HF generation loop).
 // HBM-bound: every cached K/V row of the sequence is read once per q head group; one CTA per (q head, sequence),
 // 4 warps stride over the cached positions with an online softmax each and are merged through shared memory.
+#include <cstdlib>
+
 #include "attention.h"
 #include "errors.h"
 
@@ -92,6 +94,225 @@ __global__ void __launch_bounds__(NT) decode_attn_kernel(const bf16* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Split-KV ("flash-decoding") variant: the kernel above has one CTA per (q head, sequence), i.e. 32 CTAs for one
+// sequence, each walking all cached positions with one 256-byte row in flight per warp, and every K/V row is
+// fetched once per q head of its GQA group.  Here a CTA owns (kv head, sequence, kv split): the cached positions
+// are divided over `splits` CTAs so that a single sequence still fills the GPU, all G = heads / kv_heads query heads
+// of the group share every K/V row, and two rows per 8-lane group are in flight.
+//   lanes: 4 position groups x 8 lanes per warp; lane sl of a group holds features [8 sl, 8 sl + 8) and
+//   [64 + 8 sl, 64 + 8 sl + 8) of the row, so each 16-byte load instruction of a group reads 128 contiguous bytes;
+//   a dot product is 16 FMAs + 3 shuffles per (position, q head).
+// Every (warp, position group) keeps its own online-softmax state; the 16 states of a CTA are merged through shared
+// memory, the per-split results (max, sum, unnormalised accumulator) go to an fp32 scratch and a small kernel merges
+// the splits (splits == 1: the CTA writes the final row itself).
+// ------------------------------------------------------------------------------------------
+constexpr int DS_HD = 128;
+constexpr int DS_POS_PER_ITER = 16;  // 4 warps x 4 position groups
+
+SLIME_DEVINL uint4 ld_nc16(const bf16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+SLIME_DEVINL void unpack16(const uint4& a, const uint4& b, float (&f)[16]) {
+  const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 t = unpack_bf16x2(u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(NT) decode_attn_split_kernel(const bf16* __restrict__ q, int q_ld,
+                                                               const bf16* __restrict__ kcache,
+                                                               const bf16* __restrict__ vcache, int cache_len,
+                                                               const int* __restrict__ lens, int heads, int kv_heads,
+                                                               float scale_log2, int splits, float* __restrict__ part,
+                                                               bf16* __restrict__ out, int out_ld) {
+  // merged through shared memory: [16 states][G][HD] accumulators + [16][G] max / sum
+  extern __shared__ __align__(16) uint8_t ds_smem[];
+  float* s_acc = reinterpret_cast<float*>(ds_smem);
+  float* s_m = s_acc + 16 * G * DS_HD;
+  float* s_l = s_m + 16 * G;
+
+  pdl_trigger();
+  pdl_wait();  // q, the cache rows appended in this step and lens come from the kernels before
+
+  const int kvh = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pg = lane >> 3, sl = lane & 7;
+  const int len = min(__ldcg(lens + b) + 1, cache_len);  // cached tokens + the one appended in this step
+  const int KD = kv_heads * DS_HD;
+  // this split's positions [p0, p1): equal chunks, multiples of 32 (two rounds of 16 positions per iteration)
+  const int chunk = ((len + splits - 1) / splits + 2 * DS_POS_PER_ITER - 1) / (2 * DS_POS_PER_ITER) * (2 * DS_POS_PER_ITER);
+  const int p0 = split * chunk, p1 = min(len, p0 + chunk);
+
+  float qv[G][16];
+#pragma unroll
+  for (int gi = 0; gi < G; ++gi) {
+    const bf16* qp = q + static_cast<long long>(b) * q_ld + (kvh * G + gi) * DS_HD + sl * 8;
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(qp)), c = __ldcg(reinterpret_cast<const uint4*>(qp + 64));
+    unpack16(a, c, qv[gi]);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) qv[gi][e] *= scale_log2;
+  }
+  float m[G], l[G], acc[G][16];
+#pragma unroll
+  for (int gi = 0; gi < G; ++gi) {
+    m[gi] = -INFINITY;
+    l[gi] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[gi][e] = 0.f;
+  }
+
+  const long long base = (static_cast<long long>(b) * cache_len) * KD + kvh * DS_HD + sl * 8;
+  struct Row {
+    uint4 k0, k1, v0, v1;
+  };
+  auto fetch = [&](int pos) {
+    Row r;
+    r.k0 = r.k1 = r.v0 = r.v1 = make_uint4(0u, 0u, 0u, 0u);
+    if (pos < p1) {
+      const bf16* kp = kcache + base + static_cast<long long>(pos) * KD;
+      const bf16* vp = vcache + base + static_cast<long long>(pos) * KD;
+      r.k0 = ld_nc16(kp); r.k1 = ld_nc16(kp + 64); r.v0 = ld_nc16(vp); r.v1 = ld_nc16(vp + 64);
+    }
+    return r;
+  };
+  auto step = [&](const Row& r, int pos) {
+    float kf[16], vf[16];
+    unpack16(r.k0, r.k1, kf);
+    unpack16(r.v0, r.v1, vf);
+    const bool valid = pos < p1;
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) s = fmaf(qv[gi][e], kf[e], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (valid) {
+        const float m_new = fmaxf(m[gi], s);
+        const float alpha = exp2f(m[gi] - m_new);  // first position: exp2(-inf) = 0
+        const float pe = exp2f(s - m_new);
+        l[gi] = l[gi] * alpha + pe;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[gi][e] = fmaf(acc[gi][e], alpha, pe * vf[e]);
+        m[gi] = m_new;
+      }
+    }
+  };
+
+  // Two positions per lane group and iteration, the next two already in flight: 4 rows x 512 B per 8 lanes = 16 KB per
+  // warp in flight.  Every lane of a warp runs the same number of iterations (the shuffles need the full warp).
+  int pos = p0 + warp * 4 + pg;
+  Row ra = fetch(pos), rb = fetch(pos + DS_POS_PER_ITER);
+  const int iters = (p1 - p0 + 2 * DS_POS_PER_ITER - 1) / (2 * DS_POS_PER_ITER);
+  for (int it = 0; it < iters; ++it, pos += 2 * DS_POS_PER_ITER) {
+    const Row na = fetch(pos + 2 * DS_POS_PER_ITER), nb = fetch(pos + 3 * DS_POS_PER_ITER);
+    step(ra, pos);
+    step(rb, pos + DS_POS_PER_ITER);
+    ra = na;
+    rb = nb;
+  }
+
+  // ---- merge the 16 (warp, position group) states of this CTA ----
+  const int st = warp * 4 + pg;
+#pragma unroll
+  for (int gi = 0; gi < G; ++gi) {
+    if (sl == 0) {
+      s_m[st * G + gi] = m[gi];
+      s_l[st * G + gi] = l[gi];
+    }
+    float* dst = s_acc + (st * G + gi) * DS_HD + sl * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      dst[e] = acc[gi][e];
+      dst[64 + e] = acc[gi][8 + e];
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < G * DS_HD; o += NT) {
+    const int gi = o / DS_HD, e = o % DS_HD;
+    float mt = -INFINITY;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) mt = fmaxf(mt, s_m[s2 * G + gi]);
+    float lt = 0.f, val = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) {
+      const float ms = s_m[s2 * G + gi];
+      const float a = (ms == -INFINITY) ? 0.f : exp2f(ms - mt);
+      lt += s_l[s2 * G + gi] * a;
+      val += s_acc[(s2 * G + gi) * DS_HD + e] * a;
+    }
+    const int head = kvh * G + gi;
+    if (part == nullptr) {
+      out[static_cast<long long>(b) * out_ld + head * DS_HD + e] = float_to_elem(lt > 0.f ? val / lt : 0.f);
+    } else {
+      float* pp = part + ((static_cast<long long>(b) * heads + head) * splits + split) * (DS_HD + 2);
+      pp[e] = val;
+      if (e == 0) {
+        pp[DS_HD] = mt;
+        pp[DS_HD + 1] = lt;
+      }
+    }
+  }
+}
+
+// out[b, head] = sum_s acc_s 2^(m_s - M) / sum_s l_s 2^(m_s - M)   (fixed order over the splits)
+__global__ void __launch_bounds__(DS_HD) decode_attn_merge_kernel(const float* __restrict__ part, int heads, int splits,
+                                                                  bf16* __restrict__ out, int out_ld) {
+  pdl_trigger();
+  pdl_wait();
+  const int head = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
+  const float* pp = part + (static_cast<long long>(b) * heads + head) * splits * (DS_HD + 2);
+  float mt = -INFINITY;
+  for (int s = 0; s < splits; ++s) mt = fmaxf(mt, __ldcg(pp + s * (DS_HD + 2) + DS_HD));
+  float lt = 0.f, val = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float ms = __ldcg(pp + s * (DS_HD + 2) + DS_HD);
+    const float a = (ms == -INFINITY) ? 0.f : exp2f(ms - mt);
+    lt += __ldcg(pp + s * (DS_HD + 2) + DS_HD + 1) * a;
+    val += __ldcg(pp + s * (DS_HD + 2) + e) * a;
+  }
+  out[static_cast<long long>(b) * out_ld + head * DS_HD + e] = float_to_elem(lt > 0.f ? val / lt : 0.f);
+}
+
+int g_decode_attn_mode = -1;  // -1 unset, 0 = one CTA per (q head, sequence), 1 = split-KV
+
+bool decode_split_supported(int heads, int kv_heads, int head_dim) {
+  if (g_decode_attn_mode < 0) {
+    const char* e = getenv("SLIME_DECODE_ATTN");
+    g_decode_attn_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (g_decode_attn_mode == 0 || head_dim != DS_HD || kv_heads <= 0 || heads % kv_heads != 0) return false;
+  const int G = heads / kv_heads;
+  return G == 1 || G == 2 || G == 4;  // G = 8 would spill (2 x 128 fp32 of state per lane): old kernel
+}
+
+template <int G>
+int launch_split(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, int cache_len, const int* lens, int batch,
+                 int heads, int kv_heads, float sl2, int splits, float* part, bf16* out, int out_ld,
+                 cudaStream_t stream) {
+  const int smem = (16 * G * DS_HD + 32 * G) * static_cast<int>(sizeof(float));
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    SLIME_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_split_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(kv_heads, batch, splits);
+  SLIME_CHECK_CUDA(slime_launch_kernel(decode_attn_split_kernel<G>, grid, dim3(NT), smem, stream, true, q, q_ld, kc, vc,
+                                       cache_len, lens, heads, kv_heads, sl2, splits,
+                                       splits > 1 ? part : static_cast<float*>(nullptr), out, out_ld));
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
+
 // cache_rows[i] = sample(i) * cache_len + pos_ids[i]   (packed prefill row -> slot in the per-sequence cache)
 __global__ void cache_rows_kernel(const int* __restrict__ cu, const int* __restrict__ pos_ids, int B, int total,
                                   int cache_len, int* __restrict__ rows) {
@@ -112,15 +333,87 @@ __global__ void append_rows_kernel(const int* __restrict__ lens, int B, int cach
   if (b < B) rows[b] = lens[b] < cache_len ? b * cache_len + lens[b] : -1;
 }
 
+// Appends the K / V slices of this step's qkv rows to the cache: row b -> slot lens[b] of sequence b
+// (dropped when the cache is full).  One launch for both planes, 16 bytes per thread.
+__global__ void kv_append_kernel(const bf16* __restrict__ k, const bf16* __restrict__ v, int ld, bf16* __restrict__ kc,
+                                 bf16* __restrict__ vc, int KD, const int* __restrict__ lens, int B, int cache_len) {
+  pdl_trigger();
+  pdl_wait();
+  const int chunks = KD >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * chunks * 2) return;
+  const int which = i / (B * chunks), r = i % (B * chunks);
+  const int b = r / chunks, ch = r % chunks;
+  const int pos = __ldcg(lens + b);
+  if (pos < 0 || pos >= cache_len) return;
+  const bf16* src = (which == 0 ? k : v) + static_cast<long long>(b) * ld + ch * 8;
+  bf16* dst = (which == 0 ? kc : vc) + (static_cast<long long>(b) * cache_len + pos) * KD + ch * 8;
+  *reinterpret_cast<uint4*>(dst) = __ldcg(reinterpret_cast<const uint4*>(src));
+}
+
 }  // namespace
+
+int slime_launch_kv_append(const bf16* k, const bf16* v, int ld, bf16* kcache, bf16* vcache, int KD, const int* lens,
+                           int B, int cache_len, cudaStream_t stream) {
+  SLIME_REQUIRE(KD % 8 == 0 && ld % 8 == 0, "kv append: bad KD=%d ld=%d", KD, ld);
+  if (B <= 0) return SLIME_OK;
+  const int total = B * (KD / 8) * 2;
+  SLIME_CHECK_CUDA(slime_launch_kernel(kv_append_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, true, k, v, ld,
+                                       kcache, vcache, KD, lens, B, cache_len));
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
+
+extern "C" int slime_decode_attention_set_mode(int mode) {
+  g_decode_attn_mode = mode < 0 ? -1 : (mode != 0 ? 1 : 0);
+  return SLIME_OK;
+}
+
+int slime_decode_attention_splits(int batch, int heads, int kv_heads, int head_dim, int cache_len, int num_sms) {
+  if (!decode_split_supported(heads, kv_heads, head_dim) || batch <= 0) return 0;
+  const int ctas = kv_heads * batch;
+  int s = (2 * num_sms) / ctas;                      // ONE wave of (at most) two CTAs per SM: no tail
+  const int by_len = (cache_len + 63) / 64;          // about 64 cached positions per split at least
+  if (s > by_len) s = by_len;
+  if (s > 32) s = 32;
+  return s < 1 ? 1 : s;
+}
+
+size_t slime_decode_attention_ws_floats(int batch, int heads, int splits) {
+  return splits > 1 ? static_cast<size_t>(batch) * heads * splits * (DS_HD + 2) : 0;
+}
 
 int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, const bf16* vcache, int cache_len,
                                   const int* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
-                                  bf16* out, int out_ld, cudaStream_t stream) {
+                                  bf16* out, int out_ld, int splits, float* ws, cudaStream_t stream) {
   SLIME_REQUIRE(head_dim == 64 || head_dim == 128, "decode attention: head_dim %d unsupported", head_dim);
   if (batch <= 0) return SLIME_OK;
-  dim3 grid(heads, batch);
   const float sl2 = scale * 1.4426950408889634f;
+  if (splits >= 1 && decode_split_supported(heads, kv_heads, head_dim)) {
+    SLIME_REQUIRE(splits == 1 || ws != nullptr, "decode attention: %d kv splits need a scratch buffer", splits);
+    SLIME_REQUIRE(q_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(kcache) & 15) == 0 && (reinterpret_cast<uintptr_t>(vcache) & 15) == 0,
+                  "decode attention: q / cache must be 16-byte aligned");
+    const int G = heads / kv_heads;
+    const double bytes = 2.0 * batch * static_cast<double>(cache_len) * kv_heads * head_dim * sizeof(bf16);  // upper bound
+    slime_prof_begin(1, bytes, stream);
+    int rc = SLIME_OK;
+    switch (G) {
+      case 1: rc = launch_split<1>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, stream); break;
+      case 2: rc = launch_split<2>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, stream); break;
+      default: rc = launch_split<4>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, stream); break;
+    }
+    slime_prof_end(stream);
+    SLIME_PROPAGATE(rc);
+    if (splits > 1) {
+      const float* part = ws;
+      SLIME_CHECK_CUDA(slime_launch_kernel(decode_attn_merge_kernel, dim3(heads, batch), dim3(DS_HD), 0, stream, true, part,
+                                           heads, splits, out, out_ld));
+      SLIME_AFTER_LAUNCH();
+    }
+    return SLIME_OK;
+  }
+  dim3 grid(heads, batch);
   slime_prof_begin(1, 0.0, stream);
   if (head_dim == 128) {
     decode_attn_kernel<128><<<grid, NT, 0, stream>>>(q, q_ld, kcache, vcache, cache_len, lens, heads, kv_heads, sl2, out, out_ld);

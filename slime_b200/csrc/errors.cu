@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -30,6 +31,21 @@ std::vector<ProfRec> g_recs;
 ProfRec g_open;
 bool g_has_open = false;
 }  // namespace
+
+namespace {
+int g_pdl_mode = -1;  // -1 unset, 0 off, 1 on
+}
+bool slime_pdl_enabled() {
+  if (g_pdl_mode < 0) {
+    const char* e = getenv("SLIME_PDL");
+    g_pdl_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl_mode != 0;
+}
+extern "C" int slime_set_pdl_mode(int mode) {
+  g_pdl_mode = mode < 0 ? -1 : (mode != 0 ? 1 : 0);
+  return SLIME_OK;
+}
 
 void slime_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool slime_prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }

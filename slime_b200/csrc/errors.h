@@ -43,3 +43,22 @@ void slime_prof_end(cudaStream_t stream);
     int _rc = (expr);                  \
     if (_rc != SLIME_OK) return _rc;   \
   } while (0)
+
+// Launch with (pdl = true) or without the programmatic-stream-serialization attribute (see pdl_wait() in common.cuh).
+// SLIME_PDL=0 / slime_set_pdl_mode(0) launch everything the ordinary way.
+bool slime_pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t slime_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && slime_pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}

@@ -30,6 +30,24 @@ struct GemmParams {
   int rope_max_pos = 0;
   int epi_mode = 0;    // HBM access pattern of the epilogue (gemm_epilogue.cuh): 0 direct, 1 staged through shared
                        // memory (coalesced stores and residual loads); filled in by slime_launch_gemm
+  // ---- decode-step problems (M <= 32 rows; gemm_skinny.cu) ----
+  float* splitk_ws = nullptr;   // optional fp32 scratch for split-K partial sums [splits, M, N]
+  size_t splitk_ws_floats = 0;  // its capacity; too small / absent: the problem runs unsplit
+  int force_splits = 0;         // tests: > 0 forces the weight-streaming kernel with this many k-splits
+  // optional RMSNorm of the output rows (EPI_NONE, bf16 out): norm_out = norm_w * bf16(out * rsqrt(mean(out^2) + eps)).
+  // Fused into the split-K finishing kernel on the weight-streaming path, a separate rmsnorm launch otherwise.
+  const bf16* norm_w = nullptr;
+  bf16* norm_out = nullptr;
+  int norm_ld = 0;
+  float norm_eps = 0.f;
+  // optional KV-cache append of the decode step's packed QKV projection: output columns [kv_q_cols, kv_q_cols + kv_dim)
+  // of row m also go to kv_k[(m * kv_cache_len + kv_lens[m]) * kv_dim + ...], the next kv_dim columns to kv_v (dropped
+  // when the slot is outside the cache).  Done by the epilogue on the weight-streaming path, by a kv_append launch after
+  // the GEMM otherwise.
+  bf16* kv_k = nullptr;
+  bf16* kv_v = nullptr;
+  const int* kv_lens = nullptr;
+  int kv_cache_len = 0, kv_dim = 0, kv_q_cols = 0;
 };
 
 // 0 = 1-CTA kernel only, 1 = always the 2-CTA kernel, 2 = 2-CTA for problems that fill the GPU.
@@ -44,6 +62,12 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
 // cta_group::2 variant (256 x 256 cluster tiles); arguments already validated by slime_launch_gemm.
 int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                            int num_sms, cudaStream_t stream);
+
+// Weight-streaming kernel for M <= 32 rows (gemm_skinny.cu; the decode step).  slime_launch_gemm routes to it when
+// slime_gemm_skinny_applies(); SLIME_GEMM_SKINNY=0 / slime_gemm_set_skinny_mode(0) keep such problems on the tcgen05 path.
+bool slime_gemm_skinny_applies(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms);
+int slime_launch_gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
+                             int num_sms, cudaStream_t stream);
 
 // Epilogue access pattern used by slime_launch_gemm (SLIME_GEMM_EPI_MODE overrides the compile-time default).
 #ifndef SLIME_GEMM_EPI_MODE_DEFAULT

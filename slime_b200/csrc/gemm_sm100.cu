@@ -21,6 +21,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "attention.h"
+#include "elementwise.h"
 #include "errors.h"
 #include "gemm.h"
 
@@ -381,6 +383,31 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
                       (p.rope_half & (p.rope_half - 1)) == 0 && p.rope_cols % (2 * p.rope_half) == 0 &&
                       p.rope_max_pos > 0 && p.residual == nullptr,
                   "gemm: bad RoPE epilogue configuration (half=%d cols=%d)", p.rope_half, p.rope_cols);
+
+  if (p.norm_w != nullptr)
+    SLIME_REQUIRE(epi == GEMM_EPI_NONE && p.out != nullptr && p.out_f32 == nullptr && p.norm_out != nullptr &&
+                      p.row_map == nullptr && p.norm_ld % 8 == 0,
+                  "gemm: bad fused-RMSNorm configuration");
+
+  // Decode-step problems (M <= 32): HBM-bound weight streaming instead of 128-row tensor-core tiles.
+  if (p.M <= 32 && slime_gemm_skinny_applies(A, lda, W, ldw, p, epi, num_sms))
+    return slime_launch_gemm_skinny(A, lda, W, ldw, p, epi, num_sms, stream);
+  if (p.norm_w != nullptr) {  // not fusable here: GEMM, then the RMSNorm of its output rows
+    GemmParams q = p_in;
+    q.norm_w = nullptr;
+    q.norm_out = nullptr;
+    SLIME_PROPAGATE(slime_launch_gemm(A, lda, W, ldw, q, epi, num_sms, stream));
+    return slime_launch_rmsnorm(p.out, p.out_ld, p.norm_w, p.norm_out, p.norm_ld, p.M, p.N, p.norm_eps, nullptr, stream);
+  }
+  if (p.kv_k != nullptr) {  // same for the KV-cache append of the decode step's QKV projection
+    SLIME_REQUIRE(p.out != nullptr && p.kv_v != nullptr && p.kv_lens != nullptr && p.kv_q_cols + 2 * p.kv_dim == p.N,
+                  "gemm: bad KV append configuration");
+    GemmParams q = p_in;
+    q.kv_k = nullptr;
+    SLIME_PROPAGATE(slime_launch_gemm(A, lda, W, ldw, q, epi, num_sms, stream));
+    return slime_launch_kv_append(p.out + p.kv_q_cols, p.out + p.kv_q_cols + p.kv_dim, p.out_ld, p.kv_k, p.kv_v, p.kv_dim,
+                                  p.kv_lens, p.M, p.kv_cache_len, stream);
+  }
 
   // BLOCK_N = 256 halves the A re-reads; fall back to 128 when the 256-wide grid cannot fill the GPU.
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
