@@ -435,12 +435,49 @@ def main():
     torch.cuda.synchronize()
     crops_per_s = 5 * flat.shape[0] / (e0.elapsed_time(e1) / 1e3) * world
 
+    # ---- decode step after this prefill (secondary, HBM-bound): ms per generated token ----
+    decode = None
+    try:
+        n_dec = 16
+        eng.attach_kv_cache(B, max(lengths) + n_dec + 8)
+        res_d = eng.prefill(px_d, ids_d, mask_d, grids=grids)  # fills the cache
+        lens_d = torch.tensor(res_d.lengths, dtype=torch.int32, device=dev)
+        table = eng.weights["llm.embed"]
+        x_d = table[res_d.logits_last.argmax(-1)]
+        for _ in range(3):
+            eng.decode_step(x_d, lens_d)  # (same slot rewritten: timing only)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.slime_launch_count()
+        e0.record()
+        for _ in range(n_dec):
+            eng.decode_step(x_d, lens_d)
+        e1.record()
+        torch.cuda.synchronize()
+        dms = e0.elapsed_time(e1) / n_dec
+        w_bytes = 2 * (cfg.num_hidden_layers * (cfg.qkv_dim * cfg.hidden_size + cfg.hidden_size * cfg.num_attention_heads * cfg.head_dim
+                                                 + 3 * cfg.intermediate_size * cfg.hidden_size) + cfg.vocab_size * cfg.hidden_size)
+        kv_bytes = cfg.num_hidden_layers * sum(res_d.lengths) * 2 * cfg.num_key_value_heads * cfg.head_dim * 2
+        decode = {"batch": B, "ms_per_step": dms, "tokens_per_s": B / dms * 1e3 * world, "context": float(statistics.mean(lengths)),
+                  "launches_per_step": (lib.slime_launch_count() - n0) / n_dec,
+                  "hbm_bytes_per_step": w_bytes + kv_bytes, "achieved_gbs": (w_bytes + kv_bytes) / dms / 1e6}
+    except Exception as e:  # noqa: BLE001 - never lose the prefill line over the secondary figure
+        decode = {"error": repr(e)}
+    finally:
+        try:
+            eng.detach_kv_cache()
+        except Exception:  # noqa: BLE001
+            pass
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peaks = measured_peaks()
+    if decode is not None and "achieved_gbs" in decode:
+        decode["frac_of_hbm_peak"] = decode["achieved_gbs"] / peaks["hbm"]
+        decode["kernels"] = "weight-streaming mma.sync GEMM (csrc/gemm_skinny.cu) + split-KV mma.sync attention (csrc/decode_attn.cu), PDL"
     fl = algorithmic_flops(cfg, args.crops * B, lengths, (args.crops - 1) * B * cfg.mm_resampler_dim)
     gemm_tf = pwork[0] / (pms[0] / 1e3) / 1e12 if pms[0] > 0 else 0.0
     step_ms = ms / args.steps
@@ -472,6 +509,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "e2e_from_rgb_bytes": raw,
+        "decode_step": decode,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "algorithmic_tflop_per_step": {k: v / 1e12 for k, v in fl.items()},
     }

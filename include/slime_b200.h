@@ -265,6 +265,11 @@ int slime_decode_attention_set_mode(int mode);
 /* Programmatic dependent launch of the decode-step kernels (their weight prefetch / prologue overlaps the previous
  * kernel's tail): 1 on (default), 0 ordinary stream-ordered launches, -1 = back to the SLIME_PDL environment variable. */
 int slime_set_pdl_mode(int mode);
+/* L2 prefetch duties of the decode step's latency-bound kernels (bit mask; csrc/api.cu decode_body): 1 = the QKV
+ * finishing kernel pulls the o-projection's weights, 2 = the down-projection's finishing kernel pulls the next layer's
+ * QKV weights, 4 / 8 = the attention kernel / the o-projection's finishing kernel pull 32 MB of gate/up each;
+ * -1 = back to SLIME_DECODE_PREFETCH / the build default (0: measured slower than no prefetch in every variant). */
+int slime_set_decode_prefetch(int mask);
 /* debug: CTA 0 of the tcgen05 attention kernel stamps clock64() of its first 64 tiles into buf [64][16] (NULL = off) */
 int slime_attention_set_trace(long long* buf);
 /* softmax arithmetic of the tcgen05 attention kernel: 0 = scalar FFMA + MUFU.EX2; 5 / 9 = packed fp32 pairs

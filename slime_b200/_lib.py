@@ -143,6 +143,7 @@ SIGNATURES = {
     "slime_gemm_set_skinny_mode": (_i, [_i]),
     "slime_decode_attention_set_mode": (_i, [_i]),
     "slime_set_pdl_mode": (_i, [_i]),
+    "slime_set_decode_prefetch": (_i, [_i]),
     "slime_attention_set_trace": (_i, [_vp]),
     "slime_attention_set_variant": (_i, [_i]),
     "slime_launch_count": (C.c_longlong, []),

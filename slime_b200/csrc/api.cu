@@ -4,6 +4,7 @@
 // caller's stream; scratch comes from the caller's workspace through a bump arena whose dry-run
 // twin implements the *_workspace_bytes() queries, so the two can never disagree.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -91,6 +92,9 @@ struct slime_ctx {
 
 namespace {
 
+#ifndef SLIME_DECODE_PREFETCH_DEFAULT
+#define SLIME_DECODE_PREFETCH_DEFAULT 0  // measured: every mask is slower than none (profiles/r01_decode_bench.txt)
+#endif
 constexpr int VIT_CHUNK_CROPS = 128;  // crops per pass through the ViT (bounds the workspace to ~1.6 GB)
 
 int find_weight(slime_ctx* c, const std::string& name, int64_t rows, int64_t cols, const bf16** out) {
@@ -118,6 +122,8 @@ int find_weight(slime_ctx* c, const std::string& name, int64_t rows, int64_t col
 struct GemmExtra {
   float* splitk_ws = nullptr;
   size_t splitk_ws_floats = 0;
+  const void* l2_prefetch = nullptr;  // weights of a later projection, pulled into L2 by this one's finishing kernel
+  size_t l2_prefetch_bytes = 0;
   bf16* kv_k = nullptr;  // qkv_rope only: append this step's K / V rows to the cache (slot kv_lens[row] of sequence row)
   bf16* kv_v = nullptr;
   const int* kv_lens = nullptr;
@@ -135,6 +141,8 @@ int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, in
   if (ex != nullptr) {
     p.splitk_ws = ex->splitk_ws;
     p.splitk_ws_floats = ex->splitk_ws_floats;
+    p.l2_prefetch = ex->l2_prefetch;
+    p.l2_prefetch_bytes = ex->l2_prefetch_bytes;
     p.norm_w = ex->norm_w;
     p.norm_out = ex->norm_out;
     p.norm_ld = ex->norm_ld;
@@ -174,6 +182,8 @@ int qkv_rope(slime_ctx* c, const bf16* x, const bf16* qkv_w, int rows, const int
   if (ex != nullptr) {
     p.splitk_ws = ex->splitk_ws;
     p.splitk_ws_floats = ex->splitk_ws_floats;
+    p.l2_prefetch = ex->l2_prefetch;
+    p.l2_prefetch_bytes = ex->l2_prefetch_bytes;
     p.kv_k = ex->kv_k;
     p.kv_v = ex->kv_v;
     p.kv_lens = ex->kv_lens;
@@ -407,6 +417,15 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
   return SLIME_OK;
 }
 
+int g_decode_pf = -1;  // -1 unset (SLIME_DECODE_PREFETCH or the default), else the mask
+int decode_prefetch_mask() {
+  if (g_decode_pf < 0) {
+    const char* e = getenv("SLIME_DECODE_PREFETCH");
+    g_decode_pf = (e != nullptr && e[0] >= '0' && e[0] <= '9') ? atoi(e) : SLIME_DECODE_PREFETCH_DEFAULT;
+  }
+  return g_decode_pf;
+}
+
 // One decode step for B sequences: x [B, H] = embeddings of the tokens to append; lens[b] = tokens already cached.
 // HBM-bound (every weight byte is read once per step): the projections run on the weight-streaming kernel of
 // gemm_skinny.cu for B <= 32, attention on the split-KV kernel of decode_attn.cu; 7-8 launches per layer -
@@ -438,28 +457,55 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
   GemmExtra ex;
   ex.splitk_ws = skws;
   ex.splitk_ws_floats = sk_floats;
+  const int pf = decode_prefetch_mask();
   SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, c->llm[0].in_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
   for (int l = 0; l < d.layers; ++l) {
     const LlmLayer& L = c->llm[l];
     bf16* kc = c->kv_cache + (static_cast<size_t>(l) * 2 + 0) * plane;
     bf16* vc = c->kv_cache + (static_cast<size_t>(l) * 2 + 1) * plane;
+    // L2 prefetch duties (bit mask, slime_set_decode_prefetch; OFF by default - on B200 every variant measured
+    // slower than none, 4.26 -> 5.7..7.9 ms per step): the latency-bound kernels between the projections would keep
+    // HBM busy with weights that are needed next -
+    //   1: the QKV finishing kernel pulls the o-projection (used after the attention),
+    //   2: the down-projection's finishing kernel pulls the next layer's QKV weights (or the head of lm_head),
+    //   4: the attention kernel pulls the first PF_PART bytes of gate/up, 8: the o-projection's finishing kernel too.
+    constexpr size_t PF_PART = 32u << 20;
+    const size_t gu_bytes = static_cast<size_t>(2) * I * H * sizeof(bf16);
     GemmExtra exq = ex;  // QKV projection + RoPE; K / V of the new token go straight into the cache
     exq.kv_k = kc;
     exq.kv_v = vc;
     exq.kv_lens = lens;
     exq.kv_cache_len = c->kv_cache_len;
+    if (pf & 1) {
+      exq.l2_prefetch = L.o_w;
+      exq.l2_prefetch_bytes = static_cast<size_t>(H) * QD * sizeof(bf16);
+    }
     SLIME_PROPAGATE(qkv_rope(c, t, L.qkv_w, B, lens, qkv, s, &exq));
     SLIME_PROPAGATE(slime_launch_decode_attention(qkv, QKV, kc, vc, c->kv_cache_len, lens, B, d.heads, d.kv_heads, hd,
-                                                  1.0f / sqrtf(static_cast<float>(hd)), att, QD, asplits, aws, s));
+                                                  1.0f / sqrtf(static_cast<float>(hd)), att, QD, asplits, aws,
+                                                  (pf & 4) ? L.gate_up_w : nullptr,
+                                                  (pf & 4) ? (gu_bytes < PF_PART ? gu_bytes : PF_PART) : 0, s));
     GemmExtra exn = ex;  // projection + residual, then the RMSNorm that feeds the next GEMM
     exn.norm_out = t;
     exn.norm_ld = H;
     exn.norm_eps = d.rms_eps;
     exn.norm_w = L.post_norm_w;
+    if ((pf & 8) && gu_bytes > PF_PART) {
+      exn.l2_prefetch = reinterpret_cast<const char*>(L.gate_up_w) + ((pf & 4) ? PF_PART : 0);
+      exn.l2_prefetch_bytes = (gu_bytes - ((pf & 4) ? PF_PART : 0)) < PF_PART ? gu_bytes - ((pf & 4) ? PF_PART : 0) : PF_PART;
+    }
     SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, B, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s, &exn));
     SLIME_PROPAGATE(gemm(c, t, H, L.gate_up_w, H, B, 2 * I, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_SWIGLU, act,
                          nullptr, I, s, &ex));
     exn.norm_w = (l + 1 < d.layers) ? c->llm[l + 1].in_norm_w : c->llm_norm_w;
+    exn.l2_prefetch = nullptr;
+    exn.l2_prefetch_bytes = 0;
+    if (pf & 2) {
+      const size_t head_bytes = static_cast<size_t>(d.vocab) * H * sizeof(bf16);
+      exn.l2_prefetch = (l + 1 < d.layers) ? c->llm[l + 1].qkv_w : c->llm_lm_head;
+      exn.l2_prefetch_bytes = (l + 1 < d.layers) ? static_cast<size_t>(QKV) * H * sizeof(bf16)
+                                                 : (head_bytes < 2 * PF_PART ? head_bytes : 2 * PF_PART);
+    }
     SLIME_PROPAGATE(gemm(c, act, I, L.down_w, I, B, H, I, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s, &exn));
   }
   SLIME_PROPAGATE(gemm(c, t, H, c->llm_lm_head, H, B, d.vocab, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, nullptr,
@@ -940,6 +986,11 @@ int slime_op_gemm(const void* a, int lda, const void* w, int ldw, int m, int n, 
                            static_cast<cudaStream_t>(stream));
 }
 
+int slime_set_decode_prefetch(int mask) {
+  g_decode_pf = mask;
+  return SLIME_OK;
+}
+
 int slime_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
                          const void* residual, int res_ld, int epilogue, void* out, float* out_f32, int out_ld,
                          int splits, float* ws, size_t ws_floats, const void* norm_w, void* norm_out, float norm_eps,
@@ -980,7 +1031,7 @@ int slime_op_decode_attention(const void* q, int q_ld, const void* kcache, const
                               void* out, int out_ld, int splits, float* ws, void* stream) {
   return slime_launch_decode_attention(static_cast<const bf16*>(q), q_ld, static_cast<const bf16*>(kcache),
                                        static_cast<const bf16*>(vcache), cache_len, lens, batch, heads, kv_heads,
-                                       head_dim, scale, static_cast<bf16*>(out), out_ld, splits, ws,
+                                       head_dim, scale, static_cast<bf16*>(out), out_ld, splits, ws, nullptr, 0,
                                        static_cast<cudaStream_t>(stream));
 }
 

@@ -240,6 +240,20 @@ SLIME_DEVINL float2 unpack_bf16x2(uint32_t u) {
 SLIME_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 SLIME_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
+// Fire-and-forget L2 prefetch of part `part` of `nparts` of [ptr, ptr + bytes) (16-byte aligned), 8 KB per request,
+// spread over the threads of the calling CTA.  Used by the latency-bound kernels of the decode step to keep HBM busy
+// with the NEXT projection's weights while they run (the weights are immutable, so no ordering is needed).
+SLIME_DEVINL void l2_prefetch_slice(const void* ptr, size_t bytes, int part, int nparts) {
+  constexpr size_t CH = 8192;
+  const size_t nch = (bytes + CH - 1) / CH;
+  for (size_t i = static_cast<size_t>(part) * blockDim.x + threadIdx.x; i < nch; i += static_cast<size_t>(nparts) * blockDim.x) {
+    const char* a = static_cast<const char*>(ptr) + i * CH;
+    const size_t left = bytes - i * CH;
+    const uint32_t sz = static_cast<uint32_t>((left < CH ? left : CH) & ~static_cast<size_t>(15));
+    if (sz != 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(a), "r"(sz) : "memory");
+  }
+}
+
 SLIME_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

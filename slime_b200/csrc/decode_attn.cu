@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(NT) decode_attn_split_kernel(const bf16* __res
                                                                const bf16* __restrict__ vcache, int cache_len,
                                                                const int* __restrict__ lens, int heads, int kv_heads,
                                                                float scale_log2, int splits, float* __restrict__ part,
-                                                               bf16* __restrict__ out, int out_ld) {
+                                                               bf16* __restrict__ out, int out_ld,
+                                                               const void* __restrict__ pf_ptr, size_t pf_bytes) {
   // merged through shared memory: [16 states][G][HD] accumulators + [16][G] max / sum
   extern __shared__ __align__(16) uint8_t ds_smem[];
   float* s_acc = reinterpret_cast<float*>(ds_smem);
@@ -141,6 +142,9 @@ __global__ void __launch_bounds__(NT) decode_attn_split_kernel(const bf16* __res
   float* s_l = s_m + 16 * G;
 
   pdl_trigger();
+  if (pf_bytes != 0)  // opt-in experiment (slime_set_decode_prefetch): pull a later projection's weights into L2
+    l2_prefetch_slice(pf_ptr, pf_bytes, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x,
+                      gridDim.x * gridDim.y * gridDim.z);
   pdl_wait();  // q, the cache rows appended in this step and lens come from the kernels before
 
   const int kvh = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
@@ -264,41 +268,261 @@ __global__ void __launch_bounds__(NT) decode_attn_split_kernel(const bf16* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core variant of the split-KV kernel.  The CUDA-core kernel above spends ~256 instructions per position set
+// (bf16 unpacking, 128 FMAs, shuffles, the per-position rescale of G x 128 accumulators) and at batch 16 is
+// instruction-issue bound at a third of the HBM rate.  Here a warp owns 16-position K / V tiles staged by cp.async in
+// a private 2-stage shared-memory ring (XOR-swizzled 256-byte rows: conflict-free ldmatrix) and runs the FlashAttention
+// recurrence on mma.sync.m16n8k16 with the G <= 8 query heads of the group as the (padded) 16-row operand:
+//   S[g, pos] = Q[g, :] K[pos, :]^T   8 k-steps x 2 position blocks     (ldmatrix of K rows = the col-major B operand)
+//   O[g, :]  += P[g, pos] V[pos, :]   16 feature blocks, P re-used from the S accumulator registers as the A operand,
+//                                     V through ldmatrix.trans
+// ~180 instructions per 16 positions instead of ~1000.  Per-warp states are merged exactly like the kernel above and
+// written in the same partial format, so decode_attn_merge_kernel serves both.
+// ------------------------------------------------------------------------------------------
+// A staged K / V row is 256 bytes = 16 chunks of 16 bytes; chunk ch of row r sits at position ch ^ (r & 7), so the 8 rows
+// of an ldmatrix phase and the 16 chunks of a cp.async row both spread over all banks without padding.  2 stages x
+// (K + V) x 4 warps = 64 KB per CTA: two CTAs fit the 132 KB carve-out the weight-streaming GEMM runs with, which
+// matters under PDL - an SM cannot be re-partitioned between overlapping kernels, and a projection that inherits a
+// 208 KB carve-out (the first, padded 3-stage version of this kernel) loses its L1 and with it 40 % of its bandwidth.
+constexpr int DM_ROW = 256;
+constexpr int DM_TILE = 16 * DM_ROW;  // one 16-position K (or V) tile
+constexpr int DM_STAGES = 2;
+constexpr int DM_WARP_BYTES = DM_STAGES * 2 * DM_TILE;
+constexpr int DM_SMEM = 4 * DM_WARP_BYTES;  // 65536
+SLIME_DEVINL uint32_t dm_off(int row, int chunk) { return static_cast<uint32_t>(row * DM_ROW + ((chunk ^ (row & 7)) << 4)); }
+
+SLIME_DEVINL void cp_async16_zfill(uint32_t dst, const bf16* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+SLIME_DEVINL void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+SLIME_DEVINL void ldsm4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+// rows 8..15 of the A operand are padding: a2a3 = a6a7 = 0
+SLIME_DEVINL void mma_rows8(float* d, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." SLIME_MMA_SYNC_TYPE "." SLIME_MMA_SYNC_TYPE
+               ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(NT) decode_attn_mma_kernel(const bf16* __restrict__ q, int q_ld,
+                                                             const bf16* __restrict__ kcache,
+                                                             const bf16* __restrict__ vcache, int cache_len,
+                                                             const int* __restrict__ lens, int heads, int kv_heads, int G,
+                                                             float scale_log2, int splits, float* __restrict__ part,
+                                                             bf16* __restrict__ out, int out_ld) {
+  extern __shared__ __align__(16) uint8_t ds_smem[];
+  pdl_trigger();
+  pdl_wait();  // q, the cache rows appended in this step and lens come from the kernels before
+
+  const int kvh = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int len = min(__ldcg(lens + b) + 1, cache_len);
+  const int KD = kv_heads * DS_HD;
+  // this split's positions [p0, p1): equal chunks, multiples of 64 (4 warps x 16-position tiles)
+  const int chunk = ((len + splits - 1) / splits + 63) / 64 * 64;
+  const int p0 = split * chunk, p1 = min(len, p0 + chunk);
+  const int n_tiles = p1 > p0 ? (p1 - p0 + 15) / 16 : 0;
+  const int my_tiles = n_tiles > warp ? (n_tiles - warp + 3) / 4 : 0;
+
+  // A operand: row g = query head kvh * G + g (rows >= G are zero), k-step ks = features [16 ks, 16 ks + 16)
+  uint32_t qa[8][2];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    qa[ks][0] = qa[ks][1] = 0u;
+    if (g < G) {
+      const bf16* qp = q + static_cast<long long>(b) * q_ld + (kvh * G + g) * DS_HD + ks * 16 + 2 * c;
+      qa[ks][0] = __ldcg(reinterpret_cast<const uint32_t*>(qp));
+      qa[ks][1] = __ldcg(reinterpret_cast<const uint32_t*>(qp + 8));
+    }
+  }
+  float o[16][4];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  const bf16* kbase = kcache + (static_cast<long long>(b) * cache_len) * KD + kvh * DS_HD;
+  const bf16* vbase = vcache + (static_cast<long long>(b) * cache_len) * KD + kvh * DS_HD;
+  const uint32_t wbase = smem_u32(ds_smem) + static_cast<uint32_t>(warp) * DM_WARP_BYTES;
+  auto issue = [&](int i) {  // the warp's i-th tile -> stage i % DM_STAGES (always commits a group)
+    if (i < my_tiles) {
+      const int pos0 = p0 + (warp + 4 * i) * 16;
+      const uint32_t sk = wbase + static_cast<uint32_t>(i % DM_STAGES) * (2 * DM_TILE);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // one instruction = 2 rows x 256 contiguous bytes
+        const int row = j * 2 + (lane >> 4), ch = lane & 15;
+        const int pos = pos0 + row;
+        const bool ok = pos < p1;
+        const long long off = ok ? static_cast<long long>(pos) * KD + ch * 8 : 0;
+        const uint32_t d = sk + dm_off(row, ch);
+        cp_async16_zfill(d, kbase + off, ok ? 16 : 0);            // rows past the end are zero-filled: P = 0 there,
+        cp_async16_zfill(d + DM_TILE, vbase + off, ok ? 16 : 0);  // and 0 x garbage could be NaN
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+#pragma unroll
+  for (int i = 0; i < DM_STAGES - 1; ++i) issue(i);
+  for (int i = 0; i < my_tiles; ++i) {
+    issue(i + DM_STAGES - 1);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(DM_STAGES - 1) : "memory");
+    __syncwarp();
+    const uint32_t sk = wbase + static_cast<uint32_t>(i % DM_STAGES) * (2 * DM_TILE);
+    const uint32_t sv = sk + DM_TILE;
+
+    // ---- S = Q K^T: s[0] = positions 0..7 of the tile, s[1] = positions 8..15 (this thread: columns 2c, 2c + 1) ----
+    float s[2][4];
+    s[0][0] = s[0][1] = s[0][2] = s[0][3] = s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
+    const int k_row = ((lane >> 4) << 3) + (lane & 7), k_ch = (lane >> 3) & 1;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t r0, r1, r2, r3;
+      ldsm4(sk + dm_off(k_row, ks * 2 + k_ch), r0, r1, r2, r3);
+      mma_rows8(s[0], qa[ks][0], qa[ks][1], r0, r1);
+      mma_rows8(s[1], qa[ks][0], qa[ks][1], r2, r3);
+    }
+    // ---- online softmax of row g over the tile's 16 positions ----
+    const int pos_t = p0 + (warp + 4 * i) * 16 + 2 * c;
+    float sc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int pos = pos_t + (e >> 1) * 8 + (e & 1);
+      sc[e] = pos < p1 ? s[e >> 1][e & 1] * scale_log2 : -INFINITY;
+    }
+    float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);  // finite: every issued tile has at least one valid position
+    const float alpha = exp2f(m_run - m_new);
+    m_run = m_new;
+    float pr[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pr[e] = exp2f(sc[e] - m_new);
+    l_run = l_run * alpha + (pr[0] + pr[1]) + (pr[2] + pr[3]);
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      o[n][0] *= alpha;
+      o[n][1] *= alpha;
+    }
+    // ---- O += P V: P (row g; positions 2c, 2c+1 | 8 + 2c, 8 + 2c + 1) is the A operand as it sits in registers ----
+    const uint32_t pa0 = pack_bf16x2(pr[0], pr[1]), pa2 = pack_bf16x2(pr[2], pr[3]);
+    const int v_row = (((lane >> 3) & 1) << 3) + (lane & 7), v_ch = lane >> 4;
+#pragma unroll
+    for (int dp = 0; dp < 8; ++dp) {
+      uint32_t r0, r1, r2, r3;
+      ldsm4_t(sv + dm_off(v_row, dp * 2 + v_ch), r0, r1, r2, r3);
+      mma_rows8(o[2 * dp], pa0, pa2, r0, r1);
+      mma_rows8(o[2 * dp + 1], pa0, pa2, r2, r3);
+    }
+    __syncwarp();  // every lane is done with this stage before it is refilled
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();  // the merge buffers below alias the rings
+
+  // ---- merge the 4 warp states: [4][8][HD] accumulators + [4][8] max / sum ----
+  float* s_acc = reinterpret_cast<float*>(ds_smem);
+  float* s_m = s_acc + 4 * 8 * DS_HD;
+  float* s_l = s_m + 32;
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (g < G) {
+    float* dst = s_acc + (warp * 8 + g) * DS_HD + 2 * c;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) *reinterpret_cast<float2*>(dst + n * 8) = make_float2(o[n][0], o[n][1]);
+    if (c == 0) {
+      s_m[warp * 8 + g] = m_run;
+      s_l[warp * 8 + g] = l_run;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * DS_HD; idx += NT) {
+    const int gi = idx / DS_HD, e = idx % DS_HD;
+    const float mt = fmaxf(fmaxf(s_m[gi], s_m[8 + gi]), fmaxf(s_m[16 + gi], s_m[24 + gi]));
+    float lt = 0.f, val = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float ms = s_m[w * 8 + gi];
+      const float a = (ms == -INFINITY) ? 0.f : exp2f(ms - mt);
+      lt += s_l[w * 8 + gi] * a;
+      val += s_acc[(w * 8 + gi) * DS_HD + e] * a;
+    }
+    const int head = kvh * G + gi;
+    if (part == nullptr) {
+      out[static_cast<long long>(b) * out_ld + head * DS_HD + e] = float_to_elem(lt > 0.f ? val / lt : 0.f);
+    } else {
+      float* pp = part + ((static_cast<long long>(b) * heads + head) * splits + split) * (DS_HD + 2);
+      pp[e] = val;
+      if (e == 0) {
+        pp[DS_HD] = mt;
+        pp[DS_HD + 1] = lt;
+      }
+    }
+  }
+}
+
 // out[b, head] = sum_s acc_s 2^(m_s - M) / sum_s l_s 2^(m_s - M)   (fixed order over the splits)
 __global__ void __launch_bounds__(DS_HD) decode_attn_merge_kernel(const float* __restrict__ part, int heads, int splits,
                                                                   bf16* __restrict__ out, int out_ld) {
+  __shared__ float s_a[DS_HD];  // per-split weight 2^(m_s - M) (splits <= 128)
+  __shared__ float s_red[2];
   pdl_trigger();
   pdl_wait();
   const int head = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
   const float* pp = part + (static_cast<long long>(b) * heads + head) * splits * (DS_HD + 2);
-  float mt = -INFINITY;
-  for (int s = 0; s < splits; ++s) mt = fmaxf(mt, __ldcg(pp + s * (DS_HD + 2) + DS_HD));
-  float lt = 0.f, val = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float ms = __ldcg(pp + s * (DS_HD + 2) + DS_HD);
-    const float a = (ms == -INFINITY) ? 0.f : exp2f(ms - mt);
-    lt += __ldcg(pp + s * (DS_HD + 2) + DS_HD + 1) * a;
-    val += __ldcg(pp + s * (DS_HD + 2) + e) * a;
+  // round trip 1: thread s fetches (m_s, l_s); the CTA agrees on M and on the weights (one warp: splits <= 32)
+  float ms = -INFINITY, ls = 0.f;
+  if (e < splits) {
+    ms = __ldcg(pp + e * (DS_HD + 2) + DS_HD);
+    ls = __ldcg(pp + e * (DS_HD + 2) + DS_HD + 1);
   }
+  if (e < 32) {
+    const float mt = warp_max(ms);
+    const float a = (ms == -INFINITY) ? 0.f : exp2f(ms - mt);
+    s_a[e] = a;
+    float lt = 0.f;  // fixed order over the splits: deterministic
+    for (int s = 0; s < splits; ++s) lt += __shfl_sync(0xffffffffu, ls * a, s);
+    if (e == 0) s_red[0] = lt;
+  }
+  __syncthreads();
+  // round trip 2: all partial accumulators of this feature at once
+  float val = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < splits; ++s) val += __ldcg(pp + s * (DS_HD + 2) + e) * s_a[s];
+  const float lt = s_red[0];
   out[static_cast<long long>(b) * out_ld + head * DS_HD + e] = float_to_elem(lt > 0.f ? val / lt : 0.f);
 }
 
-int g_decode_attn_mode = -1;  // -1 unset, 0 = one CTA per (q head, sequence), 1 = split-KV
+int g_decode_attn_mode = -1;  // -1 unset; 0 = one CTA per (q head, sequence); 1 = split-KV on CUDA cores; 2 = split-KV on mma.sync
 
-bool decode_split_supported(int heads, int kv_heads, int head_dim) {
+int decode_attn_mode() {
   if (g_decode_attn_mode < 0) {
     const char* e = getenv("SLIME_DECODE_ATTN");
-    g_decode_attn_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_decode_attn_mode = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }
-  if (g_decode_attn_mode == 0 || head_dim != DS_HD || kv_heads <= 0 || heads % kv_heads != 0) return false;
+  return g_decode_attn_mode;
+}
+
+bool decode_split_supported(int heads, int kv_heads, int head_dim) {
+  const int mode = decode_attn_mode();
+  if (mode == 0 || head_dim != DS_HD || kv_heads <= 0 || heads % kv_heads != 0) return false;
   const int G = heads / kv_heads;
+  if (mode == 2) return G <= 8;
   return G == 1 || G == 2 || G == 4;  // G = 8 would spill (2 x 128 fp32 of state per lane): old kernel
 }
 
 template <int G>
 int launch_split(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, int cache_len, const int* lens, int batch,
-                 int heads, int kv_heads, float sl2, int splits, float* part, bf16* out, int out_ld,
-                 cudaStream_t stream) {
+                 int heads, int kv_heads, float sl2, int splits, float* part, bf16* out, int out_ld, const void* pf_ptr,
+                 size_t pf_bytes, cudaStream_t stream) {
   const int smem = (16 * G * DS_HD + 32 * G) * static_cast<int>(sizeof(float));
   static bool attr_set = false;
   if (!attr_set && smem > 48 * 1024) {
@@ -308,7 +532,7 @@ int launch_split(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, int ca
   dim3 grid(kv_heads, batch, splits);
   SLIME_CHECK_CUDA(slime_launch_kernel(decode_attn_split_kernel<G>, grid, dim3(NT), smem, stream, true, q, q_ld, kc, vc,
                                        cache_len, lens, heads, kv_heads, sl2, splits,
-                                       splits > 1 ? part : static_cast<float*>(nullptr), out, out_ld));
+                                       splits > 1 ? part : static_cast<float*>(nullptr), out, out_ld, pf_ptr, pf_bytes));
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
@@ -365,7 +589,7 @@ int slime_launch_kv_append(const bf16* k, const bf16* v, int ld, bf16* kcache, b
 }
 
 extern "C" int slime_decode_attention_set_mode(int mode) {
-  g_decode_attn_mode = mode < 0 ? -1 : (mode != 0 ? 1 : 0);
+  g_decode_attn_mode = (mode < 0 || mode > 2) ? -1 : mode;
   return SLIME_OK;
 }
 
@@ -385,12 +609,14 @@ size_t slime_decode_attention_ws_floats(int batch, int heads, int splits) {
 
 int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, const bf16* vcache, int cache_len,
                                   const int* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
-                                  bf16* out, int out_ld, int splits, float* ws, cudaStream_t stream) {
+                                  bf16* out, int out_ld, int splits, float* ws, const void* pf_ptr, size_t pf_bytes,
+                                  cudaStream_t stream) {
   SLIME_REQUIRE(head_dim == 64 || head_dim == 128, "decode attention: head_dim %d unsupported", head_dim);
   if (batch <= 0) return SLIME_OK;
   const float sl2 = scale * 1.4426950408889634f;
   if (splits >= 1 && decode_split_supported(heads, kv_heads, head_dim)) {
     SLIME_REQUIRE(splits == 1 || ws != nullptr, "decode attention: %d kv splits need a scratch buffer", splits);
+    SLIME_REQUIRE(splits <= 32, "decode attention: at most 32 kv splits (%d given)", splits);
     SLIME_REQUIRE(q_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(kcache) & 15) == 0 && (reinterpret_cast<uintptr_t>(vcache) & 15) == 0,
                   "decode attention: q / cache must be 16-byte aligned");
@@ -398,12 +624,26 @@ int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, c
     const double bytes = 2.0 * batch * static_cast<double>(cache_len) * kv_heads * head_dim * sizeof(bf16);  // upper bound
     slime_prof_begin(1, bytes, stream);
     int rc = SLIME_OK;
+    if (decode_attn_mode() == 2) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        SLIME_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
+        attr_set = true;
+      }
+      const cudaError_t le = slime_launch_kernel(decode_attn_mma_kernel, dim3(kv_heads, batch, splits), dim3(NT), DM_SMEM, stream,
+                                                 true, q, q_ld, kcache, vcache, cache_len, lens, heads, kv_heads, G, sl2,
+                                                 splits, splits > 1 ? ws : static_cast<float*>(nullptr), out, out_ld);
+      slime_prof_end(stream);
+      SLIME_CHECK_CUDA(le);
+      SLIME_AFTER_LAUNCH();
+    } else {
     switch (G) {
-      case 1: rc = launch_split<1>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, stream); break;
-      case 2: rc = launch_split<2>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, stream); break;
-      default: rc = launch_split<4>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, stream); break;
+      case 1: rc = launch_split<1>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, pf_ptr, pf_bytes, stream); break;
+      case 2: rc = launch_split<2>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, pf_ptr, pf_bytes, stream); break;
+      default: rc = launch_split<4>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, pf_ptr, pf_bytes, stream); break;
     }
     slime_prof_end(stream);
+    }
     SLIME_PROPAGATE(rc);
     if (splits > 1) {
       const float* part = ws;

@@ -42,6 +42,22 @@ bool slime_pdl_enabled() {
   }
   return g_pdl_mode != 0;
 }
+void slime_carveout_once(const void* kernel) {
+  static std::mutex mu;
+  static std::vector<const void*> seen;
+  static int pct = -2;
+  std::lock_guard<std::mutex> lk(mu);
+  if (pct == -2) {  // SLIME_CARVEOUT_PCT: 0..100 = preferred shared-memory share for every kernel of the chain, -1 = driver's choice
+    const char* e = getenv("SLIME_CARVEOUT_PCT");
+    pct = (e != nullptr && (e[0] == '-' || (e[0] >= '0' && e[0] <= '9'))) ? atoi(e) : 44;
+  }
+  if (pct < 0) return;  // (default 44 = the 100 KB configuration: measured best, profiles/r01_decode_bench.txt)
+  for (const void* k : seen)
+    if (k == kernel) return;
+  seen.push_back(kernel);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+  cudaGetLastError();  // a preference only: never fatal
+}
 extern "C" int slime_set_pdl_mode(int mode) {
   g_pdl_mode = mode < 0 ? -1 : (mode != 0 ? 1 : 0);
   return SLIME_OK;

@@ -47,9 +47,16 @@ void slime_prof_end(cudaStream_t stream);
 // Launch with (pdl = true) or without the programmatic-stream-serialization attribute (see pdl_wait() in common.cuh).
 // SLIME_PDL=0 / slime_set_pdl_mode(0) launch everything the ordinary way.
 bool slime_pdl_enabled();
+// First launch of `kernel`: set its preferred shared-memory carve-out (SLIME_CARVEOUT_PCT, default 44 % = the 100 KB
+// configuration; -1 leaves the driver's per-kernel choice).  The weight-streaming GEMM uses L1 as the landing buffer of
+// its in-flight loads (forced to the maximum carve-out it drops from 3.9 to 6.5 ms per decode step), and under PDL an SM
+// cannot be re-partitioned between overlapping kernels, so the whole chain asks for ONE modest configuration; a kernel
+// that needs more (the GEMM with 16 staged rows: 132 KB) still gets it.
+void slime_carveout_once(const void* kernel);
 template <typename... KArgs, typename... Args>
 cudaError_t slime_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                 bool pdl, Args&&... args) {
+  slime_carveout_once(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -44,6 +44,9 @@ struct GemmParams {
   // of row m also go to kv_k[(m * kv_cache_len + kv_lens[m]) * kv_dim + ...], the next kv_dim columns to kv_v (dropped
   // when the slot is outside the cache).  Done by the epilogue on the weight-streaming path, by a kv_append launch after
   // the GEMM otherwise.
+  // optional: weights of a LATER projection to pull into L2 while this one's split-K finishing kernel runs
+  const void* l2_prefetch = nullptr;
+  size_t l2_prefetch_bytes = 0;
   bf16* kv_k = nullptr;
   bf16* kv_v = nullptr;
   const int* kv_lens = nullptr;

@@ -104,7 +104,9 @@ SLIME_DEVINL void skinny_store(const GemmParams& p, int epi, int m, int n, float
 
 // grid = ctas_per_split * splits; CTA i works on k-split i % splits.  partial == nullptr: epilogue in place
 // (splits == 1); else partial[split][m][n] fp32.
-template <int MT>
+// MT = 16-row activation groups (M <= 16 MT); HALF (MT == 1 only): M <= 8 - only rows 0..7 are staged (half the shared
+// memory, i.e. more L1 for the in-flight weight loads) and the fragment rows 8..15 are fed as zero registers.
+template <int MT, bool HALF>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, const GemmParams p,
                    int epi, int splits, int kc, int xs_stride, float* __restrict__ partial) {
@@ -126,6 +128,9 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
 #pragma unroll
     for (int u = 0; u < SK_U; ++u)
       if (u < steps) wa[u] = ld_stream16(wp0 + u * 32);
+#pragma unroll
+    for (int u = 0; u < SK_U; ++u)
+      if (SK_U + u < steps) wb[u] = ld_stream16(wp0 + (SK_U + u) * 32);
   }
   pdl_trigger();
   pdl_wait();
@@ -133,7 +138,7 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
   // ---- stage the activations of this k-split (rows >= M are zero) ----
   {
     const int chunks = klen >> 3;
-    const int total = MT * 16 * chunks;
+    const int total = (HALF ? 8 : MT * 16) * chunks;
     for (int idx = tid; idx < total; idx += SK_THREADS) {
       const int r = idx / chunks, ch = idx - r * chunks;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -168,7 +173,8 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const uint4 xa = lds16(xa_addr + static_cast<uint32_t>(mt) * 2u * row8);          // row mt*16 + g
-            const uint4 xb = lds16(xa_addr + static_cast<uint32_t>(mt) * 2u * row8 + row8);   // row mt*16 + g + 8
+            const uint4 xb = HALF ? make_uint4(0u, 0u, 0u, 0u)
+                                  : lds16(xa_addr + static_cast<uint32_t>(mt) * 2u * row8 + row8);   // row mt*16 + g + 8
             mma_16816(acc[mt], xa.x, xb.x, xa.y, xb.y, w[u].x, w[u].y);  // k = kb + 8c + {0,1 | 2,3}
             mma_16816(acc[mt], xa.z, xb.z, xa.w, xb.w, w[u].z, w[u].w);  // k = kb + 8c + {4,5 | 6,7}
           }
@@ -177,9 +183,11 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
     };
 
     for (int s0 = 0; s0 < steps; s0 += 2 * SK_U) {
+      if (t != t_first || s0 != 0) {
 #pragma unroll
-      for (int u = 0; u < SK_U; ++u)
-        if (s0 + SK_U + u < steps) wb[u] = ld_stream16(wp + (s0 + SK_U + u) * 32);
+        for (int u = 0; u < SK_U; ++u)
+          if (s0 + SK_U + u < steps) wb[u] = ld_stream16(wp + (s0 + SK_U + u) * 32);
+      }
       compute(wa, s0);
 #pragma unroll
       for (int u = 0; u < SK_U; ++u)
@@ -209,8 +217,12 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
 
 // Sum of the k-split partials in split order + epilogue; one thread per output pair.
 __global__ void __launch_bounds__(256) skinny_finish_kernel(const float* __restrict__ partial, int splits,
-                                                            const GemmParams p, int epi) {
+                                                            const GemmParams p, int epi, int work_ctas) {
   pdl_trigger();
+  if (static_cast<int>(blockIdx.x) >= work_ctas) {  // extra CTAs: only pull a later projection's weights into L2
+    l2_prefetch_slice(p.l2_prefetch, p.l2_prefetch_bytes, blockIdx.x - work_ctas, gridDim.x - work_ctas);
+    return;
+  }
   pdl_wait();
   const int pairs = p.N >> 1;
   const long long idx = blockIdx.x * 256LL + threadIdx.x;
@@ -227,50 +239,96 @@ __global__ void __launch_bounds__(256) skinny_finish_kernel(const float* __restr
 
 // Same, for out = acc (+bias) + residual followed by RMSNorm of the new row (one CTA per row):
 //   out[m] = bf16(sum);  norm_out[m] = norm_w * bf16(out[m] * rsqrt(mean(out[m]^2) + eps))   (HF LlamaRMSNorm)
-__global__ void __launch_bounds__(256) skinny_finish_norm_kernel(const float* __restrict__ partial, int splits,
-                                                                 const GemmParams p) {
-  extern __shared__ __align__(16) uint8_t sk_smem[];
-  float* row = reinterpret_cast<float*>(sk_smem);  // the rounded output row, as floats
-  __shared__ float red[8];
+// Latency-bound (a row is 8..40 KB of partials in L2): 1024 threads, every load of a thread issued before the first
+// use, the rounded row kept in registers between the two phases.  (The first version - 256 threads walking the row in
+// 8 dependent round trips - took 18 us per launch, 20 % of a batch-16 decode step.)
+constexpr int FN_THREADS = 1024;
+constexpr int FN_SLOTS = 4;  // column pairs per thread: N <= 2 * FN_THREADS * FN_SLOTS = 8192
+
+template <int SPLITS>  // 0 = run-time count
+__global__ void __launch_bounds__(FN_THREADS) skinny_finish_norm_kernel(const float* __restrict__ partial, int splits_rt,
+                                                                        const GemmParams p) {
+  __shared__ float red[FN_THREADS / 32];
   pdl_trigger();
-  pdl_wait();
+  if (static_cast<int>(blockIdx.x) >= p.M) {  // extra CTAs: only pull a later projection's weights into L2 (opt-in)
+    l2_prefetch_slice(p.l2_prefetch, p.l2_prefetch_bytes, blockIdx.x - p.M, gridDim.x - p.M);
+    return;
+  }
+  const int splits = SPLITS > 0 ? SPLITS : splits_rt;
   const int m = blockIdx.x, tid = threadIdx.x;
+  uint32_t wn[FN_SLOTS];  // the norm weight does not depend on the previous kernel: before the wait
+#pragma unroll
+  for (int i = 0; i < FN_SLOTS; ++i) {
+    const int n = (tid + i * FN_THREADS) * 2;
+    wn[i] = n < p.N ? __ldg(reinterpret_cast<const uint32_t*>(p.norm_w + n)) : 0u;
+  }
+  pdl_wait();
+  float2 v[FN_SLOTS];
+  uint32_t res[FN_SLOTS];
+#pragma unroll
+  for (int i = 0; i < FN_SLOTS; ++i) {
+    const int n = (tid + i * FN_THREADS) * 2;
+    v[i] = make_float2(0.f, 0.f);
+    res[i] = 0u;
+    if (n < p.N) {
+      if (p.residual != nullptr)
+        res[i] = __ldcg(reinterpret_cast<const uint32_t*>(p.residual + static_cast<size_t>(m) * p.res_ld + n));
+      if constexpr (SPLITS > 0) {
+        float2 t[SPLITS];
+#pragma unroll
+        for (int s = 0; s < SPLITS; ++s)
+          t[s] = __ldcg(reinterpret_cast<const float2*>(partial + (static_cast<size_t>(s) * p.M + m) * p.N + n));
+#pragma unroll
+        for (int s = 0; s < SPLITS; ++s) {  // fixed order: deterministic
+          v[i].x += t[s].x;
+          v[i].y += t[s].y;
+        }
+      } else {
+        for (int s = 0; s < splits; ++s) {
+          const float2 t = __ldcg(reinterpret_cast<const float2*>(partial + (static_cast<size_t>(s) * p.M + m) * p.N + n));
+          v[i].x += t.x;
+          v[i].y += t.y;
+        }
+      }
+    }
+  }
   float sq = 0.f;
-  for (int n = tid * 2; n < p.N; n += 512) {
-    float v0 = 0.f, v1 = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float2 t = __ldcg(reinterpret_cast<const float2*>(partial + (static_cast<size_t>(s) * p.M + m) * p.N + n));
-      v0 += t.x;
-      v1 += t.y;
+#pragma unroll
+  for (int i = 0; i < FN_SLOTS; ++i) {
+    const int n = (tid + i * FN_THREADS) * 2;
+    if (n < p.N) {
+      float v0 = v[i].x, v1 = v[i].y;
+      if (p.bias != nullptr) {
+        const float2 b = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(p.bias + n)));
+        v0 += b.x;
+        v1 += b.y;
+      }
+      if (p.residual != nullptr) {
+        const float2 r = unpack_bf16x2(res[i]);
+        v0 += r.x;
+        v1 += r.y;
+      }
+      const uint32_t pk = pack_bf16x2(v0, v1);
+      *reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(m) * p.out_ld + n) = pk;
+      v[i] = unpack_bf16x2(pk);  // the row as the next kernel will read it
+      sq += v[i].x * v[i].x + v[i].y * v[i].y;
     }
-    if (p.bias != nullptr) {
-      const float2 b = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(p.bias + n)));
-      v0 += b.x;
-      v1 += b.y;
-    }
-    if (p.residual != nullptr) {
-      const float2 r = unpack_bf16x2(__ldcg(reinterpret_cast<const uint32_t*>(p.residual + static_cast<size_t>(m) * p.res_ld + n)));
-      v0 += r.x;
-      v1 += r.y;
-    }
-    const uint32_t pk = pack_bf16x2(v0, v1);
-    *reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(m) * p.out_ld + n) = pk;
-    const float2 rr = unpack_bf16x2(pk);
-    row[n] = rr.x;
-    row[n + 1] = rr.y;
-    sq += rr.x * rr.x + rr.y * rr.y;
   }
   sq = warp_sum(sq);
   if ((tid & 31) == 0) red[tid >> 5] = sq;
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) tot += red[w];
+  for (int w = 0; w < FN_THREADS / 32; ++w) tot += red[w];
   const float rstd = rsqrtf(tot / p.N + p.norm_eps);
-  for (int n = tid * 2; n < p.N; n += 512) {  // every thread re-reads only what it wrote itself
-    const float2 w = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(p.norm_w + n)));
-    const float a = elem_to_float(float_to_elem(row[n] * rstd)), b = elem_to_float(float_to_elem(row[n + 1] * rstd));
-    *reinterpret_cast<uint32_t*>(p.norm_out + static_cast<size_t>(m) * p.norm_ld + n) = pack_bf16x2(w.x * a, w.y * b);
+#pragma unroll
+  for (int i = 0; i < FN_SLOTS; ++i) {
+    const int n = (tid + i * FN_THREADS) * 2;
+    if (n < p.N) {
+      const float2 w = unpack_bf16x2(wn[i]);
+      const float a = elem_to_float(float_to_elem(v[i].x * rstd)), b = elem_to_float(float_to_elem(v[i].y * rstd));
+      *reinterpret_cast<uint32_t*>(p.norm_out + static_cast<size_t>(m) * p.norm_ld + n) = pack_bf16x2(w.x * a, w.y * b);
+    }
   }
 }
 
@@ -337,19 +395,20 @@ SkinnyPlan make_plan(const bf16* A, int lda, const bf16* W, int ldw, const GemmP
   return pl;
 }
 
-template <int MT>
+template <int MT, bool HALF>
 int launch_skinny(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, const SkinnyPlan& pl,
                   int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
-  const int smem = MT * 16 * pl.xs_stride * 2;
+  const int rows = HALF ? 8 : MT * 16;
+  const int smem = rows * pl.xs_stride * 2;
   if (!attr_set) {
-    SLIME_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          MT * 16 * (SK_KC_MAX / MT + 32) * 2));
+    SLIME_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<MT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          rows * (SK_KC_MAX / MT + 32) * 2));
     attr_set = true;
   }
   const int ctas = (num_sms / pl.splits) * pl.splits;
   slime_prof_begin(2, static_cast<double>(p.N) * p.K * sizeof(bf16), stream);
-  const cudaError_t le = slime_launch_kernel(gemm_skinny_kernel<MT>, dim3(ctas), dim3(SK_THREADS), smem, stream, true, A, lda,
+  const cudaError_t le = slime_launch_kernel(gemm_skinny_kernel<MT, HALF>, dim3(ctas), dim3(SK_THREADS), smem, stream, true, A, lda,
                                              W, ldw, p, epi, pl.splits, pl.kc, pl.xs_stride,
                                              pl.use_partial ? p.splitk_ws : static_cast<float*>(nullptr));
   slime_prof_end(stream);
@@ -375,20 +434,35 @@ int slime_launch_gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, con
                              int num_sms, cudaStream_t stream) {
   const SkinnyPlan pl = make_plan(A, lda, W, ldw, p, epi, num_sms);
   SLIME_REQUIRE(pl.ok, "skinny gemm: problem M=%d N=%d K=%d not supported", p.M, p.N, p.K);
-  if (pl.mt == 1) {
-    SLIME_PROPAGATE(launch_skinny<1>(A, lda, W, ldw, p, epi, pl, num_sms, stream));
+  static int rows8 = -1;  // SLIME_SKINNY_ROWS8=0: always stage 16 rows (A/B)
+  if (rows8 < 0) {
+    const char* e = getenv("SLIME_SKINNY_ROWS8");
+    rows8 = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (pl.mt == 1 && p.M <= 8 && rows8 != 0) {
+    SLIME_PROPAGATE((launch_skinny<1, true>(A, lda, W, ldw, p, epi, pl, num_sms, stream)));
+  } else if (pl.mt == 1) {
+    SLIME_PROPAGATE((launch_skinny<1, false>(A, lda, W, ldw, p, epi, pl, num_sms, stream)));
   } else {
-    SLIME_PROPAGATE(launch_skinny<2>(A, lda, W, ldw, p, epi, pl, num_sms, stream));
+    SLIME_PROPAGATE((launch_skinny<2, false>(A, lda, W, ldw, p, epi, pl, num_sms, stream)));
   }
   if (!pl.use_partial) return SLIME_OK;
   const float* part = p.splitk_ws;
+  const int pf_ctas = (p.l2_prefetch != nullptr && p.l2_prefetch_bytes > 0) ? num_sms / 2 : 0;
   if (p.norm_w != nullptr) {
-    SLIME_CHECK_CUDA(slime_launch_kernel(skinny_finish_norm_kernel, dim3(p.M), dim3(256), p.N * sizeof(float), stream, true,
-                                         part, pl.splits, p));
+    const dim3 grid(p.M + pf_ctas), block(FN_THREADS);
+    switch (pl.splits) {
+      case 1: SLIME_CHECK_CUDA(slime_launch_kernel(skinny_finish_norm_kernel<1>, grid, block, 0, stream, true, part, pl.splits, p)); break;
+      case 2: SLIME_CHECK_CUDA(slime_launch_kernel(skinny_finish_norm_kernel<2>, grid, block, 0, stream, true, part, pl.splits, p)); break;
+      case 4: SLIME_CHECK_CUDA(slime_launch_kernel(skinny_finish_norm_kernel<4>, grid, block, 0, stream, true, part, pl.splits, p)); break;
+      case 8: SLIME_CHECK_CUDA(slime_launch_kernel(skinny_finish_norm_kernel<8>, grid, block, 0, stream, true, part, pl.splits, p)); break;
+      default: SLIME_CHECK_CUDA(slime_launch_kernel(skinny_finish_norm_kernel<0>, grid, block, 0, stream, true, part, pl.splits, p)); break;
+    }
   } else {
     const long long pairs = static_cast<long long>(p.M) * (p.N / 2);
-    SLIME_CHECK_CUDA(slime_launch_kernel(skinny_finish_kernel, dim3(static_cast<unsigned>((pairs + 255) / 256)), dim3(256), 0,
-                                         stream, true, part, pl.splits, p, epi));
+    const int work_ctas = static_cast<int>((pairs + 255) / 256);
+    SLIME_CHECK_CUDA(slime_launch_kernel(skinny_finish_kernel, dim3(work_ctas + pf_ctas), dim3(256), 0, stream, true, part,
+                                         pl.splits, p, epi, work_ctas));
   }
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;

@@ -185,9 +185,20 @@ def decode_attention(q, kc, vc, lens, heads, kv_heads, splits):
     return out
 
 
-@pytest.mark.parametrize("heads,kv_heads", [(32, 8), (8, 8), (4, 2)])
+@pytest.fixture(params=[2, 1], ids=["mma", "cuda_core"])
+def attn_mode(request):
+    """2 = split-KV kernel on mma.sync (default), 1 = split-KV kernel on CUDA cores."""
+    lib = _L().load()
+    lib.slime_decode_attention_set_mode(request.param)
+    yield request.param
+    lib.slime_decode_attention_set_mode(-1)
+
+
+@pytest.mark.parametrize("heads,kv_heads", [(32, 8), (8, 8), (4, 2), (16, 2)])
 @pytest.mark.parametrize("splits", [0, 1, 3, 8, 32])
-def test_decode_attention_split_kv(heads, kv_heads, splits):
+def test_decode_attention_split_kv(heads, kv_heads, splits, attn_mode):
+    if attn_mode == 1 and heads // kv_heads == 8 and splits > 0:
+        pytest.skip("the CUDA-core split kernel covers G <= 4 (falls back to the one-CTA-per-head kernel)")
     torch.manual_seed(heads + splits)
     B, cache_len, hd = 5, 700, 128
     kc, vc = rnd(B, cache_len, kv_heads * hd), rnd(B, cache_len, kv_heads * hd)
@@ -271,8 +282,9 @@ def test_decode_step_pdl_is_bit_identical(pname, B):
     pos = torch.cat([torch.arange(n) for n in lens0]).to(device="cuda", dtype=torch.int32)
     xs = [(torch.randn(B, cfg.hidden_size, device="cuda") * 0.5).to(torch.bfloat16) for _ in range(6)]
     outs = []
-    for mode in (1, 0, 1):
+    for mode, pf in ((1, 15), (0, 0), (1, 3)):
         lib.slime_set_pdl_mode(mode)
+        lib.slime_set_decode_prefetch(pf)  # L2 prefetch duties of the small kernels: no effect on results either
         try:
             eng.attach_kv_cache(B, 96)
             eng.decoder_prefill(rows, cu, pos, lens0)
@@ -285,6 +297,7 @@ def test_decode_step_pdl_is_bit_identical(pname, B):
         finally:
             eng.detach_kv_cache()
             lib.slime_set_pdl_mode(-1)
+            lib.slime_set_decode_prefetch(-1)
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1]), "PDL on vs off"
     assert torch.equal(outs[0], outs[2]), "PDL run to run"

@@ -26,7 +26,9 @@ def main():
     ap.add_argument("--batches", default="1,16")
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--layers", type=int, default=None)
-    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "decode_bench.json"))
+    ap.add_argument("--no-projections", action="store_true", help="skip the isolated projection timings")
+    ap.add_argument("--quick", action="store_true", help="only the two PDL configurations (mma / CUDA-core attention)")
+    ap.add_argument("--out", default=None, help="write the rows as JSON here (default: print only)")
     args = ap.parse_args()
 
     import torch
@@ -75,12 +77,16 @@ def main():
         pos = torch.cat([torch.arange(n) for n in lens0]).to(device=dev, dtype=torch.int32)
         x = (torch.randn(B, H, device=dev) * 0.5).to(torch.bfloat16)
         kv_bytes = cfg.num_hidden_layers * sum(lens0) * 2 * KD * 2
-        for mode, pdl, name in ((1, 1, "weight-streaming GEMM + split-KV attention, PDL"),
-                                (1, 0, "weight-streaming GEMM + split-KV attention, ordinary launches"),
-                                (0, 0, "tcgen05 tile GEMM + one CTA per head")):
+        for mode, amode, pdl, pf, name in (
+                (1, 2, 1, 0, "weight-streaming GEMM + split-KV attention (mma.sync), PDL"),
+                (1, 1, 1, 0, "weight-streaming GEMM + split-KV attention (CUDA cores), PDL"),
+                (1, 2, 0, 0, "weight-streaming GEMM + split-KV attention (mma.sync), ordinary launches"),
+                (1, 2, 1, 1, "as the first + L2 prefetch of the o-projection by the QKV finishing kernel"),
+                (0, 0, 0, 0, "tcgen05 tile GEMM + one CTA per head"))[:2 if args.quick else None]:
             lib.slime_gemm_set_skinny_mode(mode)
-            lib.slime_decode_attention_set_mode(mode)
+            lib.slime_decode_attention_set_mode(amode)
             lib.slime_set_pdl_mode(pdl)
+            lib.slime_set_decode_prefetch(pf)
             eng.attach_kv_cache(B, args.ctx + 8)
             try:
                 eng.decoder_prefill(rows, cu, pos, lens0)
@@ -112,11 +118,12 @@ def main():
                 lib.slime_gemm_set_skinny_mode(-1)
                 lib.slime_decode_attention_set_mode(-1)
                 lib.slime_set_pdl_mode(-1)
+                lib.slime_set_decode_prefetch(-1)
 
     # ---- isolated projections of one layer at M = 1 / 16 (L2 flushed between launches: weights come from HBM) ----
     gem = []
     shapes = [("qkv", QKV, H), ("o_proj", H, QD), ("gate_up", 2 * I, H), ("down", H, I), ("lm_head", V, H)]
-    for M in (1, 16):
+    for M in (() if args.no_projections else (1, 16)):
         for nm, N, K in shapes:
             a = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
             w = (torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16)
@@ -159,9 +166,10 @@ def main():
             gem.append(row)
             print(json.dumps(row), flush=True)
     results["projections"] = gem
-    os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    with open(args.out, "w") as f:
-        json.dump(results, f, indent=1)
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        with open(args.out, "w") as f:
+            json.dump(results, f, indent=1)
 
 
 if __name__ == "__main__":
