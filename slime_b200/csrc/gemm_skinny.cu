@@ -104,8 +104,11 @@ SLIME_DEVINL void skinny_store(const GemmParams& p, int epi, int m, int n, float
 
 // grid = ctas_per_split * splits; CTA i works on k-split i % splits.  partial == nullptr: epilogue in place
 // (splits == 1); else partial[split][m][n] fp32.
-// MT = 16-row activation groups (M <= 16 MT); HALF (MT == 1 only): M <= 8 - only rows 0..7 are staged (half the shared
-// memory, i.e. more L1 for the in-flight weight loads) and the fragment rows 8..15 are fed as zero registers.
+// MT = 16-row activation groups (M <= 16 MT); HALF (MT == 1 only): M <= 8 - only the M real rows are staged (8 KB of
+// shared memory at M = 1 instead of 132 KB, i.e. more L1 for the in-flight weight loads) and the other fragment rows
+// are fed as zero registers.
+// (A 256-thread variant with two CTAs per SM - small enough to become resident next to the attention / finishing CTAs
+// under PDL - was measured and is not faster: 3.54 vs 3.54 ms at B = 1, 4.06 vs 3.94 at B = 4, 4.12 vs 4.30 at B = 8.)
 template <int MT, bool HALF>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, const GemmParams p,
@@ -138,7 +141,7 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
   // ---- stage the activations of this k-split (rows >= M are zero) ----
   {
     const int chunks = klen >> 3;
-    const int total = (HALF ? 8 : MT * 16) * chunks;
+    const int total = (HALF ? p.M : MT * 16) * chunks;  // HALF: exactly the M <= 8 real rows (8 KB at M = 1)
     for (int idx = tid; idx < total; idx += SK_THREADS) {
       const int r = idx / chunks, ch = idx - r * chunks;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -172,7 +175,8 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
           const uint32_t xa_addr = xs_lane + static_cast<uint32_t>(s) * 64u;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            const uint4 xa = lds16(xa_addr + static_cast<uint32_t>(mt) * 2u * row8);          // row mt*16 + g
+            const uint4 xa = (HALF && g >= p.M) ? make_uint4(0u, 0u, 0u, 0u)
+                                                : lds16(xa_addr + static_cast<uint32_t>(mt) * 2u * row8);  // row mt*16 + g
             const uint4 xb = HALF ? make_uint4(0u, 0u, 0u, 0u)
                                   : lds16(xa_addr + static_cast<uint32_t>(mt) * 2u * row8 + row8);   // row mt*16 + g + 8
             mma_16816(acc[mt], xa.x, xb.x, xa.y, xb.y, w[u].x, w[u].y);  // k = kb + 8c + {0,1 | 2,3}
@@ -400,7 +404,7 @@ int launch_skinny(const bf16* A, int lda, const bf16* W, int ldw, const GemmPara
                   int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   const int rows = HALF ? 8 : MT * 16;
-  const int smem = rows * pl.xs_stride * 2;
+  const int smem = (HALF ? p.M : rows) * pl.xs_stride * 2;
   if (!attr_set) {
     SLIME_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<MT, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           rows * (SK_KC_MAX / MT + 32) * 2));
