@@ -41,6 +41,11 @@ extern "C" {
  * 2i+1 = q_proj row i + head_dim/2 (same for k_proj) - so the rotary embedding (HF llama/modeling_llama.py:152-176)
  * is applied in the epilogue of the QKV GEMM instead of by a separate pass over q and k. */
 #define SLIME_FLAG_ROPE_INTERLEAVED 8u
+/* config.mm_resampler_type == "qformer": slime_router_fwd / slime_router_fwd_embeds score the local tokens with the
+ * cross-attention router (reference multimodal_resampler/builder.py:94-162 TextGuidedRouterAttention; weight group
+ * "router.*") instead of the cosine router.  Like the reference, its softmax output is soft-maxed once more by the
+ * sampler (builder.py:160 and :258) before the top-p rule. */
+#define SLIME_FLAG_ROUTER_QFORMER 16u
 
 typedef struct slime_ctx slime_ctx;
 

@@ -34,6 +34,9 @@ CASES = {
     "tiny_flat_left_trunc": ("tiny", dict(mm_patch_merge_type="flat", tokenizer_padding_side="left",
                                           tokenizer_model_max_length=900), 3, 4, 40, 7, True, (672, 672), True),
     "small_wide_topp50": ("small", dict(mm_resampler_topp=0.5), 1, 7, 32, 9, False, (1008, 672), False),
+    # the cross-attention router (mm_resampler_type='qformer', reference multimodal_resampler/builder.py:94-162)
+    "tiny_qformer_router_b2": ("tiny", dict(mm_resampler_type="qformer", mm_resampler_topp=0.6), 2, 5, 24, 5, True,
+                               (672, 672), False),
 }
 
 

@@ -172,6 +172,29 @@ def router_probs(local: torch.Tensor, text: torch.Tensor, mask: torch.Tensor, te
     return torch.softmax(sim / temp, dim=-1)
 
 
+def router_qformer(sd, local: torch.Tensor, text: torch.Tensor, mask: torch.Tensor, temp: float = 1.0,
+                   prefix: str = "model.sampler.selector.") -> torch.Tensor:
+    """TextGuidedRouterAttention.forward (reference multimodal_resampler/builder.py:148-160): the local tokens [N, H]
+    cross-attend the prompt [T, H] (nn.MultiheadAttention, heads of 128, key_padding_mask = ~mask), ln_post, the
+    Linear-ReLU-Linear `prob_proj`, softmax(logits / temp) over the N tokens.  `query` / `self_attn` are unused there."""
+    H = local.shape[1]
+    heads, hd = H // 128, 128
+    ln = lambda x, n: F.layer_norm(x, (H,), sd[prefix + n + ".weight"], sd[prefix + n + ".bias"], 1e-5)  # noqa: E731
+    x, t = ln(local, "ln_q"), ln(text, "ln_kv")
+    w, b = sd[prefix + "cross_attn.in_proj_weight"], sd[prefix + "cross_attn.in_proj_bias"]
+    q = (x @ w[:H].t() + b[:H]).view(-1, heads, hd).transpose(0, 1)
+    k = (t @ w[H:2 * H].t() + b[H:2 * H]).view(-1, heads, hd).transpose(0, 1)
+    v = (t @ w[2 * H:].t() + b[2 * H:]).view(-1, heads, hd).transpose(0, 1)
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    sc = sc.masked_fill((mask == 0)[None, None, :], float("-inf"))
+    o = (torch.softmax(sc, -1) @ v).transpose(0, 1).reshape(-1, H)
+    o = o @ sd[prefix + "cross_attn.out_proj.weight"].t() + sd[prefix + "cross_attn.out_proj.bias"]
+    o = ln(o, "ln_post")
+    h = F.relu(o @ sd[prefix + "prob_proj.0.weight"].t() + sd[prefix + "prob_proj.0.bias"])
+    logit = (h @ sd[prefix + "prob_proj.2.weight"].t() + sd[prefix + "prob_proj.2.bias"]).squeeze(-1)
+    return torch.softmax(logit / temp, dim=-1)
+
+
 def top_p_select(probs: torch.Tensor, top_p: float) -> torch.Tensor:
     """The selection rule of TextGuidedSampler.forward (reference multimodal_resampler/builder.py:259-273),
     with the tie-break the framework specifies (stable: lower index first among equal probabilities;
@@ -291,7 +314,11 @@ def encode_images(sd, cfg, pixels: torch.Tensor, ids: torch.Tensor, mask: torch.
                 lp = projection(sd, lc)
                 lm = spatial_merge(lp, grids[b], g) if cfg.mm_patch_merge_type == "spatial" else lp.flatten(0, 1)
                 te, tm = pure_text_embedding(embed, ids[b], mask[b])
-                pr = router_probs(lm, te, tm, cfg.mm_resampler_temp)
+                if cfg.mm_resampler_type == "qformer":
+                    # the sampler soft-maxes the router's soft-max once more (builder.py:160 and :258)
+                    pr = torch.softmax(router_qformer(sd, lm, te, tm, cfg.mm_resampler_temp) / cfg.mm_resampler_temp, -1)
+                else:
+                    pr = router_probs(lm, te, tm, cfg.mm_resampler_temp)
                 sel = forced_selection[b] if forced_selection is not None else top_p_select(pr, cfg.mm_resampler_topp)
                 res["local_c"].append(lc)
                 res["local_m"].append(lm)

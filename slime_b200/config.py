@@ -90,8 +90,11 @@ class SlimeConfig:
     def validate(self) -> None:
         if self.mm_projector_type != "gated":
             raise NotImplementedError("only mm_projector_type='gated' (the SliME release setting) is built")
-        if self.mm_resampler_type != "cosine":
-            raise NotImplementedError("only mm_resampler_type='cosine' (the SliME release setting) is built")
+        if self.mm_resampler_type not in ("cosine", "qformer"):
+            raise NotImplementedError("mm_resampler_type must be 'cosine' (the SliME release setting) or 'qformer' "
+                                      "(the cross-attention router, reference multimodal_resampler/builder.py:94-162)")
+        if self.mm_resampler_type == "qformer" and self.hidden_size % 128:
+            raise ValueError("the 'qformer' router needs hidden_size % 128 == 0 (heads = hidden_size // 128)")
         if self.mm_vision_select_feature != "patch":
             raise NotImplementedError("only mm_vision_select_feature='patch' is built")
         if self.vit_hidden % 128:

@@ -63,6 +63,11 @@ struct Resampler {
 struct LlmLayer {
   const bf16 *in_norm_w, *qkv_w, *o_w, *post_norm_w, *gate_up_w, *down_w;
 };
+// TextGuidedRouterAttention (mm_resampler_type == "qformer"): cross_attn in/out projections, three LayerNorms, prob_proj
+struct QformerRouter {
+  const bf16 *ln_q_w, *ln_q_b, *ln_kv_w, *ln_kv_b, *ln_post_w, *ln_post_b, *in_w, *in_b, *out_w, *out_b, *fc1_w, *fc1_b,
+      *fc2_w, *fc2_b;
+};
 
 }  // namespace
 
@@ -76,7 +81,8 @@ struct slime_ctx {
   bool finalized = false;
   bf16* kv_cache = nullptr;  // caller-owned [layers][2][kv_cache_batch][kv_cache_len][kv_heads*head_dim], or nullptr
   int kv_cache_batch = 0, kv_cache_len = 0;
-  bool has_vit = false, has_rs[2] = {false, false}, has_proj = false, has_llm = false;
+  bool has_vit = false, has_rs[2] = {false, false}, has_proj = false, has_llm = false, has_router = false;
+  QformerRouter qf = {};
   std::mutex mu;
   // resolved at finalize
   int vit_tokens = 0, vit_patches = 0, vit_kpad = 0;
@@ -331,9 +337,66 @@ int gated_body(slime_ctx* c, Arena& a, const bf16* x, int n, bf16* out, cudaStre
 
 // ids != nullptr: prompt given as token ids (rows gathered from the embedding table, placeholders skipped);
 // ids == nullptr: prompt given as a dense [B, T, H] embedding tensor `text` (the reference's module-level API).
+// 'qformer' router: probs1 = softmax(prob_proj(ln_post(cross_attn(ln_q(local), ln_kv(text), ln_kv(text)))) / temp)
+// (reference multimodal_resampler/builder.py:148-160), then the sampler's own softmax + top-p (:258-273).
+int router_qformer_body(slime_ctx* c, Arena& a, const bf16* local, int n_per, const int* n_valid, const long long* ids,
+                        const bf16* text, const unsigned char* mask, int B, int T, float* probs_out, int* sel_idx,
+                        int* sel_count, cudaStream_t s) {
+  const int H = c->d.hidden, Dh = H / 4, heads = H / 128;
+  const size_t rows = static_cast<size_t>(B) * (n_per > 0 ? n_per : 1), trows = static_cast<size_t>(B) * T;
+  int* dst_row = a.get<int>(trows);
+  int* cu_k = a.get<int>(B + 1);
+  bf16* tpack = a.get<bf16>(trows * H);       // kept prompt rows, packed
+  bf16* tn = a.get<bf16>(trows * H);          // ln_kv(text)
+  bf16* kv = a.get<bf16>(trows * 2 * H);      // K | V
+  bf16* xn = a.get<bf16>(rows * H);           // ln_q(local), later the attention output
+  bf16* q = a.get<bf16>(rows * H);            // Q, later out_proj + ln_post
+  bf16* hid = a.get<bf16>(rows * Dh);         // first prob_proj layer (pre-ReLU)
+  float* logit = a.get<float>(rows);
+  ARENA_CHECK(a, "router (qformer)");
+  if (a.dry || B <= 0) return SLIME_OK;
+  if (n_per <= 0) {
+    SLIME_CHECK_CUDA(cudaMemsetAsync(sel_count, 0, sizeof(int) * B, s));
+    return SLIME_OK;
+  }
+  SLIME_REQUIRE(c->has_router, "router: mm_resampler_type='qformer' but the weight group 'router' is not registered");
+  const QformerRouter& R = c->qf;
+  const int n_rows = B * n_per, t_rows = B * T;
+  SLIME_CHECK_CUDA(cudaMemsetAsync(tpack, 0, trows * H * sizeof(bf16), s));  // rows past the packed end stay finite
+  SLIME_PROPAGATE(slime_launch_qf_pack_text(ids, mask, ids != nullptr ? c->llm_embed : text, B, T, H, c->d.image_token,
+                                            c->d.vocab, dst_row, cu_k, tpack, s));
+  constexpr float LN_EPS = 1e-5f;  // nn.LayerNorm default (builder.py:108 norm_layer=nn.LayerNorm)
+  SLIME_PROPAGATE(slime_launch_layernorm(tpack, H, R.ln_kv_w, R.ln_kv_b, tn, H, t_rows, H, LN_EPS, 0, 0, 0, s));
+  SLIME_PROPAGATE(slime_launch_layernorm(local, H, R.ln_q_w, R.ln_q_b, xn, H, n_rows, H, LN_EPS, 0, 0, 0, s));
+  // packed in_proj: rows [0, H) = q, [H, 2H) = k, [2H, 3H) = v (torch.nn.MultiheadAttention)
+  SLIME_PROPAGATE(gemm(c, xn, H, R.in_w, H, n_rows, H, H, R.in_b, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, q, nullptr, H, s));
+  SLIME_PROPAGATE(gemm(c, tn, H, R.in_w + static_cast<size_t>(H) * H, H, t_rows, 2 * H, H, R.in_b + H, nullptr, 0, 0, nullptr,
+                       GEMM_EPI_NONE, kv, nullptr, 2 * H, s));
+  AttnParams ap;
+  ap.q = q; ap.k = kv; ap.v = kv + H; ap.o = xn;
+  ap.q_ld = H; ap.k_ld = ap.v_ld = 2 * H; ap.o_ld = H;
+  ap.cu_q = nullptr; ap.cu_k = cu_k;           // every sample's n_per queries against its own kept prompt tokens
+  ap.seqlen_q = n_per; ap.seqlen_k = T;
+  ap.q_batch_rows = n_per; ap.k_batch_rows = 0; ap.o_batch_rows = n_per;
+  ap.batch = B; ap.num_heads = heads; ap.num_kv_heads = heads; ap.head_dim = 128;
+  ap.scale = 1.0f / sqrtf(128.0f); ap.causal = 0;
+  ap.total_q_rows = n_rows; ap.total_k_rows = t_rows;
+  SLIME_PROPAGATE(slime_launch_attention(ap, s));
+  SLIME_PROPAGATE(gemm(c, xn, H, R.out_w, H, n_rows, H, H, R.out_b, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, q, nullptr, H, s));
+  SLIME_PROPAGATE(slime_launch_layernorm(q, H, R.ln_post_w, R.ln_post_b, xn, H, n_rows, H, LN_EPS, 0, 0, 0, s));
+  SLIME_PROPAGATE(gemm(c, xn, H, R.fc1_w, H, n_rows, Dh, H, R.fc1_b, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, hid, nullptr, Dh, s));
+  SLIME_PROPAGATE(slime_launch_qf_logits(hid, R.fc2_w, R.fc2_b, logit, n_rows, Dh, B, n_per, n_valid, c->d.temp, s));
+  // the sampler soft-maxes the router's (already soft-maxed) output once more before the top-p rule
+  SLIME_PROPAGATE(slime_launch_router_select(logit, B, n_per, n_valid, c->d.temp, c->d.top_p, 0, probs_out, sel_idx,
+                                             sel_count, s));
+  return SLIME_OK;
+}
+
 int router_body(slime_ctx* c, Arena& a, const bf16* local, int n_per, const int* n_valid, const long long* ids,
                 const bf16* text, const unsigned char* mask, int B, int T, float* probs_out, int* sel_idx,
                 int* sel_count, cudaStream_t s) {
+  if ((c->d.flags & SLIME_FLAG_ROUTER_QFORMER) != 0)
+    return router_qformer_body(c, a, local, n_per, n_valid, ids, text, mask, B, T, probs_out, sel_idx, sel_count, s);
   const int H = c->d.hidden;
   float* inv_norm = a.get<float>(static_cast<size_t>(B) * T);
   float* tvec = a.get<float>(static_cast<size_t>(B) * H);
@@ -649,7 +712,7 @@ int slime_ctx_finalize_weights(slime_ctx* c, void* ws, size_t ws_bytes, void* st
   c->has_rs[1] = c->w.count("rs_global.query") > 0;
   c->has_proj = c->w.count("proj.fc1_w") > 0;
   c->has_llm = c->w.count("llm.embed") > 0;
-  SLIME_REQUIRE(c->has_vit || c->has_rs[0] || c->has_rs[1] || c->has_proj || c->has_llm,
+  SLIME_REQUIRE(c->has_vit || c->has_rs[0] || c->has_rs[1] || c->has_proj || c->has_llm || c->w.count("router.in_proj_w") > 0,
                 "finalize: no weight group registered");
   if (c->has_vit) {
   W("vit.patch_w", D, c->vit_kpad, c->vit_patch_w);
@@ -706,6 +769,24 @@ int slime_ctx_finalize_weights(slime_ctx* c, void* ws, size_t ws_bytes, void* st
   W("proj.fc2_b", 1, H, c->proj_fc2_b);
   W("proj.w_gate", D, 2, c->proj_w_gate);
   }  // has_proj
+  c->has_router = c->w.count("router.in_proj_w") > 0;
+  if (c->has_router) {
+  SLIME_REQUIRE(H % 128 == 0 && (H / 4) % 8 == 0, "qformer router needs hidden_size %% 128 == 0 (heads = H/128)");
+  W("router.ln_q_w", 1, H, c->qf.ln_q_w);
+  W("router.ln_q_b", 1, H, c->qf.ln_q_b);
+  W("router.ln_kv_w", 1, H, c->qf.ln_kv_w);
+  W("router.ln_kv_b", 1, H, c->qf.ln_kv_b);
+  W("router.ln_post_w", 1, H, c->qf.ln_post_w);
+  W("router.ln_post_b", 1, H, c->qf.ln_post_b);
+  W("router.in_proj_w", 3 * H, H, c->qf.in_w);
+  W("router.in_proj_b", 1, 3 * H, c->qf.in_b);
+  W("router.out_w", H, H, c->qf.out_w);
+  W("router.out_b", 1, H, c->qf.out_b);
+  W("router.fc1_w", H / 4, H, c->qf.fc1_w);
+  W("router.fc1_b", 1, H / 4, c->qf.fc1_b);
+  W("router.fc2_w", 1, H / 4, c->qf.fc2_w);
+  W("router.fc2_b", 1, 1, c->qf.fc2_b);
+  }  // has_router
   const int QKV = (d.heads + 2 * d.kv_heads) * d.head_dim;
   if (c->has_llm) {
   W("llm.embed", d.vocab, H, c->llm_embed);

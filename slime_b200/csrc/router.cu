@@ -263,7 +263,137 @@ __global__ void __launch_bounds__(SEL_THREADS) router_select_kernel(
   if (tid == 0) sel_count[b] = keep;
 }
 
+// ------------------------------------------------------------------------------------------
+// 'qformer' router (reference multimodal_resampler/builder.py:94-162, TextGuidedRouterAttention): the local tokens
+// cross-attend the prompt, an MLP turns every attended token into one logit, softmax over the tokens.  The dense
+// parts (LayerNorms, in/out projections, 128-wide heads, first MLP layer) run on the library's GEMM / attention /
+// LayerNorm kernels (api.cu router_qformer_body); what is specific to this router lives here:
+//   * packing the kept prompt tokens of every sample into contiguous rows (the attention kernel takes key ranges,
+//     key_padding_mask = ~mask in the reference) - the cross-attention has no positional term, so only the SET of
+//     kept tokens matters and the placeholder-removal / zero-padding of get_pure_text_embedding reduces to "keep";
+//   * logit_i = <relu(h_i), w2> + b2 and the per-sample softmax.
+// ------------------------------------------------------------------------------------------
+// One CTA; warp w handles samples w, w + nwarps, ...: count the kept tokens, then (after the prefix sum over the samples)
+// assign every kept token its packed row.  dst_row[b*T + t] = packed row or -1;  cu[b] = first packed row of sample b.
+__global__ void __launch_bounds__(1024) qf_text_rows_kernel(const long long* __restrict__ ids,
+                                                            const unsigned char* __restrict__ mask, int B, int T,
+                                                            long long image_token, int vocab, int* __restrict__ dst_row,
+                                                            int* __restrict__ cu) {
+  extern __shared__ int qf_cnt[];  // [B + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  auto keep = [&](int b, int t) {
+    const long long i = static_cast<long long>(b) * T + t;
+    if (mask != nullptr && mask[i] == 0) return false;
+    if (ids == nullptr) return true;
+    const long long id = ids[i];
+    return id != image_token && id >= 0 && id < vocab;
+  };
+  for (int b = warp; b < B; b += nw) {
+    int n = 0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      n += __popc(__ballot_sync(0xffffffffu, t < T && keep(b, t)));
+    }
+    if (lane == 0) qf_cnt[b + 1] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    qf_cnt[0] = 0;
+    for (int b = 0; b < B; ++b) qf_cnt[b + 1] += qf_cnt[b];
+    for (int b = 0; b <= B; ++b) cu[b] = qf_cnt[b];
+  }
+  __syncthreads();
+  for (int b = warp; b < B; b += nw) {
+    int base = qf_cnt[b];
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      const bool k = t < T && keep(b, t);
+      const unsigned bal = __ballot_sync(0xffffffffu, k);
+      if (t < T) dst_row[static_cast<long long>(b) * T + t] = k ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
+      base += __popc(bal);
+    }
+  }
+}
+
+// packed[dst_row[i]] = E[ids[i]] (ids != nullptr) or text[i]; 16 bytes per thread
+__global__ void qf_gather_text_kernel(const long long* __restrict__ ids, const bf16* __restrict__ src,
+                                      const int* __restrict__ dst_row, bf16* __restrict__ packed, int rows, int H) {
+  const int chunks = H >> 3;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * chunks) return;
+  const int r = static_cast<int>(i / chunks), ch = static_cast<int>(i % chunks);
+  const int d = dst_row[r];
+  if (d < 0) return;
+  const long long srow = ids != nullptr ? ids[r] : r;
+  *reinterpret_cast<uint4*>(packed + static_cast<long long>(d) * H + ch * 8) =
+      *reinterpret_cast<const uint4*>(src + srow * H + ch * 8);
+}
+
+// logit[i] = <relu(h[i, :]), w2> + b2   (warp per row; prob_proj = Linear, ReLU, Linear)
+__global__ void qf_logit_kernel(const bf16* __restrict__ h, const bf16* __restrict__ w2, const bf16* __restrict__ b2,
+                                float* __restrict__ logit, int rows, int Dh) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float acc = 0.f;
+  for (int c = lane; c < Dh; c += 32)
+    acc += fmaxf(elem_to_float(h[static_cast<long long>(row) * Dh + c]), 0.f) * elem_to_float(w2[c]);
+  acc = warp_sum(acc);
+  if (lane == 0) logit[row] = acc + elem_to_float(b2[0]);
+}
+
+// in place: x[b, :n] = softmax(x[b, :n] / temp)   (one CTA per sample; n = n_valid[b] or n_per)
+__global__ void __launch_bounds__(256) qf_softmax_kernel(float* __restrict__ x, int n_per, const int* __restrict__ n_valid,
+                                                         float temp) {
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = n_valid != nullptr ? min(n_valid[b], n_per) : n_per;
+  float* xb = x + static_cast<long long>(b) * n_per;
+  const float inv_t = 1.0f / temp;
+  float m = -INFINITY;
+  for (int i = tid; i < n; i += 256) m = fmaxf(m, xb[i] * inv_t);
+  m = warp_max(m);
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = tid; i < n; i += 256) sum += expf(xb[i] * inv_t - m);
+  sum = warp_sum(sum);
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  for (int i = tid; i < n; i += 256) xb[i] = expf(xb[i] * inv_t - m) / sum;
+}
+
 }  // namespace
+
+int slime_launch_qf_pack_text(const long long* ids, const unsigned char* mask, const bf16* src, int B, int T, int H,
+                              long long image_token, int vocab, int* dst_row, int* cu, bf16* packed,
+                              cudaStream_t stream) {
+  SLIME_REQUIRE(H % 8 == 0 && B <= 4096, "qformer router: bad H=%d / B=%d", H, B);
+  if (B <= 0 || T <= 0) return SLIME_OK;
+  qf_text_rows_kernel<<<1, 1024, (B + 1) * sizeof(int), stream>>>(ids, mask, B, T, image_token, vocab, dst_row, cu);
+  SLIME_AFTER_LAUNCH();
+  const long long total = static_cast<long long>(B) * T * (H / 8);
+  qf_gather_text_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(ids, src, dst_row, packed, B * T, H);
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
+
+int slime_launch_qf_logits(const bf16* h, const bf16* w2, const bf16* b2, float* logit, int rows, int Dh, int B,
+                           int n_per, const int* n_valid, float temp, cudaStream_t stream) {
+  SLIME_REQUIRE(temp > 0.f, "qformer router: temperature must be positive");
+  if (rows <= 0) return SLIME_OK;
+  qf_logit_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(h, w2, b2, logit, rows, Dh);
+  SLIME_AFTER_LAUNCH();
+  qf_softmax_kernel<<<B, 256, 0, stream>>>(logit, n_per, n_valid, temp);
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
 
 int slime_launch_text_dir(const long long* ids, const unsigned char* mask, const bf16* embed,
                           float* inv_norm_ws, float* tvec, int B, int T, int H, long long image_token,

@@ -13,3 +13,13 @@ int slime_launch_router_score(const bf16* x, const float* tvec, float* score, in
 int slime_launch_router_select(const float* in, int B, int n_per, const int* n_valid, float temp,
                                float top_p, int from_probs, float* probs_out, int* sel_idx,
                                int* sel_count, cudaStream_t stream);
+
+// ---- 'qformer' router (TextGuidedRouterAttention) ----
+// Packs the kept prompt tokens (mask != 0 and a real token id) of every sample into contiguous rows of `packed`
+// (E[ids] rows when ids != nullptr, else rows of the dense [B*T, H] tensor `src`): dst_row [B*T] (scratch), cu [B+1].
+int slime_launch_qf_pack_text(const long long* ids, const unsigned char* mask, const bf16* src, int B, int T, int H,
+                              long long image_token, int vocab, int* dst_row, int* cu, bf16* packed,
+                              cudaStream_t stream);
+// logit[i] = <relu(h[i, :Dh]), w2> + b2, then in place per sample: softmax(logit / temp) over its first n_valid rows
+int slime_launch_qf_logits(const bf16* h, const bf16* w2, const bf16* b2, float* logit, int rows, int Dh, int B,
+                           int n_per, const int* n_valid, float temp, cudaStream_t stream);

@@ -93,7 +93,8 @@ class SlimeEngine:
         d.flags = ((L.SLIME_FLAG_LEFT_PAD if cfg.tokenizer_padding_side == "left" else 0)
                    | (L.SLIME_FLAG_USE_GLOBAL_ONLY if cfg.use_global_only else 0)
                    | (L.SLIME_FLAG_USE_LOCAL_ONLY if cfg.use_local_only else 0)
-                   | (L.SLIME_FLAG_ROPE_INTERLEAVED if self.fused_rope else 0))
+                   | (L.SLIME_FLAG_ROPE_INTERLEAVED if self.fused_rope else 0)
+                   | (L.SLIME_FLAG_ROUTER_QFORMER if cfg.mm_resampler_type == "qformer" else 0))
         self._desc = d
         self._ctx = C.c_void_p()
         with torch.cuda.device(self.device):

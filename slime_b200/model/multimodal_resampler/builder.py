@@ -1,6 +1,7 @@
 """Drop-in for the reference's llava/model/multimodal_resampler/builder.py: TextGuidedSampler
-(local compression layer `post_qformer` + cosine text-guided router + top-p selection) and
-build_vision_sampler.  Only mm_resampler_type='cosine' - the setting of every SliME release - is built."""
+(local compression layer `post_qformer` + text-guided router + top-p selection) and build_vision_sampler.
+mm_resampler_type='cosine' (the setting of every SliME release) and 'qformer' (the cross-attention router
+TextGuidedRouterAttention, reference builder.py:94-162) are built."""
 from __future__ import annotations
 
 import math
@@ -9,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from ...config import SlimeConfig
-from .sampler import Resampler
+from .sampler import Resampler, _MHAParams
 from .._runtime import EngineBinding, bind, binding_of
 
 
@@ -31,17 +32,48 @@ class TextGuidedRouterCosine(nn.Module):
         self.temp = temp
 
 
+class TextGuidedRouterAttention(nn.Module):
+    """Parameter holder of the reference's cross-attention router (builder.py:94-162): same parameter names and
+    shapes (`query` and `self_attn` exist in the reference but are never used in its forward); the arithmetic runs
+    inside slime_router_fwd* when the ctx is created with SLIME_FLAG_ROUTER_QFORMER."""
+
+    def __init__(self, grid_size, embed_dim, num_heads, kv_dim=None, temp=1.0, norm_layer=nn.LayerNorm):
+        super().__init__()
+        if kv_dim is not None and kv_dim != embed_dim:
+            raise NotImplementedError("kv_proj != Identity is not reachable from TextGuidedSampler")
+        if num_heads != embed_dim // 128:
+            raise NotImplementedError("the reference always builds heads of 128 (num_heads = embed_dim // 128)")
+        self.num_queries = 1
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.temp = temp
+        self.query = nn.Parameter(torch.zeros(self.num_queries, embed_dim))
+        nn.init.trunc_normal_(self.query, std=.02)
+        self.kv_proj = nn.Identity()
+        self.self_attn = _MHAParams(embed_dim)
+        self.cross_attn = _MHAParams(embed_dim)
+        self.ln_q = norm_layer(embed_dim)
+        self.ln_kv = norm_layer(embed_dim)
+        self.ln_post = norm_layer(embed_dim)
+        self.prob_proj = nn.Sequential(nn.Linear(embed_dim, embed_dim // 4), nn.ReLU(), nn.Linear(embed_dim // 4, 1))
+
+
 class TextGuidedSampler(nn.Module):
     def __init__(self, projector_type, config):
         super().__init__()
-        if projector_type != "cosine":
-            raise NotImplementedError("only the 'cosine' text-guided router (the SliME release setting) is built")
+        if projector_type not in ("cosine", "qformer"):
+            raise NotImplementedError("text-guided router types built: 'cosine' (the SliME release setting), 'qformer'")
         self.num_queries = config.mm_resampler_dim
         self.topp = config.mm_resampler_topp
         self.temp = config.mm_resampler_temp
         self.grid_size = int(math.sqrt(self.num_queries))
-        self.selector = TextGuidedRouterCosine(pad_token_id=getattr(config, "pad_token_id", 0), temp=self.temp,
-                                               embed_dim=config.hidden_size)
+        self.router_type = projector_type
+        if projector_type == "cosine":
+            self.selector = TextGuidedRouterCosine(pad_token_id=getattr(config, "pad_token_id", 0), temp=self.temp,
+                                                   embed_dim=config.hidden_size)
+        else:
+            self.selector = TextGuidedRouterAttention(grid_size=1, embed_dim=config.hidden_size,
+                                                      num_heads=config.hidden_size // 128, temp=self.temp)
         self.post_qformer = Resampler(grid_size=self.grid_size, embed_dim=config.mm_hidden_size,
                                       num_heads=config.mm_hidden_size // 128, kv_dim=config.mm_hidden_size,
                                       llm_hidden_size=config.hidden_size)
@@ -50,8 +82,9 @@ class TextGuidedSampler(nn.Module):
     def _engine(self, device):
         b = binding_of(self)
         if b is None:
-            cfg = SlimeConfig.from_hf_config(self._config).replace(vit_hidden=self._config.mm_hidden_size)
-            b = EngineBinding(self, cfg, "model.sampler.", ("rs_local",))
+            cfg = SlimeConfig.from_hf_config(self._config).replace(vit_hidden=self._config.mm_hidden_size,
+                                                                   mm_resampler_type=self.router_type)
+            b = EngineBinding(self, cfg, "model.sampler.", ("rs_local", "router"))
             bind(self, b)
         return b.engine(device)
 

@@ -85,6 +85,21 @@ def weight_specs(cfg: SlimeConfig) -> Iterator[Tuple[str, Tuple[int, ...], str]]
         for ln in ("ln_q", "ln_kv", "ln_post"):
             yield prefix + ln + ".weight", (D,), "ln_w"
             yield prefix + ln + ".bias", (D,), "ln_b"
+    if cfg.mm_resampler_type == "qformer":  # TextGuidedRouterAttention (reference multimodal_resampler/builder.py:101-137)
+        r = "model.sampler.selector."
+        yield r + "query", (1, H), "embed"
+        for att in ("self_attn", "cross_attn"):  # self_attn is built by the reference but never used in forward
+            yield r + att + ".in_proj_weight", (3 * H, H), "linear"
+            yield r + att + ".in_proj_bias", (3 * H,), "bias"
+            yield r + att + ".out_proj.weight", (H, H), "linear"
+            yield r + att + ".out_proj.bias", (H,), "bias"
+        for ln in ("ln_q", "ln_kv", "ln_post"):
+            yield r + ln + ".weight", (H,), "ln_w"
+            yield r + ln + ".bias", (H,), "ln_b"
+        yield r + "prob_proj.0.weight", (H // 4, H), "linear"
+        yield r + "prob_proj.0.bias", (H // 4,), "bias"
+        yield r + "prob_proj.2.weight", (1, H // 4), "router_out"
+        yield r + "prob_proj.2.bias", (1,), "bias"
     m = "model.mm_projector."
     yield m + "w_gate", (D, 2), "gate"
     yield m + "w_noise", (D, 2), "zeros"
@@ -133,6 +148,8 @@ def synth_tensor(name: str, shape: Tuple[int, ...], kind: str, seed: int, device
         x = x * (1.0 / math.sqrt(fan_in))
     elif kind == "gate":
         x = x * (2.0 / math.sqrt(shape[0]))
+    elif kind == "router_out":  # last layer of the qformer router: logits of O(3) so the inner softmax is not flat
+        x = x * (6.0 / math.sqrt(shape[1]))
     elif kind == "bias":
         x = x * 0.1
     elif kind == "ln_w":

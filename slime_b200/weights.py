@@ -37,7 +37,7 @@ def resize_pos_table(pos: torch.Tensor, tgt: int) -> torch.Tensor:
     return out.permute(0, 2, 3, 1).flatten(0, 2).to(pos.dtype)
 
 
-ALL_GROUPS = ("vit", "rs_local", "rs_global", "proj", "llm")
+ALL_GROUPS = ("vit", "rs_local", "rs_global", "proj", "llm", "router")  # "router": only packed for mm_resampler_type="qformer"
 
 
 def rope_interleave_rows(w: torch.Tensor, head_dim: int) -> torch.Tensor:
@@ -65,6 +65,8 @@ def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device,
     _pack_adapter(cfg, g, out, device, groups, bf)
     if "llm" in groups:
         _pack_llm(cfg, g, out, rope_interleaved)
+    if "router" in groups and cfg.mm_resampler_type == "qformer":
+        _pack_router(cfg, g, out)
     for k, t in out.items():
         assert t.dim() == 2 and t.is_contiguous() and t.dtype == bf, k
     return out
@@ -123,6 +125,23 @@ def _pack_adapter(cfg, g, out, device, groups, bf):
     out["proj.fc2_w"] = g(m + "projection.2.weight").contiguous()
     out["proj.fc2_b"] = g(m + "projection.2.bias").reshape(1, -1)
     out["proj.w_gate"] = g(m + "w_gate").contiguous()
+
+
+def _pack_router(cfg, g, out):
+    """TextGuidedRouterAttention (reference multimodal_resampler/builder.py:101-137); `query` and `self_attn` are
+    parameters the reference creates but never uses in forward - they are not sent to the device."""
+    r = "model.sampler.selector."
+    out["router.in_proj_w"] = g(r + "cross_attn.in_proj_weight").contiguous()
+    out["router.in_proj_b"] = g(r + "cross_attn.in_proj_bias").reshape(1, -1)
+    out["router.out_w"] = g(r + "cross_attn.out_proj.weight").contiguous()
+    out["router.out_b"] = g(r + "cross_attn.out_proj.bias").reshape(1, -1)
+    for ln in ("ln_q", "ln_kv", "ln_post"):
+        out[f"router.{ln}_w"] = g(r + ln + ".weight").reshape(1, -1)
+        out[f"router.{ln}_b"] = g(r + ln + ".bias").reshape(1, -1)
+    out["router.fc1_w"] = g(r + "prob_proj.0.weight").contiguous()
+    out["router.fc1_b"] = g(r + "prob_proj.0.bias").reshape(1, -1)
+    out["router.fc2_w"] = g(r + "prob_proj.2.weight").reshape(1, -1).contiguous()
+    out["router.fc2_b"] = g(r + "prob_proj.2.bias").reshape(1, 1)
 
 
 def _pack_llm(cfg, g, out, rope_interleaved=False):

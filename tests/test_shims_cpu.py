@@ -27,7 +27,7 @@ def make_model(pname="tiny", **over):
                      max_position_embeddings=cfg.max_position_embeddings, pad_token_id=cfg.pad_token_id,
                      mm_vision_tower=tmp, mm_vision_select_layer=cfg.mm_vision_select_layer,
                      mm_vision_select_feature="patch", mm_projector_type="gated", mm_hidden_size=cfg.vit_hidden,
-                     mm_resampler_type="cosine", mm_resampler_dim=cfg.mm_resampler_dim,
+                     mm_resampler_type=cfg.mm_resampler_type, mm_resampler_dim=cfg.mm_resampler_dim,
                      mm_resampler_topp=cfg.mm_resampler_topp, mm_resampler_temp=cfg.mm_resampler_temp,
                      mm_learnable_gated=-1, mm_patch_merge_type=cfg.mm_patch_merge_type, image_aspect_ratio="anyres",
                      seperator=cfg.seperator, tokenizer_padding_side=cfg.tokenizer_padding_side,
@@ -46,6 +46,18 @@ def test_state_dict_keys_match_reference_exactly():
     res = model.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     assert set(model.state_dict().keys()) == set(sd.keys())
+
+
+def test_qformer_router_state_dict_keys_match_reference():
+    """mm_resampler_type='qformer' (TextGuidedRouterAttention, reference multimodal_resampler/builder.py:94-162): the same
+    synthetic dict the unmodified reference strict-loads for the golden case tiny_qformer_router_b2."""
+    cfg, model = make_model(mm_resampler_type="qformer")
+    sd = synth_state_dict(cfg)
+    assert "model.sampler.selector.cross_attn.in_proj_weight" in sd and "model.sampler.selector.query" in sd
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    assert type(model.get_model().sampler.selector).__name__ == "TextGuidedRouterAttention"
 
 
 def test_reference_attributes_present():
@@ -95,5 +107,5 @@ def test_unsupported_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
         build_vision_projector(SimpleNamespace(mm_projector_type="mlp2x_gelu", mm_hidden_size=1024, hidden_size=4096))
     with pytest.raises(NotImplementedError):
-        build_vision_sampler(SimpleNamespace(mm_resampler_type="qformer", mm_resampler_dim=144, mm_resampler_topp=0.9,
+        build_vision_sampler(SimpleNamespace(mm_resampler_type="perceiver", mm_resampler_dim=144, mm_resampler_topp=0.9,
                                              mm_resampler_temp=1.0, mm_hidden_size=1024, hidden_size=4096))
