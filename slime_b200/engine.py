@@ -376,8 +376,10 @@ class SlimeEngine:
 
     @torch.no_grad()
     def generate_packed(self, rows, cu_seqlens, pos_ids, lengths, max_new_tokens: int = 20, eos_token_ids=(),
-                        sample_fn=None) -> torch.Tensor:
-        """Decoder prefill of packed embedding rows with the KV cache attached, then decode steps."""
+                        sample_fn=None, on_step=None) -> torch.Tensor:
+        """Decoder prefill of packed embedding rows with the KV cache attached, then decode steps.
+        on_step(next_ids [B], generated_so_far list of [B]) is called after every sampled token (streamers, stopping
+        criteria of the HF generate() API); a true return value ends the generation."""
         B = len(lengths)
         cache_len = min(self._desc.max_pos, max(lengths) + max_new_tokens + 1)
         self.attach_kv_cache(B, cache_len)
@@ -390,6 +392,8 @@ class SlimeEngine:
             for step in range(max_new_tokens):
                 nxt = logits.argmax(-1) if sample_fn is None else sample_fn(logits)
                 out.append(nxt)
+                if on_step is not None and on_step(nxt, out):
+                    break
                 if eos.numel():
                     done |= torch.isin(nxt, eos)
                     if bool(done.all()):

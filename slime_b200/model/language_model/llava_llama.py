@@ -218,6 +218,10 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         top_p = kwargs.pop("top_p", None)
         if int(kwargs.pop("num_beams", 1) or 1) != 1:
             raise NotImplementedError("beam search is not built")
+        # HF generate() hooks the reference's callers use: serve/cli.py:95-105 and serve/model_worker.py:168-189 read the
+        # output through a `streamer`, eval scripts pass `stopping_criteria=[KeywordsStoppingCriteria(...)]` (mm_utils.py:292)
+        streamer = kwargs.pop("streamer", None)
+        stopping = kwargs.pop("stopping_criteria", None) or []
         eos = kwargs.pop("eos_token_id", getattr(self.config, "eos_token_id", None))
         eos = set(eos) if isinstance(eos, (list, tuple)) else ({eos} if eos is not None else set())
         eng = self._engine(inputs.device)
@@ -246,8 +250,26 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
                 probs = torch.zeros_like(probs).scatter(1, si, sp_ / sp_.sum(-1, keepdim=True))
             return torch.multinomial(probs, 1, generator=gen).squeeze(1)
 
+        if streamer is not None:
+            # like GenerationMixin with inputs_embeds: the first put() carries the (empty) prompt ids
+            streamer.put(torch.zeros(inputs.shape[0], 0, dtype=torch.long))
+
+        def on_step(nxt, so_far):
+            if streamer is not None:
+                streamer.put(nxt.cpu())
+            if stopping:
+                ids_so_far = torch.stack(so_far, 1)  # generated tokens only, as HF passes them for inputs_embeds prompts
+                for crit in stopping:
+                    r = crit(ids_so_far, None)
+                    if bool(r.all()) if torch.is_tensor(r) else bool(r):
+                        return True
+            return False
+
         # prefill with the KV cache attached, then native decode steps (slime_decoder_decode_fwd)
-        toks = eng.generate_packed(rows, cu_t, pos, lengths, max_new, tuple(eos), sample)
+        toks = eng.generate_packed(rows, cu_t, pos, lengths, max_new, tuple(eos), sample,
+                                   on_step if (streamer is not None or stopping) else None)
+        if streamer is not None:
+            streamer.end()
         # like HF: positions after a sequence's EOS are padded
         pad = getattr(self.config, "pad_token_id", 0) or 0
         if eos:

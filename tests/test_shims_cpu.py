@@ -109,3 +109,75 @@ def test_unsupported_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
         build_vision_sampler(SimpleNamespace(mm_resampler_type="perceiver", mm_resampler_dim=144, mm_resampler_topp=0.9,
                                              mm_resampler_temp=1.0, mm_hidden_size=1024, hidden_size=4096))
+
+
+class _StubEngine:
+    """Stands in for SlimeEngine in generate(): emits a scripted token sequence through the same generate_packed
+    contract (sample_fn on [B, V] logits, on_step hook, EOS handling) so the HF-API plumbing is testable without a GPU."""
+
+    def __init__(self, vocab, hidden, script):
+        self.device = torch.device("cpu")
+        self.weights = {"llm.embed": torch.randn(vocab, hidden)}
+        self.script = script  # list of token ids per step (same for every sequence)
+        self.vocab = vocab
+
+    def generate_packed(self, rows, cu_seqlens, pos_ids, lengths, max_new_tokens=20, eos_token_ids=(), sample_fn=None,
+                        on_step=None):
+        B = len(lengths)
+        out, done = [], torch.zeros(B, dtype=torch.bool)
+        eos = torch.tensor(list(eos_token_ids), dtype=torch.long)
+        for step in range(max_new_tokens):
+            logits = torch.full((B, self.vocab), -10.0)
+            logits[:, self.script[min(step, len(self.script) - 1)]] = 10.0
+            nxt = logits.argmax(-1) if sample_fn is None else sample_fn(logits)
+            out.append(nxt)
+            if on_step is not None and on_step(nxt, out):
+                break
+            if eos.numel():
+                done |= torch.isin(nxt, eos)
+                if bool(done.all()):
+                    break
+        return torch.stack(out, 1)
+
+
+def test_generate_streamer_and_stopping_criteria_hooks(monkeypatch):
+    """generate(streamer=..., stopping_criteria=[...]) as the reference's callers use it (serve/cli.py:95-105,
+    serve/model_worker.py:168-189, mm_utils.py:292 KeywordsStoppingCriteria): prompt put first, one put per token,
+    end(); a criterion returning True (bool or tensor) stops the loop; tokens after EOS are padded."""
+    cfg, model = make_model()
+    stub = _StubEngine(cfg.vocab_size, cfg.hidden_size, script=[11, 12, 13, 14, 15, 16])
+    monkeypatch.setattr(type(model), "_engine", lambda self, device=None: stub)
+    ids = torch.randint(3, 100, (1, 7))
+
+    class Streamer:
+        def __init__(self):
+            self.puts, self.ended = [], False
+
+        def put(self, v):
+            self.puts.append(v.clone())
+
+        def end(self):
+            self.ended = True
+
+    st = Streamer()
+    out = model.generate(ids, max_new_tokens=4, streamer=st)
+    assert out.tolist() == [[11, 12, 13, 14]]
+    assert st.ended and len(st.puts) == 5 and st.puts[0].shape == (1, 0)
+    assert [int(p[0]) for p in st.puts[1:]] == [11, 12, 13, 14]
+
+    seen = []
+
+    def crit_bool(output_ids, scores):
+        seen.append(output_ids.clone())
+        return output_ids.shape[1] >= 3
+
+    out = model.generate(ids, max_new_tokens=6, stopping_criteria=[crit_bool])
+    assert out.tolist() == [[11, 12, 13]]
+    assert [s.shape[1] for s in seen] == [1, 2, 3] and seen[-1].tolist() == [[11, 12, 13]]
+    out = model.generate(ids, max_new_tokens=6, stopping_criteria=[lambda o, s: torch.tensor([o[0, -1] == 12])])
+    assert out.tolist() == [[11, 12]]
+    # EOS: generation ends when every sequence has produced it
+    out = model.generate(ids, max_new_tokens=6, eos_token_id=13)
+    assert out.tolist() == [[11, 12, 13]]
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, max_new_tokens=2, num_beams=4)
