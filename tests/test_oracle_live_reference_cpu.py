@@ -1,0 +1,115 @@
+"""Pins the CPU oracle against the UNMODIFIED reference running live in this container (/root/reference, read-only;
+skipped where the tree is absent, e.g. on the GPU box), on randomised inputs the committed golden fixtures do not
+cover: arbitrary attention-mask patterns (gaps, left / right padding of the INPUT), both output padding sides,
+truncation at tokenizer_model_max_length, labels, prompts without an image placeholder, 1 / 3 / 5 crops per sample,
+flat and spatial merge, several top-p values.  Integer outputs (attention mask, labels, position ids, lengths) must be
+exact; embeddings and last-token logits agree to fp32 summation order (reference llava_arch.py:162-459,
+multimodal_resampler/builder.py:248-281, llava_llama.py:57-104)."""
+import random
+
+import pytest
+import torch
+
+from oracle import ref_harness
+from oracle import slime_oracle as O
+from slime_b200.config import preset
+from slime_b200.synth import synth_inputs, synth_state_dict
+
+pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree not present")
+
+
+def _build(router):
+    cfg = preset("tiny", mm_patch_merge_type="flat", mm_resampler_type=router)
+    torch.manual_seed(0)
+    model = ref_harness.build_reference(cfg, dtype=torch.float32)
+    return cfg, model, synth_state_dict(cfg)
+
+
+@pytest.fixture(scope="module")
+def live():
+    return _build("cosine")
+
+
+@pytest.fixture(scope="module")
+def live_qformer():
+    """the cross-attention router (TextGuidedRouterAttention, multimodal_resampler/builder.py:94-162)"""
+    return _build("qformer")
+
+
+def rel(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def make_trial(cfg, seed):
+    rng = random.Random(seed)
+    B = rng.choice([1, 2, 3])
+    n = rng.choice([1, 3, 5])
+    T = rng.randint(8, 36)
+    ipos = rng.randint(0, T - 1)
+    px, ids, mask = synth_inputs(cfg, B, n, T, seed=1000 + seed, image_pos=ipos, ragged=False)
+    for b in range(B):  # arbitrary mask patterns: right padding, left padding, a hole - never on the placeholder
+        kind = rng.choice(["full", "right", "left", "hole"])
+        if kind == "right" and ipos < T - 1:
+            mask[b, rng.randint(ipos + 1, T - 1):] = 0
+        elif kind == "left" and ipos > 0:
+            mask[b, : rng.randint(1, ipos)] = 0
+        elif kind == "hole":
+            j = rng.randint(0, T - 1)
+            if j != ipos:
+                mask[b, j] = 0
+    if B > 1 and rng.random() < 0.3:  # a prompt without an image placeholder (llava_arch.py:369-376)
+        ids[B - 1, ipos] = 7
+    labels = None
+    if rng.random() < 0.6:
+        labels = ids.clone()
+        labels[:, : rng.randint(0, T // 2)] = -100
+        labels[labels == -200] = -100
+    over = dict(tokenizer_padding_side=rng.choice(["right", "left"]),
+                tokenizer_model_max_length=rng.choice([None, None, 200, 450]),
+                mm_resampler_topp=rng.choice([0.3, 0.6, 0.95]),
+                mm_patch_merge_type="spatial" if (n == 5 and rng.random() < 0.5) else "flat")
+    return px, ids, mask, labels, over
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_oracle_equals_live_reference(live, seed):
+    _check(live, seed)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 4, 9, 13])
+def test_oracle_equals_live_reference_qformer_router(live_qformer, seed):
+    _check(live_qformer, seed)
+
+
+def _check(built, seed):
+    cfg0, model, sd = built
+    px, ids, mask, labels, over = make_trial(cfg0, seed)
+    cfg = cfg0.replace(**over)
+    B = px.shape[0]
+    sizes = [(672, 672)] * B
+    model.config.tokenizer_padding_side = cfg.tokenizer_padding_side
+    model.config.tokenizer_model_max_length = cfg.tokenizer_model_max_length
+    model.config.mm_patch_merge_type = cfg.mm_patch_merge_type
+    model.get_model().sampler.topp = cfg.mm_resampler_topp
+    with torch.no_grad():
+        _, pos, attn, _, emb, lab = model.prepare_inputs_labels_for_multimodal(ids, None, mask, None, labels, px,
+                                                                               image_sizes=sizes)
+        out = model(input_ids=ids, attention_mask=mask, images=px, image_sizes=sizes, labels=labels, use_cache=False)
+        grids = [O.grid_shape(sizes[0], cfg.vit_image)] * B
+        res = O.prefill(sd, cfg, px, ids, mask, grids, labels=labels)
+    # ---- integer outputs: exact ----
+    lens = attn.sum(1).tolist()
+    assert res["lengths"] == lens, (over, res["lengths"], lens)
+    assert torch.equal(res["attention_mask"], attn.bool())
+    if lab is not None:
+        assert torch.equal(res["labels"], lab)
+    if pos is not None:
+        assert torch.equal(res["position_ids"], pos)
+    # ---- floats: same arithmetic, fp32 summation order only ----
+    assert res["inputs_embeds"].shape == emb.shape
+    assert rel(res["inputs_embeds"], emb) < 2e-5
+    left = cfg.tokenizer_padding_side == "left"
+    for b in range(B):
+        ref_last = out.logits[b, -1] if left else out.logits[b, lens[b] - 1]
+        assert rel(res["logits"][b][-1], ref_last) < 2e-4, (seed, b)
