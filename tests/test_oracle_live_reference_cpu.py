@@ -113,3 +113,28 @@ def _check(built, seed):
     for b in range(B):
         ref_last = out.logits[b, -1] if left else out.logits[b, lens[b] - 1]
         assert rel(res["logits"][b][-1], ref_last) < 2e-4, (seed, b)
+
+
+def test_grid_math_equals_live_reference():
+    """select_best_resolution_uhd / get_anyres_image_grid_shape (reference llava/mm_utils.py:41-97,156-174) - the host
+    integer math that decides the crop grid and therefore the raster order of the local tokens - on 6000 random image
+    sizes plus the degenerate ones: the framework's function AND the oracle's restatement must return the reference's."""
+    import sys
+
+    if ref_harness.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_harness.REFERENCE_ROOT)
+    from llava import mm_utils as R  # type: ignore
+
+    from slime_b200 import mm_utils as M
+
+    rng = random.Random(7)
+    sizes = [(rng.randint(1, 4000), rng.randint(1, 4000)) for _ in range(3000)]
+    sizes += [(rng.randint(300, 1100), rng.randint(300, 1100)) for _ in range(3000)]  # around the tile multiples
+    sizes += [(336, 336), (672, 672), (1008, 1008), (1344, 1344), (1, 1), (1, 5000), (5000, 1), (337, 336), (671, 673)]
+    pin = [[336, 672], [672, 336], [672, 672], [1008, 336], [336, 1008]]
+    for size in sizes:
+        ref_res = R.select_best_resolution_uhd(size, (336, 336))
+        assert tuple(M.select_best_resolution_uhd(size, (336, 336))) == tuple(ref_res), size
+        ref_grid = tuple(R.get_anyres_image_grid_shape(size, pin, 336))
+        assert tuple(M.get_anyres_image_grid_shape(size, pin, 336)) == ref_grid, size
+        assert tuple(O.grid_shape(size, 336)) == ref_grid, size
