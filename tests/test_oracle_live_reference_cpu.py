@@ -138,3 +138,54 @@ def test_grid_math_equals_live_reference():
         ref_grid = tuple(R.get_anyres_image_grid_shape(size, pin, 336))
         assert tuple(M.get_anyres_image_grid_shape(size, pin, 336)) == ref_grid, size
         assert tuple(O.grid_shape(size, 336)) == ref_grid, size
+
+
+def test_image_preprocessing_equals_live_reference():
+    """The reference's own process_images (llava/mm_utils.py:231-259: anyres slicing incl. the bicubic global view,
+    'pad' and plain CLIP modes) run live on random images of random sizes; the pre-processing oracle - which the CUDA
+    kernels are compared with bit for bit on the GPU - must return exactly the same float32 tensors."""
+    import sys
+    import types
+
+    import numpy as np
+
+    pil_clip = pytest.importorskip("transformers.models.clip.image_processing_pil_clip")
+    from PIL import Image
+
+    if ref_harness.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_harness.REFERENCE_ROOT)
+    from llava.mm_utils import process_images  # type: ignore
+
+    from oracle import preprocess_oracle as PO
+    from slime_b200.mm_utils import select_best_resolution_uhd
+
+    hf = pil_clip.CLIPImageProcessorPil(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336})
+
+    class Proc:  # transformers 5.x returns SizeDict objects; the reference (4.37.2) expects plain dicts
+        crop_size, size = {"height": 336, "width": 336}, {"shortest_edge": 336}
+        image_mean, image_std = list(hf.image_mean), list(hf.image_std)
+        preprocess = staticmethod(hf.preprocess)
+
+        def __call__(self, images, return_tensors=None):
+            return hf(images, return_tensors=return_tensors)
+
+    rng = np.random.default_rng(2024)
+    trials = [("anyres", 640, 480), ("anyres", 97, 1301), ("pad", 500, 123), (None, 400, 700)]
+    for _ in range(8):
+        trials.append((["anyres", "anyres", "pad", None][int(rng.integers(0, 4))], int(rng.integers(40, 1400)),
+                       int(rng.integers(40, 1400))))
+    for mode, w, h in trials:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if rng.random() < 0.5:  # smooth content with saturated patches: bicubic over/undershoot must clip like PIL
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = np.clip(np.stack([127 + 125 * np.sin(xx / (5.0 + c) + yy / 9.0) for c in range(3)], -1), 0, 255).astype(np.uint8)
+            img[h // 3: h // 3 + h // 6 + 1, w // 4: w // 4 + w // 5 + 1] = 255
+        cfg = types.SimpleNamespace(image_aspect_ratio=mode, image_grid_pinpoints="[(336, 672)]")
+        ref = process_images([Image.fromarray(img)], Proc(), cfg)
+        ref = (ref[0] if mode == "anyres" else ref).numpy()
+        if mode == "anyres":
+            got = PO.process_anyres(img, select_best_resolution_uhd((w, h), (336, 336)))
+        else:
+            got = PO.process_single(img, mode)[None]
+        assert got.shape == ref.shape, (mode, w, h, got.shape, ref.shape)
+        assert np.array_equal(got, ref), (mode, w, h, float(np.abs(got - ref).max()))
