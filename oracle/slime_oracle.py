@@ -5,7 +5,8 @@ leg as the CHECKER; the product path (slime_b200/) never touches it.
 Pinned: tests/test_oracle_cpu.py checks every function here against tests/golden/*.npz, which were
 produced by running the UNMODIFIED reference (/root/reference + transformers 5.5.0) on the same
 synthetic weights (oracle/gen_golden.py).  The reference itself ships no tests or golden vectors
-(SURVEY.md section 4), so those generated fixtures are the pin.
+(SURVEY.md section 4), so those generated fixtures are the pin; tests/test_oracle_live_reference_cpu.py additionally runs the
+reference LIVE next to this file on randomised inputs wherever /root/reference exists (integer outputs exact).
 
 Each function cites the reference lines it restates.  "HF:" = transformers 5.5.0
 (site-packages/transformers/), the third-party dependency that holds the CLIP / Llama arithmetic
