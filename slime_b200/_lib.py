@@ -141,6 +141,7 @@ SIGNATURES = {
     "slime_op_qkv_rope": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "slime_gemm_set_2cta_mode": (_i, [_i]),
     "slime_gemm_set_epi_mode": (_i, [_i]),
+    "slime_gemm_set_tail_split": (_i, [_i]),
     "slime_gemm_set_skinny_mode": (_i, [_i]),
     "slime_decode_attention_set_mode": (_i, [_i]),
     "slime_set_pdl_mode": (_i, [_i]),
