@@ -510,10 +510,12 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
   bf16* qkv = a.get<bf16>(static_cast<size_t>(B) * QKV);
   bf16* att = a.get<bf16>(static_cast<size_t>(B) * QD);
   bf16* act = a.get<bf16>(static_cast<size_t>(B) * I);
-  // split-K scratch of the projections: up to 8 splits of the [B, <= max(QKV, H)] outputs, 2 of the wide ones
+  // split-K scratch of the projections: up to 8 splits of the [B, <= max(QKV, H)] outputs, 4 of the wide ones (more
+  // than 16 sequences stage at most 2048 k per split: hidden size 5120 needs 4 splits of gate/up and the LM head;
+  // tests/test_skinny_plan_cpu.py mirrors the plan and checks this bound for every model size and batch)
   const size_t wide = static_cast<size_t>(2 * I > d.vocab ? 2 * I : d.vocab);
   const size_t narrow = static_cast<size_t>(QKV > H ? QKV : H);
-  const size_t sk_floats = static_cast<size_t>(B) * (8 * narrow > 2 * wide ? 8 * narrow : 2 * wide);
+  const size_t sk_floats = static_cast<size_t>(B) * (8 * narrow > 4 * wide ? 8 * narrow : 4 * wide);
   float* skws = a.get<float>(sk_floats);
   // kv splits of the attention: sized for the attached cache (the dry run has none: assume the worst case)
   const int cache_len = c->kv_cache != nullptr ? c->kv_cache_len : d.max_pos;
