@@ -19,7 +19,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from .config import IGNORE_INDEX, IMAGE_TOKEN_INDEX, SlimeConfig
+from .config import IMAGE_TOKEN_INDEX, SlimeConfig
 from .mm_utils import get_anyres_image_grid_shape
 from .weights import ALL_GROUPS, pack_weights
 

@@ -189,3 +189,29 @@ def test_image_preprocessing_equals_live_reference():
             got = PO.process_single(img, mode)[None]
         assert got.shape == ref.shape, (mode, w, h, got.shape, ref.shape)
         assert np.array_equal(got, ref), (mode, w, h, float(np.abs(got - ref).max()))
+
+
+@pytest.mark.parametrize("seed,n,T", [(0, 5, 20), (1, 3, 12), (2, 1, 9)])
+def test_greedy_generation_equals_live_reference(live, seed, n, T):
+    """The reference's generate() (llava_llama.py:106-144 -> HF greedy search with a KV cache on the spliced
+    inputs_embeds) against the definition the decode-step tests use on the GPU: token t+1 = argmax of a fresh prefill of
+    the sequence grown by token t (tests/test_decode_gpu.py compares the CUDA decode steps with exactly that)."""
+    cfg, model, sd = live
+    px, ids, mask = synth_inputs(cfg, 1, n, T, seed=500 + seed, image_pos=min(3, T - 1), ragged=False)
+    model.config.tokenizer_padding_side = "right"
+    model.config.tokenizer_model_max_length = None
+    model.config.mm_patch_merge_type = "flat"
+    model.get_model().sampler.topp = cfg.mm_resampler_topp
+    steps = 6
+    with torch.no_grad():
+        ref = model.generate(ids, images=px, image_sizes=[(672, 672)], attention_mask=mask, max_new_tokens=steps,
+                             do_sample=False, use_cache=True, pad_token_id=0)
+        res = O.prefill(sd, cfg, px, ids, mask, [None])
+        seq = res["inputs_embeds"][0, : res["lengths"][0]]
+        embed, toks = sd["model.embed_tokens.weight"], []
+        for _ in range(steps):
+            t = int(O.llama_prefill(sd, cfg, seq[None], [seq.shape[0]])[0][-1].argmax())
+            toks.append(t)
+            seq = torch.cat([seq, embed[t][None]])
+    assert ref.shape == (1, steps)
+    assert ref[0].tolist() == toks
