@@ -9,12 +9,17 @@ A "step" = one prefill pass over one synthetic batch: SliME-Llama3-8B, 672x672 i
 local 336 px crops), 256-token prompt, `--batch` samples per GPU (weak scaling: per-GPU work fixed).
   value : prefill tokens/s with pixels/ids already resident in HBM (real spliced tokens, no padding)
   e2e   : the same metric through the public API (SlimeEngine.prefill) from pinned HOST buffers, with
-          the host->device copy of pixels+ids and the device->host read of the last-token logits inside
-          the timed region
+          the host->device copy of pixels+ids and the device->host read of the (gathered) last-token
+          logits inside the timed region
   roofline     : the tcgen05 GEMM kernel (dominant: ~95 % of FLOPs), algorithmic FLOPs / CUDA-event time
                  of its launches inside the timed region, against the measured bf16 peak
   cpu_baseline : the CPU oracle port of the reference algorithm on this box's host cores (bounded sample)
-Prints ONE JSON line on rank 0.
+  secondary    : short runs of the other modes / BASELINE.json configurations (batch-1 latency, top-p 1.0
+                 fixed-length mode, the fp16 build, and at 8 GPUs the per-GPU shapes of configs 4 and 5)
+Multi-GPU: the only exchange step is the all-gather of the last-token logits; it runs on a side stream
+(slime_b200/parallel.py LogitsGather) and `gather_check` verifies, un-timed, that the gathered blocks are
+bit-identical to what a single GPU computes for the same shard.
+Prints ONE JSON line on rank 0 (stdout); NCCL's own log, if NCCL_DEBUG is set, goes to stderr.
 """
 from __future__ import annotations
 
@@ -121,146 +126,153 @@ def algorithmic_flops(cfg, n_crops, lengths, n_local_tokens_in):
 # --------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference algorithm on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_baseline_sample(cfg, prompt_len, n_crops, decoder_layers_sampled=2, seed=3407, repeats=1, dtype=None):
-    """Bounded sample of the SAME workload on the CPU: one sample (5 crops, T-token prompt) through the full
-    vision tower + SliME adapter + router + splice at real dimensions, and `decoder_layers_sampled` of the
-    decoder layers + final norm + last-token lm_head; the decoder layer time is scaled to all layers (they are
-    identical in shape).  fp32, all host threads.  Returns (tokens/s, description, threads)."""
-    import torch
+class CpuBaseline:
+    """ONE sample of the benchmark workload (n crops, T-token prompt) through oracle/slime_oracle.py on the host
+    cores, at the real dimensions and with EVERY stage executed in full: vision tower + SliME adapter + router +
+    splice, all `num_hidden_layers` decoder layers (oracle.llama_hidden), final norm + last-token lm_head.  To keep
+    host memory bounded the decoder holds `layers_held` layers' weights and cycles through them (layer l runs with the
+    weights of layer l % layers_held; 0.9 GB per fp32 layer is far beyond any cache, so this does not flatter the CPU).
+    Nothing is extrapolated."""
 
-    from oracle import slime_oracle as O
-    from slime_b200.synth import synth_inputs, synth_tensor, weight_specs
+    def __init__(self, cfg, prompt_len, n_crops, dtype=None, layers_held=2, seed=3407, threads=None):
+        import torch
 
-    # give the CPU path its best shot: probe a few thread counts on a GEMM of the path's shape and keep the fastest
-    # (on many-core hosts the largest count is not always the best one for L ~ 1400-row matrices)
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (ncpu, ncpu // 2, 64, 32, 16) if 1 <= c <= ncpu}, reverse=True)
-    a = torch.randn(1400, cfg.hidden_size)
-    w = torch.randn(cfg.intermediate_size, cfg.hidden_size)
-    best_t, best_s = ncpu, float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        torch.matmul(a, w.t())
-        t0 = time.perf_counter()
-        for _ in range(3):
+        from slime_b200.synth import grid_for_crops, synth_inputs, synth_tensor, weight_specs
+
+        self.torch, self.cfg, self.dtype = torch, cfg, dtype
+        self.threads = threads or self.pick_threads(cfg)
+        torch.set_num_threads(self.threads)
+        held = cfg.replace(num_hidden_layers=layers_held)
+        self.layer_map = [l % layers_held for l in range(cfg.num_hidden_layers)]
+        sd = {}
+        for name, shape, kind in weight_specs(held):
+            if name.startswith("model.vision_tower") and f"layers.{cfg.vit_layers - 1}." in name:
+                continue  # the last ViT layer is never executed (select_layer = -2)
+            if kind in ("linear", "embed", "gate") and len(shape) >= 2 and shape[0] * shape[1] > 1 << 22:
+                # cheap N(0, 1/fan_in) fill for the big matrices (values do not matter for timing)
+                sd[name] = torch.empty(shape, dtype=torch.float32).normal_(0, 1.0 / (shape[-1] ** 0.5))
+            else:
+                sd[name] = synth_tensor(name, shape, kind, seed)
+        px, self.ids, self.mask = synth_inputs(held, 1, n_crops, prompt_len, seed=seed)
+        if dtype is not None:  # the reference's other CPU configuration (SURVEY.md 8d: bf16 is ~3x faster on AMX hosts)
+            sd = {k: v.to(dtype) for k, v in sd.items()}
+            px = px.to(dtype)
+        self.sd, self.px = sd, px
+        self.grids = [grid_for_crops(n_crops - 1)]
+        self.n_crops, self.prompt_len = n_crops, prompt_len
+
+    @staticmethod
+    def pick_threads(cfg):
+        """Give the CPU path its best shot: probe a few thread counts on a GEMM of the path's shape, keep the fastest."""
+        import torch
+
+        ncpu = os.cpu_count() or 1
+        cands = sorted({c for c in (ncpu, ncpu // 2, 64, 32, 16) if 1 <= c <= ncpu}, reverse=True)
+        a = torch.randn(1400, cfg.hidden_size)
+        w = torch.randn(cfg.intermediate_size, cfg.hidden_size)
+        best_t, best_s = ncpu, float("inf")
+        for c in cands:
+            torch.set_num_threads(c)
             torch.matmul(a, w.t())
-        dt = time.perf_counter() - t0
-        if dt < best_s:
-            best_t, best_s = c, dt
-    del a, w
-    threads = best_t
-    torch.set_num_threads(threads)
-    small = cfg.replace(num_hidden_layers=decoder_layers_sampled)
-    sd = {}
-    for name, shape, kind in weight_specs(small):
-        if name.startswith("model.vision_tower") and f"layers.{cfg.vit_layers - 1}." in name:
-            continue  # the last ViT layer is never executed (select_layer = -2)
-        if kind in ("linear", "embed", "gate") and len(shape) >= 2 and shape[0] * shape[1] > 1 << 22:
-            # cheap N(0, 1/fan_in) fill for the big matrices (values do not matter for timing)
-            t = torch.empty(shape, dtype=torch.float32).normal_(0, 1.0 / (shape[-1] ** 0.5))
-            sd[name] = t
-        else:
-            sd[name] = synth_tensor(name, shape, kind, seed)
-    px, ids, mask = synth_inputs(small, 1, n_crops, prompt_len, seed=seed)
-    if dtype is not None:  # the reference's other CPU configuration (SURVEY.md 8d: bf16 is ~3x faster on AMX hosts)
-        sd = {k: v.to(dtype) for k, v in sd.items()}
-        px = px.to(dtype)
-    from slime_b200.synth import grid_for_crops
-
-    grids = [grid_for_crops(n_crops - 1)]
-    best = None
-    with torch.no_grad():
-        for _ in range(repeats):
             t0 = time.perf_counter()
-            enc = O.encode_images(sd, small, px, ids, mask, grids)
-            emb, am, pid, lab, lens = O.splice(sd["model.embed_tokens.weight"], ids, mask, None, enc["feats"])
+            for _ in range(3):
+                torch.matmul(a, w.t())
+            dt = time.perf_counter() - t0
+            if dt < best_s:
+                best_t, best_s = c, dt
+        return best_t
+
+    def step(self):
+        """One full pass; returns (seconds, spliced tokens, (front, decoder, head) seconds)."""
+        from oracle import slime_oracle as O
+
+        torch, sd, cfg = self.torch, self.sd, self.cfg
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            enc = O.encode_images(sd, cfg, self.px, self.ids, self.mask, self.grids)
+            emb, _, _, _, lens = O.splice(sd["model.embed_tokens.weight"], self.ids, self.mask, None, enc["feats"])
             t1 = time.perf_counter()
-            # decoder slice: time all-position hidden states through the sampled layers, last-token logits only
-            x = emb[0, :lens[0]]
-            tl0 = time.perf_counter()
-            hidden = _decoder_layers_only(O, sd, small, x)
-            tl1 = time.perf_counter()
-            last = O.rms_norm(hidden[-1:], sd["model.norm.weight"], small.rms_norm_eps) @ sd["lm_head.weight"].t()
-            tl2 = time.perf_counter()
-            t_front = t1 - t0
-            t_layers = (tl1 - tl0) * (cfg.num_hidden_layers / decoder_layers_sampled)
-            t_head = tl2 - tl1
-            total = t_front + t_layers + t_head
-            if best is None or total < best[0]:
-                best = (total, t_front, t_layers, t_head, lens[0])
-    total, t_front, t_layers, t_head, L = best
-    cpu_baseline_sample.last_seconds = total  # (scaled) seconds of the one-sample step; the reference arm's ms_per_step
-    desc = (f"1 sample ({n_crops} crops, T={prompt_len}, L={L}) on {threads} threads, "
-            f"{'fp32' if dtype is None else str(dtype).replace('torch.', '')} torch CPU: vision+adapter+router+"
-            f"splice {t_front:.2f}s measured in full; {decoder_layers_sampled}/{cfg.num_hidden_layers} decoder layers measured "
-            f"and scaled x{cfg.num_hidden_layers // decoder_layers_sampled} = {t_layers:.2f}s; final norm + last-token "
-            f"lm_head {t_head:.2f}s")
-    return L / total, desc, threads
+            hidden = O.llama_hidden(sd, cfg, emb[0, :lens[0]], layers=self.layer_map)
+            t2 = time.perf_counter()
+            last = O.rms_norm(hidden[-1:], sd["model.norm.weight"], cfg.rms_norm_eps) @ sd["lm_head.weight"].t()
+            t3 = time.perf_counter()
+        assert last.shape[-1] == cfg.vocab_size
+        return t3 - t0, lens[0], (t1 - t0, t2 - t1, t3 - t2)
+
+    def describe(self, secs, L, parts):
+        dt = "fp32" if self.dtype is None else str(self.dtype).replace("torch.", "")
+        return (f"1 sample ({self.n_crops} crops, T={self.prompt_len}, L={L}) on {self.threads} threads, {dt} torch CPU, "
+                f"every stage in full: vision+adapter+router+splice {parts[0]:.2f}s, all {self.cfg.num_hidden_layers} "
+                f"decoder layers {parts[1]:.2f}s (weights of {len(set(self.layer_map))} layers cycled), final norm + "
+                f"last-token lm_head {parts[2]:.2f}s")
 
 
-def _decoder_layers_only(O, sd, cfg, x):
-    """The layer loop of oracle.llama_prefill without the all-position lm_head (same arithmetic)."""
-    import math
-
+def cpu_baseline_block(cfg, prompt_len, n_crops):
+    """cpu_baseline object of the main line: one bf16 pass (the CPU's faster configuration, AMX / AVX512-BF16) and one
+    fp32 pass (the dtype BASELINE.json's config 1 names), ~15-20 s of CPU work."""
     import torch
-    import torch.nn.functional as F
 
-    nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
-    L = x.shape[0]
-    inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
-    ang = torch.arange(L, dtype=torch.float32)[:, None] * inv[None]
-    cos, sin = torch.cat([ang, ang], -1).cos()[None].to(x.dtype), torch.cat([ang, ang], -1).sin()[None].to(x.dtype)
-    rot = lambda t: torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)  # noqa: E731
-    causal = torch.ones(L, L, dtype=torch.bool).tril()
-    for l in range(cfg.num_hidden_layers):
-        p = f"model.layers.{l}."
-        h = O.rms_norm(x, sd[p + "input_layernorm.weight"], cfg.rms_norm_eps)
-        q = (h @ sd[p + "self_attn.q_proj.weight"].t()).view(L, nh, hd).transpose(0, 1)
-        k = (h @ sd[p + "self_attn.k_proj.weight"].t()).view(L, nkv, hd).transpose(0, 1)
-        v = (h @ sd[p + "self_attn.v_proj.weight"].t()).view(L, nkv, hd).transpose(0, 1)
-        q, k = q * cos + rot(q) * sin, k * cos + rot(k) * sin
-        k, v = k.repeat_interleave(nh // nkv, 0), v.repeat_interleave(nh // nkv, 0)
-        s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
-        a = torch.softmax(s.masked_fill(~causal, float("-inf")), -1) @ v
-        x = x + a.transpose(0, 1).reshape(L, nh * hd) @ sd[p + "self_attn.o_proj.weight"].t()
-        h = O.rms_norm(x, sd[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
-        g = F.silu(h @ sd[p + "mlp.gate_proj.weight"].t()) * (h @ sd[p + "mlp.up_proj.weight"].t())
-        x = x + g @ sd[p + "mlp.down_proj.weight"].t()
-    return x
+    out = {"unit": UNIT, "kind": "port"}
+    try:
+        cb = CpuBaseline(cfg, prompt_len, n_crops, dtype=torch.bfloat16)
+        cb.step()  # first touch / oneDNN primitive creation
+        s, L, parts = cb.step()
+        out.update(value=L / s, cores=cb.threads, dtype="bf16", sample=cb.describe(s, L, parts))
+        threads = cb.threads
+        del cb
+        c32 = CpuBaseline(cfg, prompt_len, n_crops, dtype=None, threads=threads)
+        s, L, parts = c32.step()
+        out.update(value_fp32=L / s, sample_fp32=c32.describe(s, L, parts))
+    except Exception as e:  # noqa: BLE001
+        out.setdefault("value", None)
+        out.setdefault("cores", os.cpu_count())
+        out["sample"] = out.get("sample", "") + f" failed: {e!r}"
+    return out
 
 
 # --------------------------------------------------------------------------------------------
 # reference arm
 # --------------------------------------------------------------------------------------------
 def run_reference_arm(args, cfg):
-    """The reference's CPU implementation of the path on this box's host cores.  The reference is a Python
-    repo that cannot travel to the GPU box (/root/reference is absent there), so this times the CPU oracle
-    port of its algorithm (oracle/slime_oracle.py, pinned to the reference's golden vectors)."""
+    """The reference's CPU implementation of the path on this box's host cores.  The reference is a Python repo that
+    cannot travel to the GPU box (/root/reference is absent there), so this times the CPU oracle port of its algorithm
+    (oracle/slime_oracle.py, pinned to the reference's golden vectors): `--warmup` untimed and exactly `--steps` timed
+    steps, a step = ONE sample of the workload's batch (samples are independent) executed in full, in the CPU's
+    fastest dtype (bf16 where the host has AMX / AVX512-BF16 - 2-3x faster than fp32; the fp32 figure is measured
+    once and reported next to it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
 
-    vals, secs, desc, threads = [], [], "", 1
-    for _ in range(max(1, min(args.steps, 2))):
-        v, desc, threads = cpu_baseline_sample(cfg, args.prompt_len, args.crops, decoder_layers_sampled=2)
-        vals.append(v)
-        secs.append(getattr(cpu_baseline_sample, "last_seconds", None))
-    value = max(vals)
-    step_ms = secs[vals.index(value)] * 1e3 if secs[vals.index(value)] is not None else None
-    bf16_value, bf16_desc = None, None
-    try:  # the reference's faster CPU configuration on AMX hosts; the headline stays the fp32 figure BASELINE.json names
-        bf16_value, bf16_desc, _ = cpu_baseline_sample(cfg, args.prompt_len, args.crops, decoder_layers_sampled=2,
-                                                       dtype=torch.bfloat16)
+    cb = CpuBaseline(cfg, args.prompt_len, args.crops, dtype=torch.bfloat16)
+    for _ in range(args.warmup):
+        cb.step()
+    secs, toks, parts = [], 0, None
+    for _ in range(args.steps):
+        s, L, parts = cb.step()
+        secs.append(s)
+        toks += L
+    total = sum(secs)
+    value = toks / total
+    desc = cb.describe(secs[-1], L, parts)
+    threads = cb.threads
+    del cb
+    fp32_value, fp32_desc = None, None
+    try:
+        c32 = CpuBaseline(cfg, args.prompt_len, args.crops, dtype=None, threads=threads)
+        s, L32, p32 = c32.step()
+        fp32_value, fp32_desc = L32 / s, c32.describe(s, L32, p32)
     except Exception as e:  # noqa: BLE001
-        bf16_desc = f"failed: {e!r}"
+        fp32_desc = f"failed: {e!r}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
-                         "value_bf16": bf16_value, "sample_bf16": bf16_desc},
+        "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg),
+        "step_samples": 1,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "dtype": "bf16",
+                         "sample": f"each of the {args.steps} timed steps = " + desc,
+                         "value_fp32": fp32_value, "sample_fp32": fp32_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -275,8 +287,136 @@ def workload_config(args, cfg):
 
 
 # --------------------------------------------------------------------------------------------
-# main
+# GPU arm
 # --------------------------------------------------------------------------------------------
+class Bench:
+    """One engine + one synthetic batch shard per rank, and the timing loops over it."""
+
+    def __init__(self, torch, dist, eng, cfg, B, crops, T, rank, world, dev, flat=False):
+        from slime_b200.parallel import LogitsGather
+        from slime_b200.synth import grid_for_crops, synth_inputs
+
+        self.torch, self.dist, self.eng, self.cfg = torch, dist, eng, cfg
+        self.B, self.crops, self.T, self.rank, self.world, self.dev = B, crops, T, rank, world, dev
+        self.grids = None if flat else [grid_for_crops(crops - 1)] * B
+        self.set_inputs(3407 + rank)
+        self.gather = LogitsGather(B, cfg.vocab_size, dev) if world > 1 else None
+        self.logits_h = [torch.empty(world * B, cfg.vocab_size, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def set_inputs(self, seed):
+        from slime_b200.synth import synth_inputs
+
+        px_h, ids_h, mask_h = synth_inputs(self.cfg, self.B, self.crops, self.T, seed=seed)
+        self.px_h = px_h.to(self.eng.dtype).pin_memory()
+        self.ids_h, self.mask_h = ids_h.pin_memory(), mask_h.pin_memory()
+        self.px_d, self.ids_d, self.mask_d = self.px_h.to(self.dev), self.ids_h.to(self.dev), self.mask_h.to(self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def step_device(self):
+        res = self.eng.prefill(self.px_d, self.ids_d, self.mask_d, grids=self.grids)
+        if self.gather is not None:  # the one exchange step of the path (SURVEY.md 8e), on the side stream
+            self.last_slot = self.gather.submit(res.logits_last)
+        return res
+
+    def step_e2e(self):
+        """Pinned host pixels + ids -> H2D -> SlimeEngine.prefill -> (all-gather) -> D2H of the result logits; the host
+        reads step k's logits while step k+1 is in flight (double-buffered pinned result buffers)."""
+        torch = self.torch
+        px = self.px_h.to(self.dev, non_blocking=True)
+        ids = self.ids_h.to(self.dev, non_blocking=True)
+        mask = self.mask_h.to(self.dev, non_blocking=True)
+        res = self.eng.prefill(px, ids, mask, grids=self.grids)
+        k = getattr(self, "_e2e_k", 0)
+        self._e2e_k = k + 1
+        prev = getattr(self, "_e2e_ev", None)
+        if self.gather is not None:
+            slot = self.gather.submit(res.logits_last)
+            with torch.cuda.stream(self.gather.stream):
+                self.logits_h[k & 1].copy_(self.gather.bufs[slot], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.gather.stream)
+        else:
+            self.logits_h[k & 1].copy_(res.logits_last, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+        if prev is not None:
+            prev.synchronize()  # the host holds step k-1's logits now
+        self._e2e_ev = ev
+        return res
+
+    def timed(self, fn, steps):
+        torch, dist = self.torch, self.dist
+        lib = self.eng.lib
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = lib.slime_launch_count()
+        e0.record()
+        toks = 0
+        for _ in range(steps):
+            toks += fn().total_tokens
+        if self.gather is not None:
+            self.gather.drain()  # every gather (and result copy) issued in the region is inside the timing
+        ev = getattr(self, "_e2e_ev", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.slime_launch_count() - launches0
+        if self.world > 1:
+            t = torch.tensor([ms, float(toks)], dtype=torch.float64, device=self.dev)
+            tmax, tsum = t.clone(), t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            ms, toks = float(tmax[0]), float(tsum[1])
+        return ms, toks, launches
+
+    def gather_check(self):
+        """Un-timed, N > 1 (VERDICT r1 row i; the reference's multi-GPU story is N independent processes whose outputs
+        are concatenated, scripts/llama/eval/gqa.sh:20-43).  (1) every rank computes the SAME shard: all gathered row
+        blocks must be bit-identical;  (2) each rank computes its own shard, rank 0 then re-computes rank 1's shard
+        on its own GPU and compares it bit for bit with block 1 of the gather."""
+        torch = self.torch
+        if self.gather is None:
+            return None
+        B = self.B
+        self.set_inputs(3407)  # the same inputs everywhere
+        res = self.step_device()
+        g = self.gather.result(self.last_slot).clone()
+        same = all(torch.equal(g[:B], g[r * B:(r + 1) * B]) for r in range(1, self.world)) and torch.equal(g[:B], res.logits_last)
+        self.set_inputs(3407 + self.rank)  # own shard again
+        res = self.step_device()
+        g = self.gather.result(self.last_slot).clone()
+        own = torch.equal(g[self.rank * B:(self.rank + 1) * B], res.logits_last)
+        cross = True
+        if self.rank == 0:
+            self.set_inputs(3407 + 1)
+            r1 = self.eng.prefill(self.px_d, self.ids_d, self.mask_d, grids=self.grids)
+            cross = torch.equal(g[B:2 * B], r1.logits_last)
+            self.set_inputs(3407 + self.rank)
+        ok = torch.tensor([int(same and own and cross)], device=self.dev)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+        torch.cuda.synchronize()
+        return "ok" if int(ok) == 1 else f"MISMATCH (same-shard {same}, own-block {own}, rank0-recomputes-rank1 {cross})"
+
+
+def short_run(torch, dist, eng, cfg, B, crops, T, rank, world, dev, steps, flat=False, warm=3):
+    """A short secondary measurement on one engine: (tokens/s whole job, ms per step, whole-step TFLOP/s per GPU)."""
+    b = Bench(torch, dist, eng, cfg, B, crops, T, rank, world, dev, flat=flat)
+    for _ in range(warm):
+        res = b.step_device()
+    ms, toks, _ = b.timed(b.step_device, steps)
+    fl = algorithmic_flops(cfg, crops * B, res.lengths, (crops - 1) * B * cfg.mm_resampler_dim)
+    step_ms = ms / steps
+    return dict(tokens_per_s=toks / (ms / 1e3), ms_per_step=step_ms, batch_per_gpu=B, crops=crops, prompt_len=T,
+                whole_step_tflops_per_gpu=fl["total"] / (step_ms / 1e3) / 1e12,
+                mean_len=float(statistics.mean(res.lengths)))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,6 +429,7 @@ def main():
     ap.add_argument("--prompt-len", type=int, default=256)
     ap.add_argument("--topp", type=float, default=None, help="override mm_resampler_topp (default 0.95)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short secondary measurements")
     ap.add_argument("--layers", type=int, default=None, help="debug only: truncate the decoder (INVALID as a bench number)")
     args = ap.parse_args()
 
@@ -304,12 +445,17 @@ def main():
         run_reference_arm(args, cfg)
         return
 
+    # NCCL's log (NCCL_DEBUG=INFO from the driver) must not land between stdout's one JSON line: send it to stderr
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
-    from slime_b200 import _lib as L
     from slime_b200.engine import SlimeEngine
-    from slime_b200.synth import grid_for_crops, synth_inputs, synth_tensor, weight_specs
+    from slime_b200.synth import synth_tensor, weight_specs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -318,72 +464,22 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SLIME_NCCL_DEBUG", "WARN")  # stdout = the one JSON line (no banner)
         dist.init_process_group("nccl", device_id=dev)
 
+    def make_engine(c, dtype=torch.bfloat16):
+        specs = {name: (shape, kind) for name, shape, kind in weight_specs(c)}
+        e = SlimeEngine(c, local_rank, max_pos=4096, dtype=dtype)
+        e.load_weights(lambda name: synth_tensor(name, specs[name][0], specs[name][1], 3407, device=dev, dtype=torch.bfloat16))
+        return e
+
     # ---- model: random-init weights of the named architecture, generated on the GPU ----
-    specs = {name: (shape, kind) for name, shape, kind in weight_specs(cfg)}
-    eng = SlimeEngine(cfg, local_rank, max_pos=4096)
-    eng.load_weights(lambda name: synth_tensor(name, specs[name][0], specs[name][1], 3407, device=dev,
-                                               dtype=torch.bfloat16))
+    eng = make_engine(cfg)
     lib = eng.lib
-
-    # ---- inputs: a different synthetic batch shard per rank, pinned on the host ----
     B = args.batch
-    px_h, ids_h, mask_h = synth_inputs(cfg, B, args.crops, args.prompt_len, seed=3407 + rank)
-    px_h = px_h.to(torch.bfloat16).pin_memory()
-    ids_h = ids_h.pin_memory()
-    mask_h = mask_h.pin_memory()
-    grids = [grid_for_crops(args.crops - 1)] * B
-    px_d, ids_d, mask_d = px_h.to(dev), ids_h.to(dev), mask_h.to(dev)
-    gathered = torch.empty(world * B, cfg.vocab_size, dtype=torch.float32, device=dev) if world > 1 else None
-    logits_h = torch.empty(B, cfg.vocab_size, dtype=torch.float32).pin_memory()
-
-    def step_device():
-        res = eng.prefill(px_d, ids_d, mask_d, grids=grids)
-        if world > 1:  # the one exchange step of the path: gather the last-token logits
-            dist.all_gather_into_tensor(gathered, res.logits_last)
-        return res
-
-    def step_e2e():
-        px = px_h.to(dev, non_blocking=True)
-        ids = ids_h.to(dev, non_blocking=True)
-        mask = mask_h.to(dev, non_blocking=True)
-        res = eng.prefill(px, ids, mask, grids=grids)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, res.logits_last)
-        logits_h.copy_(res.logits_last, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return res
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = lib.slime_launch_count()
-        e0.record()
-        toks = 0
-        for _ in range(steps):
-            toks += fn().total_tokens
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = lib.slime_launch_count() - launches0
-        t = torch.tensor([ms, float(toks)], dtype=torch.float64, device=dev)
-        if world > 1:
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = t.clone()
-            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            ms, toks = float(tmax[0]), float(tsum[1])
-        return ms, toks, launches
+    bench = Bench(torch, dist, eng, cfg, B, args.crops, args.prompt_len, rank, world, dev)
 
     for _ in range(max(args.warmup, 3)):
-        res = step_device()
+        res = bench.step_device()
     torch.cuda.synchronize()
     lengths = res.lengths
 
@@ -392,9 +488,7 @@ def main():
     if rank == 0:
         sampler.start()
     lib.slime_profile_enable(1)
-    ms, toks, launches = timed(step_device, args.steps)
-    import ctypes as C
-
+    ms, toks, launches = bench.timed(bench.step_device, args.steps)
     pms, pwork, pl = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
     lib.slime_profile_collect(pms, pwork, pl)
     lib.slime_profile_enable(0)
@@ -403,11 +497,15 @@ def main():
 
     # ---- timed region 2: end to end from pinned host memory through the public API ----
     for _ in range(2):
-        step_e2e()
-    ms_e2e, toks_e2e, _ = timed(step_e2e, args.steps)
+        bench.step_e2e()
+    ms_e2e, toks_e2e, _ = bench.timed(bench.step_e2e, args.steps)
     e2e_value = toks_e2e / (ms_e2e / 1e3)
-    h2d = px_h.numel() * px_h.element_size() + ids_h.numel() * 8 + mask_h.numel() * 8
-    d2h = logits_h.numel() * 4 + (B + 1) * 4
+    h2d = bench.px_h.numel() * bench.px_h.element_size() + bench.ids_h.numel() * 8 + bench.mask_h.numel() * 8
+    d2h = bench.logits_h[0].numel() * 4 + (B + 1) * 4
+    bench._e2e_ev = None
+
+    # ---- un-timed: the gathered logits equal what a single GPU computes (bit for bit) ----
+    gather_check = bench.gather_check()
 
     # ---- timed region 3: from raw RGB bytes - GPU pre-processing (process_images) + prefill ----
     raw = None
@@ -418,28 +516,29 @@ def main():
 
         rng = np.random.default_rng(3407 + rank)
         imgs = [rng.integers(0, 256, (672, 672, 3), dtype=np.uint8) for _ in range(B)]  # 672^2 -> 1 + 2x2 crops
+        host_out = torch.empty(B, cfg.vocab_size, dtype=torch.float32).pin_memory()
 
         def step_raw():
             crops, _ = preprocess_images(imgs, "anyres", dtype=torch.bfloat16, device=dev)
-            ids = ids_h.to(dev, non_blocking=True)
-            mask = mask_h.to(dev, non_blocking=True)
-            res = eng.prefill(torch.stack(crops), ids, mask, grids=grids)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, res.logits_last)
-            logits_h.copy_(res.logits_last, non_blocking=True)
+            ids = bench.ids_h.to(dev, non_blocking=True)
+            mask = bench.mask_h.to(dev, non_blocking=True)
+            r = eng.prefill(torch.stack(crops), ids, mask, grids=bench.grids)
+            if bench.gather is not None:
+                bench.gather.submit(r.logits_last)
+            host_out.copy_(r.logits_last, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return res
+            return r
 
         for _ in range(2):
             step_raw()
-        ms_raw, toks_raw, _ = timed(step_raw, args.steps)
+        ms_raw, toks_raw, _ = bench.timed(step_raw, args.steps)
         raw = {"value": toks_raw / (ms_raw / 1e3), "unit": UNIT, "ms_per_step": ms_raw / args.steps,
-               "h2d_bytes_per_step": B * 672 * 672 * 3 + ids_h.numel() * 8 + mask_h.numel() * 8,
+               "h2d_bytes_per_step": B * 672 * 672 * 3 + bench.ids_h.numel() * 8 + bench.mask_h.numel() * 8,
                "note": "raw 672x672 RGB bytes on the host -> slime_preprocess_fwd (Pillow-exact resize, tiling, "
                        "CLIP normalise) -> prefill -> logits on the host"}
 
     # ---- ViT crops/s (secondary metric of BASELINE.json) ----
-    flat = px_d.flatten(0, 1)
+    flat = bench.px_d.flatten(0, 1)
     for _ in range(2):
         eng.vision_tower(flat)
     torch.cuda.synchronize()
@@ -452,56 +551,127 @@ def main():
     crops_per_s = 5 * flat.shape[0] / (e0.elapsed_time(e1) / 1e3) * world
 
     # ---- decode step after this prefill (secondary, HBM-bound): ms per generated token ----
-    decode = None
-    try:
-        n_dec = 16
-        eng.attach_kv_cache(B, max(lengths) + n_dec + 8)
-        res_d = eng.prefill(px_d, ids_d, mask_d, grids=grids)  # fills the cache
-        lens_d = torch.tensor(res_d.lengths, dtype=torch.int32, device=dev)
-        table = eng.weights["llm.embed"]
-        x_d = table[res_d.logits_last.argmax(-1)]
-        for _ in range(3):
-            eng.decode_step(x_d, lens_d)  # (same slot rewritten: timing only)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = lib.slime_launch_count()
-        e0.record()
-        for _ in range(n_dec):
-            eng.decode_step(x_d, lens_d)
-        e1.record()
-        torch.cuda.synchronize()
-        dms = e0.elapsed_time(e1) / n_dec
-        w_bytes = 2 * (cfg.num_hidden_layers * (cfg.qkv_dim * cfg.hidden_size + cfg.hidden_size * cfg.num_attention_heads * cfg.head_dim
-                                                 + 3 * cfg.intermediate_size * cfg.hidden_size) + cfg.vocab_size * cfg.hidden_size)
-        kv_bytes = cfg.num_hidden_layers * sum(res_d.lengths) * 2 * cfg.num_key_value_heads * cfg.head_dim * 2
-        decode = {"batch": B, "ms_per_step": dms, "tokens_per_s": B / dms * 1e3 * world, "context": float(statistics.mean(lengths)),
-                  "launches_per_step": (lib.slime_launch_count() - n0) / n_dec,
-                  "hbm_bytes_per_step": w_bytes + kv_bytes, "achieved_gbs": (w_bytes + kv_bytes) / dms / 1e6}
-    except Exception as e:  # noqa: BLE001 - never lose the prefill line over the secondary figure
-        decode = {"error": repr(e)}
-    finally:
+    def decode_timing(e, c, px, ids, mask, grids, n_dec=16):
         try:
-            eng.detach_kv_cache()
-        except Exception:  # noqa: BLE001
-            pass
+            nb = px.shape[0]
+            r0 = e.prefill(px, ids, mask, grids=grids)
+            e.attach_kv_cache(nb, max(r0.lengths) + n_dec + 8)
+            res_d = e.prefill(px, ids, mask, grids=grids)  # fills the cache
+            lens_d = torch.tensor(res_d.lengths, dtype=torch.int32, device=dev)
+            x_d = e.weights["llm.embed"][res_d.logits_last.argmax(-1)]
+            for _ in range(3):
+                e.decode_step(x_d, lens_d)  # (same slot rewritten: timing only)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = e.lib.slime_launch_count()
+            t0.record()
+            for _ in range(n_dec):
+                e.decode_step(x_d, lens_d)
+            t1.record()
+            torch.cuda.synchronize()
+            dms = t0.elapsed_time(t1) / n_dec
+            w_bytes = 2 * (c.num_hidden_layers * (c.qkv_dim * c.hidden_size + c.hidden_size * c.num_attention_heads * c.head_dim
+                                                  + 3 * c.intermediate_size * c.hidden_size) + c.vocab_size * c.hidden_size)
+            kv_bytes = c.num_hidden_layers * sum(res_d.lengths) * 2 * c.num_key_value_heads * c.head_dim * 2
+            return {"batch": nb, "ms_per_step": dms, "tokens_per_s": nb / dms * 1e3 * world,
+                    "context": float(statistics.mean(res_d.lengths)),
+                    "launches_per_step": (e.lib.slime_launch_count() - n0) / n_dec,
+                    "hbm_bytes_per_step": w_bytes + kv_bytes, "achieved_gbs": (w_bytes + kv_bytes) / dms / 1e6}
+        except Exception as ex:  # noqa: BLE001 - never lose the prefill line over a secondary figure
+            return {"error": repr(ex)}
+        finally:
+            try:
+                e.detach_kv_cache()
+            except Exception:  # noqa: BLE001
+                pass
+
+    decode = decode_timing(eng, cfg, bench.px_d, bench.ids_d, bench.mask_d, bench.grids)
+    decode_b1 = decode_timing(eng, cfg, bench.px_d[:1], bench.ids_d[:1], bench.mask_d[:1], bench.grids[:1])
+
+    # ---- secondary measurements (short step counts; same kernels, other modes / BASELINE.json configurations) ----
+    peaks = measured_peaks()
+    secondary = {}
+    if not args.no_secondary and args.layers is None:
+        def guarded(name, fn):
+            try:
+                secondary[name] = fn()
+            except Exception as ex:  # noqa: BLE001
+                secondary[name] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
+
+        def lat(e, c, crops, T):
+            r = short_run(torch, None, e, c, 1, crops, T, rank, 1, dev, steps=20)
+            return {"ms": r["ms_per_step"], "tokens_per_s": r["tokens_per_s"],
+                    "whole_step_frac": r["whole_step_tflops_per_gpu"] / peaks["tf_sustained"], "mean_len": r["mean_len"]}
+
+        # batch-1 latency (the reference's eval loop is batch 1, llava/eval/model_vqa_loader.py:103-119)
+        guarded("latency_b1", lambda: {"headline_llama3_8b_T256": lat(eng, cfg, args.crops, args.prompt_len)})
+        # fixed-length mode: top-p 1.0 keeps (almost) every local token (SURVEY.md 8d defines the roofline figure there)
+        def topp1():
+            e1 = eng.clone(mm_resampler_topp=1.0)
+            r = short_run(torch, dist, e1, e1.cfg, B, args.crops, args.prompt_len, rank, world, dev, steps=4)
+            r["whole_step_frac"] = r["whole_step_tflops_per_gpu"] / peaks["tf_sustained"]
+            return r
+        guarded("topp_1.0", topp1)
+        if world == 8 and args.model == "llama3-8b":
+            # BASELINE.json config 4 at its 8-GPU shape: 8B, 8-frame video = 8 crops (flat merge), T 256, 4 samples / GPU
+            def cfg4():
+                e4 = eng.clone(mm_patch_merge_type="flat")
+                return short_run(torch, dist, e4, e4.cfg, 4, 8, 256, rank, world, dev, steps=6, flat=True)
+            guarded("config4_8b_8crops_b32_dp8", cfg4)
+        # the float16 build (the reference's inference dtype, llava/model/builder.py:43) on the headline shape
+        def fp16():
+            e16 = make_engine(cfg, torch.float16)
+            r = short_run(torch, dist, e16, cfg, B, args.crops, args.prompt_len, rank, world, dev, steps=4)
+            r["whole_step_frac"] = r["whole_step_tflops_per_gpu"] / peaks["tf_sustained"]
+            e16.close()
+            return r
+        guarded("fp16_build", fp16)
+        # the other models need their own weights: release the 8B first
+        if args.model == "llama3-8b":
+            bench = None
+            eng.close()
+            del eng
+            torch.cuda.empty_cache()
+            def cfg2():
+                c7 = preset("vicuna-7b")
+                e7 = make_engine(c7)
+                out = lat(e7, c7, 5, 128)
+                e7.close()
+                return out
+            guarded("latency_b1_config2_vicuna7b_T128", cfg2)
+            if world == 8:
+                # BASELINE.json config 5: Vicuna-13B, 1344 px = 17 crops (flat), T 512, batch 64 over 8 GPUs = 8 / GPU
+                def cfg5():
+                    c13 = preset("vicuna-13b", mm_patch_merge_type="flat")
+                    e13 = make_engine(c13)
+                    out = short_run(torch, dist, e13, c13, 8, 17, 512, rank, world, dev, steps=3, flat=True, warm=2)
+                    e13.close()
+                    return out
+                guarded("config5_13b_17crops_b64_dp8", cfg5)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = measured_peaks()
-    if decode is not None and "achieved_gbs" in decode:
-        decode["frac_of_hbm_peak"] = decode["achieved_gbs"] / peaks["hbm"]
+    for d in (decode, decode_b1):
+        if d is not None and "achieved_gbs" in d:
+            d["frac_of_hbm_peak"] = d["achieved_gbs"] / peaks["hbm"]
+    if "achieved_gbs" in decode:
         decode["kernels"] = "weight-streaming mma.sync GEMM (csrc/gemm_skinny.cu) + split-KV mma.sync attention (csrc/decode_attn.cu), PDL"
+        decode["batch_1"] = decode_b1
     fl = algorithmic_flops(cfg, args.crops * B, lengths, (args.crops - 1) * B * cfg.mm_resampler_dim)
     gemm_tf = pwork[0] / (pms[0] / 1e3) / 1e12 if pms[0] > 0 else 0.0
     step_ms = ms / args.steps
     traffic, traffic_note = None, None
-    try:  # DRAM bytes per launch of the dominant GEMM from the committed ncu --set full capture (tools/ncu_summary.py)
+    try:  # DRAM bytes per launch of the dominant GEMM: NOT measured by this run (ncu cannot run inside a timed bench) -
+        # the committed `ncu --set full` capture of the same kernel on the same shape (tools/ncu_summary.py)
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             tr = json.load(f)["gemm"]
-        traffic, traffic_note = tr["dram_bytes_per_launch"], f"mean over {tr['launches']} captured launches, {tr['source']}"
+        traffic = tr["dram_bytes_per_launch"]
+        traffic_note = (f"static: read from profiles/roofline_traffic.json (ncu --set full capture, {tr['launches']} "
+                        f"launch(es), {tr['source']}), not measured in this run")
     except Exception:
         pass
     roofline = {
@@ -513,7 +683,7 @@ def main():
         "launches_per_step": pl[0] / args.steps, "gemm_ms_per_step": pms[0] / args.steps,
         "gemm_share_of_step": (pms[0] / args.steps) / step_ms,
         "attention_ms_per_step": pms[1] / args.steps, "attention_launches_per_step": pl[1] / args.steps,
-        "whole_step_tflops": fl["total"] / (step_ms / 1e3) / 1e12,
+        "whole_step_tflops": fl["total"] / (step_ms / 1e3) / 1e12 * world,
         "whole_step_frac_of_peak": fl["total"] / (step_ms / 1e3) / 1e12 / peaks["tf_sustained"],
     }
     line = {
@@ -528,21 +698,17 @@ def main():
         "decode_step": decode,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "algorithmic_tflop_per_step": {k: v / 1e12 for k, v in fl.items()},
+        "secondary": secondary,
     }
+    if world > 1:
+        line["gather_check"] = gather_check
+        line["gather"] = "all_gather of [B_local, V] fp32 last-token logits on a side stream (slime_b200/parallel.py LogitsGather)"
+    if "latency_b1" in secondary:
+        line["latency_b1"] = dict(secondary["latency_b1"])
+        if "latency_b1_config2_vicuna7b_T128" in secondary:
+            line["latency_b1"]["config2_vicuna7b_T128"] = secondary["latency_b1_config2_vicuna7b_T128"]
     if world == 1 and not args.no_cpu_baseline:
-        try:
-            v, desc, threads = cpu_baseline_sample(cfg, args.prompt_len, args.crops)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
-            try:  # the same sample in bf16 (the faster CPU configuration where the host has AMX / AVX512-BF16)
-                vb, descb, _ = cpu_baseline_sample(cfg, args.prompt_len, args.crops, dtype=torch.bfloat16)
-                line["cpu_baseline"]["value_bf16"] = vb
-                line["cpu_baseline"]["sample_bf16"] = descb
-            except Exception as e:  # noqa: BLE001
-                line["cpu_baseline"]["value_bf16"] = None
-                line["cpu_baseline"]["sample_bf16"] = f"failed: {e!r}"
-        except Exception as e:  # noqa: BLE001
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"failed: {e!r}"}
+        line["cpu_baseline"] = cpu_baseline_block(cfg, args.prompt_len, args.crops)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

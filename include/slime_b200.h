@@ -275,11 +275,6 @@ int slime_set_pdl_mode(int mode);
  * QKV weights, 4 / 8 = the attention kernel / the o-projection's finishing kernel pull 32 MB of gate/up each;
  * -1 = back to SLIME_DECODE_PREFETCH / the build default (0: measured slower than no prefetch in every variant). */
 int slime_set_decode_prefetch(int mask);
-/* OPT-IN, not yet validated on hardware: 1 = the 2-CTA GEMM splits the K range of its last, nearly empty wave of tiles over
- * all clusters (csrc/gemm2_tail_sm100.cu; batch-1 latency), 0 = off (default), -1 = back to SLIME_GEMM_TAIL_SPLIT.  Takes
- * effect for contexts created afterwards (the scratch is allocated by slime_ctx_create).  Trades the bit-exact batch
- * invariance of the default schedule for latency. */
-int slime_gemm_set_tail_split(int mode);
 /* debug: CTA 0 of the tcgen05 attention kernel stamps clock64() of its first 64 tiles into buf [64][16] (NULL = off) */
 int slime_attention_set_trace(long long* buf);
 /* softmax arithmetic of the tcgen05 attention kernel: 0 = scalar FFMA + MUFU.EX2; 5 / 9 = packed fp32 pairs
@@ -287,6 +282,9 @@ int slime_attention_set_trace(long long* buf);
  * (5 is the default); 21 = variant 5 with the kv tiles alternating between two softmax warp groups; 32 = measurement
  * only (no softmax, garbage output); -1 = back to the default (SLIME_ATTN_VARIANT / build default). */
 int slime_attention_set_variant(int variant);
+/* two-query-tile attention kernel (csrc/attention_tc2.cu): how many of every 8 score-column pairs are exponentiated by a
+ * polynomial on the FMA pipe instead of MUFU.EX2 (0, 2, 3 or 4; -1 = back to SLIME_ATTN_POLY / the build default). */
+int slime_attention_set_poly(int pairs_of_8);
 long long slime_launch_count(void);
 int slime_profile_enable(int on);
 int slime_profile_collect(double* ms3, double* work3, long long* launches3);

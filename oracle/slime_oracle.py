@@ -239,14 +239,15 @@ def splice(embed: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, labels: O
     lens = [s.shape[0] for s in seqs]
     Lmax, H = max(lens), embed.shape[1]
     out = embed.new_zeros(B, Lmax, H)
-    am = torch.zeros(B, Lmax, dtype=torch.bool)
-    pid = torch.zeros(B, Lmax, dtype=torch.long)
-    lab = torch.full((B, Lmax), IGNORE_INDEX, dtype=torch.long)
+    dev = embed.device
+    am = torch.zeros(B, Lmax, dtype=torch.bool, device=dev)
+    pid = torch.zeros(B, Lmax, dtype=torch.long, device=dev)
+    lab = torch.full((B, Lmax), IGNORE_INDEX, dtype=torch.long, device=dev)
     for b, L in enumerate(lens):
         sl = slice(Lmax - L, Lmax) if left_pad else slice(0, L)
         out[b, sl] = seqs[b]
         am[b, sl] = True
-        pid[b, sl] = torch.arange(L)
+        pid[b, sl] = torch.arange(L, device=dev)
         lab[b, sl] = labs[b]
     return out, am, pid, lab, lens
 
@@ -255,37 +256,60 @@ def splice(embed: torch.Tensor, ids: torch.Tensor, mask: torch.Tensor, labels: O
 # Llama decoder
 # ------------------------------------------------------------------------------------------
 def rms_norm(x, w, eps):
-    """HF:models/llama/modeling_llama.py:62-67."""
-    return w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+    """HF:models/llama/modeling_llama.py:62-67 - variance in fp32, cast back to the input dtype BEFORE the weight
+    multiply (identical to the plain formula for fp32 inputs; matters when the oracle is run in bf16 as the
+    "reference's own bf16 execution" of the full-size floor test)."""
+    dt = x.dtype
+    xf = x.float()
+    xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return w * xf.to(dt)
+
+
+def llama_hidden(sd, cfg, x: torch.Tensor, layers: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """The decoder layer stack of LlamaModel.forward for ONE sequence x [L, H] (HF:models/llama/modeling_llama.py:
+    :73-168 rotary, :187-288 attention, :171-184 MLP, :291-332 layer), before the final norm.  Runs on x's device
+    in x's dtype (cos / sin are computed in fp32 and cast like HF does); `layers` selects which layers' weights to
+    run (default: all cfg.num_hidden_layers) - the CPU baseline uses it to time every layer position while holding
+    only a few layers' weights in RAM."""
+    nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
+    L, dev = x.shape[0], x.device
+    inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32, device=dev) / hd))
+    ang = torch.arange(L, dtype=torch.float32, device=dev)[:, None] * inv[None]
+    cos, sin = torch.cat([ang, ang], -1).cos()[None].to(x.dtype), torch.cat([ang, ang], -1).sin()[None].to(x.dtype)
+    rot = lambda t: torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)  # noqa: E731
+    causal = torch.ones(L, L, dtype=torch.bool, device=dev).tril()
+    for l in (range(cfg.num_hidden_layers) if layers is None else layers):
+        p = f"model.layers.{l}."
+        h = rms_norm(x, sd[p + "input_layernorm.weight"], cfg.rms_norm_eps)
+        q = (h @ sd[p + "self_attn.q_proj.weight"].t()).view(L, nh, hd).transpose(0, 1)
+        k = (h @ sd[p + "self_attn.k_proj.weight"].t()).view(L, nkv, hd).transpose(0, 1)
+        v = (h @ sd[p + "self_attn.v_proj.weight"].t()).view(L, nkv, hd).transpose(0, 1)
+        q, k = q * cos + rot(q) * sin, k * cos + rot(k) * sin
+        k, v = k.repeat_interleave(nh // nkv, 0), v.repeat_interleave(nh // nkv, 0)
+        s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+        a = torch.softmax(s.masked_fill(~causal, float("-inf")), -1) @ v
+        x = x + a.transpose(0, 1).reshape(L, nh * hd) @ sd[p + "self_attn.o_proj.weight"].t()
+        h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
+        g = F.silu(h @ sd[p + "mlp.gate_proj.weight"].t()) * (h @ sd[p + "mlp.up_proj.weight"].t())
+        x = x + g @ sd[p + "mlp.down_proj.weight"].t()
+    return x
+
+
+def llama_last_logits(sd, cfg, x: torch.Tensor, layers: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Last-token logits [V] of one sequence x [L, H] (final norm + lm_head on the last row only: the all-position
+    lm_head of a 128256-entry vocabulary would be L x V fp32); same arithmetic as llama_prefill."""
+    h = llama_hidden(sd, cfg, x, layers)
+    h = rms_norm(h[-1:], sd["model.norm.weight"], cfg.rms_norm_eps)
+    return (h @ sd["lm_head.weight"].t())[0]
 
 
 def llama_prefill(sd, cfg, embeds: torch.Tensor, lengths: Sequence[int]) -> List[torch.Tensor]:
     """LlamaForCausalLM.forward(inputs_embeds=...) (HF:models/llama/modeling_llama.py:355-507), run per
     sequence (causal attention never crosses samples, so this equals the padded+masked batch).
     embeds [B, Lmax, H] right-padded; returns per-sample logits [L_b, V]."""
-    nh, nkv, hd, H = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim, cfg.hidden_size
     out = []
-    inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
     for b, L in enumerate(lengths):
-        x = embeds[b, :L]
-        ang = torch.arange(L, dtype=torch.float32)[:, None] * inv[None]
-        cos, sin = torch.cat([ang, ang], -1).cos()[None], torch.cat([ang, ang], -1).sin()[None]
-        rot = lambda t: torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)  # noqa: E731
-        causal = torch.ones(L, L, dtype=torch.bool).tril()
-        for l in range(cfg.num_hidden_layers):
-            p = f"model.layers.{l}."
-            h = rms_norm(x, sd[p + "input_layernorm.weight"], cfg.rms_norm_eps)
-            q = (h @ sd[p + "self_attn.q_proj.weight"].t()).view(L, nh, hd).transpose(0, 1)
-            k = (h @ sd[p + "self_attn.k_proj.weight"].t()).view(L, nkv, hd).transpose(0, 1)
-            v = (h @ sd[p + "self_attn.v_proj.weight"].t()).view(L, nkv, hd).transpose(0, 1)
-            q, k = q * cos + rot(q) * sin, k * cos + rot(k) * sin
-            k, v = k.repeat_interleave(nh // nkv, 0), v.repeat_interleave(nh // nkv, 0)
-            s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
-            a = torch.softmax(s.masked_fill(~causal, float("-inf")), -1) @ v
-            x = x + a.transpose(0, 1).reshape(L, nh * hd) @ sd[p + "self_attn.o_proj.weight"].t()
-            h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
-            g = F.silu(h @ sd[p + "mlp.gate_proj.weight"].t()) * (h @ sd[p + "mlp.up_proj.weight"].t())
-            x = x + g @ sd[p + "mlp.down_proj.weight"].t()
+        x = llama_hidden(sd, cfg, embeds[b, :L])
         x = rms_norm(x, sd["model.norm.weight"], cfg.rms_norm_eps)
         out.append(x @ sd["lm_head.weight"].t())
     return out

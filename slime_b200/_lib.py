@@ -141,13 +141,13 @@ SIGNATURES = {
     "slime_op_qkv_rope": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "slime_gemm_set_2cta_mode": (_i, [_i]),
     "slime_gemm_set_epi_mode": (_i, [_i]),
-    "slime_gemm_set_tail_split": (_i, [_i]),
     "slime_gemm_set_skinny_mode": (_i, [_i]),
     "slime_decode_attention_set_mode": (_i, [_i]),
     "slime_set_pdl_mode": (_i, [_i]),
     "slime_set_decode_prefetch": (_i, [_i]),
     "slime_attention_set_trace": (_i, [_vp]),
     "slime_attention_set_variant": (_i, [_i]),
+    "slime_attention_set_poly": (_i, [_i]),
     "slime_launch_count": (C.c_longlong, []),
     "slime_profile_enable": (_i, [_i]),
     "slime_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

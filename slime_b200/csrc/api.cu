@@ -1,6 +1,6 @@
 // C-ABI of libslime_b200 (include/slime_b200.h): context, weight registry, and the per-stage
 // orchestration of the SliME prefill path.  Every stage is a fixed sequence of launches of the
-// kernels in gemm_sm100.cu / attention_fa.cu / elementwise.cu / router.cu / splice.cu on the
+// kernels in gemm_sm100.cu / attention_tc2.cu / elementwise.cu / router.cu / splice.cu on the
 // caller's stream; scratch comes from the caller's workspace through a bump arena whose dry-run
 // twin implements the *_workspace_bytes() queries, so the two can never disagree.
 #include <cmath>
@@ -78,8 +78,6 @@ struct slime_ctx {
   std::unordered_map<std::string, Tensor> w;
   float* rope_table = nullptr;  // [max_pos, head_dim/2] (cos, sin) fp32, owned
   int* err_flag = nullptr;      // device int, owned
-  float* tail_ws = nullptr;     // owned, only with SLIME_GEMM_TAIL_SPLIT=1: partial tiles of the tail-split GEMM
-  int* tail_counters = nullptr;  // owned, zeroed: its arrival counters
   bool finalized = false;
   bf16* kv_cache = nullptr;  // caller-owned [layers][2][kv_cache_batch][kv_cache_len][kv_heads*head_dim], or nullptr
   int kv_cache_batch = 0, kv_cache_len = 0;
@@ -165,11 +163,6 @@ int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, in
   p.out = out;
   p.out_f32 = out_f32;
   p.out_ld = out_ld;
-  if (p.splitk_ws == nullptr && c->tail_ws != nullptr) {  // opt-in tail-split GEMM: ctx-owned scratch + counters
-    p.splitk_ws = c->tail_ws;
-    p.splitk_ws_floats = slime_gemm_tail_ws_floats(c->num_sms);
-    p.tail_counters = c->tail_counters;
-  }
   return slime_launch_gemm(A, lda, W, ldw, p, epi, c->num_sms, s);
 }
 
@@ -675,16 +668,6 @@ int slime_ctx_create(slime_ctx** out, int device, const slime_model_desc* desc) 
     return SLIME_ECUDA;
   }
   cudaMemset(c->err_flag, 0, sizeof(int));
-  if (slime_gemm_tail_split_enabled()) {
-    const size_t ints = slime_gemm_tail_counter_ints(c->num_sms);
-    if (cudaMalloc(&c->tail_ws, slime_gemm_tail_ws_floats(c->num_sms) * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&c->tail_counters, ints * sizeof(int)) != cudaSuccess) {
-      slime_set_error("ctx_create: cudaMalloc of the tail-split scratch failed");
-      delete c;
-      return SLIME_ECUDA;
-    }
-    cudaMemset(c->tail_counters, 0, ints * sizeof(int));
-  }
   int rc = slime_launch_rope_table(c->rope_table, d.max_pos, d.head_dim, d.rope_theta, nullptr);
   if (rc != SLIME_OK) {
     delete c;
@@ -699,8 +682,6 @@ void slime_ctx_destroy(slime_ctx* ctx) {
   if (ctx == nullptr) return;
   if (ctx->rope_table) cudaFree(ctx->rope_table);
   if (ctx->err_flag) cudaFree(ctx->err_flag);
-  if (ctx->tail_ws) cudaFree(ctx->tail_ws);
-  if (ctx->tail_counters) cudaFree(ctx->tail_counters);
   delete ctx;
 }
 

@@ -1,11 +1,16 @@
-// Host-side interface of the fused attention kernels (attention_tc.cu, attention_fa.cu, decode_attn.cu).
+// Host-side interface of the fused attention kernels (attention_tc.cu, attention_tc2.cu, decode_attn.cu).
 #pragma once
 #include "common.cuh"
 
 // default implementation when neither AttnParams::impl nor SLIME_ATTN_IMPL selects one:
-// 1 = mma.sync kernel, 2 = tcgen05 kernel
+// 2 = tcgen05 kernel with one query tile per CTA (attention_tc.cu), 3 = two query tiles per CTA (attention_tc2.cu)
 #ifndef SLIME_ATTN_DEFAULT_IMPL
 #define SLIME_ATTN_DEFAULT_IMPL 2
+#endif
+// attention_tc2.cu: how many of every 8 score-column pairs are exponentiated by a polynomial on the FMA pipe
+// instead of MUFU.EX2 (0, 2, 3 or 4)
+#ifndef SLIME_ATTN_POLY_DEFAULT
+#define SLIME_ATTN_POLY_DEFAULT 2
 #endif
 
 // softmax arithmetic variant of the tcgen05 kernel (attention_tc.cu: 0 scalar MUFU, 1 + 2*P packed pairs with P of
@@ -33,13 +38,14 @@ struct AttnParams {
   int causal;    // 1: query i attends keys <= i + (seqlen_k - seqlen_q)
   long long total_q_rows = 0;  // rows of the q matrix (needed for the TMA map when cu_q != nullptr; 0 = derive)
   long long total_k_rows = 0;  // rows of the k / v matrices (same)
-  int impl = 0;                // 0 = default (tcgen05), 1 = mma.sync flash kernel, 2 = tcgen05
+  int impl = 0;                // 0 = default, 2 = one query tile per CTA, 3 = two query tiles per CTA
   long long* trace = nullptr;  // debug: CTA 0 writes clock64() stamps of its first 64 tiles here ([64][16])
 };
 
 int slime_launch_attention(const AttnParams& p, cudaStream_t stream);
-// tcgen05 / TMEM implementation (attention_tc.cu)
+// tcgen05 / TMEM implementations (attention_tc.cu, attention_tc2.cu)
 int slime_launch_attention_tc(const AttnParams& p, int num_sms, cudaStream_t stream);
+int slime_launch_attention_tc2(const AttnParams& p, int num_sms, cudaStream_t stream);
 
 // ---- decode step (decode_attn.cu) ----
 // q [batch, heads*head_dim] (row stride q_ld) against the cache k/v [batch, cache_len, kv_heads*head_dim];

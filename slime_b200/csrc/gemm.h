@@ -31,8 +31,6 @@ struct GemmParams {
   int epi_mode = 0;    // HBM access pattern of the epilogue (gemm_epilogue.cuh): 0 direct, 1 staged through shared
                        // memory (coalesced stores and residual loads); filled in by slime_launch_gemm
   // ---- decode-step problems (M <= 32 rows; gemm_skinny.cu) ----
-  int* tail_counters = nullptr;  // opt-in tail-split 2-CTA kernel (gemm2_tail_sm100.cu): zeroed arrival counters; its
-                                 // partial tiles use splitk_ws
   float* splitk_ws = nullptr;   // optional fp32 scratch for split-K partial sums [splits, M, N]
   size_t splitk_ws_floats = 0;  // its capacity; too small / absent: the problem runs unsplit
   int force_splits = 0;         // tests: > 0 forces the weight-streaming kernel with this many k-splits
@@ -67,14 +65,6 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
 // cta_group::2 variant (256 x 256 cluster tiles); arguments already validated by slime_launch_gemm.
 int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                            int num_sms, cudaStream_t stream);
-
-// Opt-in (SLIME_GEMM_TAIL_SPLIT=1), not yet validated: 2-CTA kernel whose last, nearly empty wave of tiles is split along K
-// over all clusters (gemm2_tail_sm100.cu).  *launched = 1 when it took the problem.
-bool slime_gemm_tail_split_enabled();
-size_t slime_gemm_tail_ws_floats(int num_sms);
-int slime_gemm_tail_counter_ints(int num_sms);
-int slime_launch_gemm_2cta_tail(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms,
-                                cudaStream_t stream, int* launched);
 
 // Weight-streaming kernel for M <= 32 rows (gemm_skinny.cu; the decode step).  slime_launch_gemm routes to it when
 // slime_gemm_skinny_applies(); SLIME_GEMM_SKINNY=0 / slime_gemm_set_skinny_mode(0) keep such problems on the tcgen05 path.

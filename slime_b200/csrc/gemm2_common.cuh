@@ -1,6 +1,6 @@
 // Shared pieces of the 2-CTA (cta_group::2) tcgen05 GEMM kernels: tile constants, the cluster / TMA / UMMA / TMEM
-// wrappers and the rasterisation.  Included INSIDE the anonymous namespace of gemm2_sm100.cu (the product kernel) and
-// gemm2_tail_sm100.cu (the opt-in tail-split variant); needs gemm.h and common.cuh before it.
+// wrappers and the rasterisation.  Included INSIDE the anonymous namespace of gemm2_sm100.cu; needs gemm.h and
+// common.cuh before it.
 #pragma once
 
 constexpr int BLOCK_M = 128;      // rows per CTA (256 per cluster tile)

@@ -178,11 +178,6 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, i
 
 int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms,
                            cudaStream_t stream) {
-  if (slime_gemm_tail_split_enabled()) {  // opt-in: rebalance a nearly empty last wave (gemm2_tail_sm100.cu)
-    int launched = 0;
-    SLIME_PROPAGATE(slime_launch_gemm_2cta_tail(A, lda, W, ldw, p, epi, num_sms, stream, &launched));
-    if (launched) return SLIME_OK;
-  }
   CUtensorMap ta, tb;
   SLIME_PROPAGATE(slime_get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
   SLIME_PROPAGATE(slime_get_tmap(W, p.N, p.K, ldw, BLOCK_N / 2, &tb));

@@ -120,13 +120,27 @@ class SlimeEngine:
         """groups: which weight groups to register ("vit", "rs_local", "rs_global", "proj", "llm"); a stage
         whose group is absent fails loudly (used by the stand-alone module shims of slime_b200/model)."""
         with self._lock, torch.cuda.device(self.device):
-            self.weights = pack_weights(self.cfg, get, self.device, groups, self.dtype, rope_interleaved=self.fused_rope)
+            self._register(pack_weights(self.cfg, get, self.device, groups, self.dtype, rope_interleaved=self.fused_rope))
+
+    def _register(self, weights: Dict[str, torch.Tensor]) -> None:
+        """Hand the packed tensors to the library (borrowed pointers: self.weights keeps them alive) and let it
+        derive the input-independent Resampler tensors."""
+        with self._lock, torch.cuda.device(self.device):
+            self.weights = weights
             for name, t in self.weights.items():
                 self._check(self.lib.slime_ctx_set_weight(self._ctx, name.encode(), L.ptr(t), t.shape[0], t.shape[1]),
-                        f"set_weight({name})")
+                            f"set_weight({name})")
             ws = self._workspace(self.lib.slime_finalize_workspace_bytes(self._ctx))
             self._check(self.lib.slime_ctx_finalize_weights(self._ctx, L.ptr(ws), ws.numel(), L.stream_ptr()), "finalize")
             torch.cuda.current_stream().synchronize()
+
+    def clone(self, **cfg_overrides) -> "SlimeEngine":
+        """A second context over the SAME packed weights (no copy) with some configuration attributes changed -
+        top-p, merge type, padding side, ... (everything that lives in slime_model_desc rather than in the weights)."""
+        other = SlimeEngine(self.cfg.replace(**cfg_overrides), self.device, max_pos=self._desc.max_pos, dtype=self.dtype,
+                            fused_rope=self.fused_rope)
+        other._register(self.weights)
+        return other
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:

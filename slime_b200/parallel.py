@@ -50,3 +50,52 @@ def gather_logits(local_logits: torch.Tensor, n_samples: int, group=None) -> tor
     if all(s == width for s in sizes):
         return out
     return torch.cat([out[r * width: r * width + sizes[r]] for r in range(world)])
+
+
+class LogitsGather:
+    """The path's one exchange step, taken OFF the compute stream: the all-gather of the [B_local, V] last-token logits
+    is issued on a side stream behind an event, so a rank's next prefill never waits for the slowest rank's previous
+    one (on the compute stream the collective acts as a per-step barrier: every step then runs at the pace of the most
+    power-throttled GPU).  `depth` result buffers rotate; result(slot) makes the calling stream wait for that gather.
+    Equal block sizes on every rank (the benchmark's weak-scaling layout); gather_logits() handles ragged blocks.
+    On CPU tensors (gloo tests) the gather simply runs synchronously."""
+
+    def __init__(self, rows: int, vocab: int, device, dtype=torch.float32, group=None, depth: int = 2):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cuda = torch.device(device).type == "cuda"
+        self.bufs = [torch.empty(self.world * rows, vocab, dtype=dtype, device=device) for _ in range(depth)]
+        self.done = [None] * depth
+        self.count = 0
+        self.stream = torch.cuda.Stream(device) if self.cuda else None
+
+    def submit(self, local_logits: torch.Tensor) -> int:
+        slot = self.count % len(self.bufs)
+        self.count += 1
+        if self.world == 1:
+            self.bufs[slot].copy_(local_logits)
+            return slot
+        if not self.cuda:
+            dist.all_gather_into_tensor(self.bufs[slot], local_logits.contiguous(), group=self.group)
+            return slot
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        self.stream.wait_event(ready)
+        local_logits.record_stream(self.stream)  # allocated on the compute stream, consumed on the side stream
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self.bufs[slot], local_logits, group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.done[slot] = ev
+        return slot
+
+    def result(self, slot: int) -> torch.Tensor:
+        """The gathered [world * rows, V] logits of submission `slot`; the current stream waits for that gather."""
+        if self.cuda and self.done[slot] is not None:
+            torch.cuda.current_stream().wait_event(self.done[slot])
+        return self.bufs[slot]
+
+    def drain(self) -> None:
+        """Make the current stream wait for every gather issued so far (end of a timed region)."""
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.stream)

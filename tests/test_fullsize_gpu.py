@@ -61,89 +61,184 @@ class LazyFp32Dict(dict):
         return self._get(k).float()
 
 
-# tolerances (rel-L2 vs the fp32 oracle): bf16 keeps 8 significand bits per rounding, fp16 11 -> 8x tighter.
-# north_star asks for 1e-3 "bf16/fp16 tolerance": the fp16 build is what gets the 32-layer logits to that order;
-# in bf16 the reference's own bf16 execution is ~1e-2 away from fp32 as well (tolerances).
-TOL = {torch.bfloat16: dict(stage=2e-2, logits=5e-2), torch.float16: dict(stage=2.5e-3, logits=3e-3)}
+class LazyCastDict(dict):
+    """The same weights cast to a 16-bit dtype on demand: the oracle run "in bf16" is the reference's own low-precision
+    execution (plain torch ops on 16-bit tensors: cuBLAS GEMMs with fp32 accumulation, every intermediate rounded)."""
+
+    def __init__(self, get, dtype):
+        super().__init__()
+        self._get, self._dtype = get, dtype
+
+    def __missing__(self, k):
+        return self._get(k).to(self._dtype)
+
+
+# Bounds (rel-L2 vs the fp32 oracle on the GPU).  north_star asks for "1e-3 relative bf16/fp16 tolerance"; one bf16
+# rounding alone is 1.7e-3, so the bf16 path is judged against the FLOOR instead: the oracle itself executed in bf16
+# (test_fullsize_floor_*: ours <= 1.2 x that, per stage and on the logits), and the absolute bounds below are the
+# values measured on B200 (profiles/r02_fullsize_parity.txt) x 1.3, so a regression of a third already fails.  The fp16
+# build (the reference's inference dtype, llava/model/builder.py:43) is the one that reaches the 1e-3 order.
+MEASURED = {  # dtype -> stage -> measured rel-L2 (32 layers, real dimensions)
+    torch.bfloat16: dict(vit=9.5e-3, glob=1.40e-2, local=4.3e-3, probs=6e-3, logits=1.37e-2),
+    torch.float16: dict(vit=1.2e-3, glob=1.55e-3, local=5.0e-4, probs=8e-4, logits=1.75e-3),
+}
+TOL = {dt: {k: 1.3 * v for k, v in m.items()} for dt, m in MEASURED.items()}
+
+
+def _run_case(name, T, dtype, B, n, layers=None, flat=False, floor=False, seed=11):
+    """One batch at real dimensions through the CUDA path and through the fp32 oracle on the GPU (teacher-forced
+    selection); returns the per-stage errors (and, with floor=True, the errors of the oracle executed in `dtype`)."""
+    from oracle import slime_oracle as O
+    from slime_b200.synth import grid_for_crops, synth_inputs
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg, eng, get, specs = build(name, layers, dtype=dtype)
+    if flat:
+        cfg = cfg.replace(mm_patch_merge_type="flat")
+        eng.cfg.mm_patch_merge_type = "flat"
+    try:
+        px, ids, mask = synth_inputs(cfg, B, n, T, seed=seed, ragged=True)
+        px, ids, mask = px.cuda(), ids.cuda(), mask.cuda()
+        sd = LazyFp32Dict(get)
+        grids = None if flat else [grid_for_crops(n - 1)] * B
+        out = {}
+        with torch.no_grad():
+            enc = O.encode_images(sd, cfg, px, ids, mask, grids)           # fp32 oracle, on the GPU
+            res = eng.prefill(px, ids, mask, grids=grids, forced_selection=enc["sel"], keep_stages=True)
+            out["vit"] = rel(res.stages["vit"], torch.cat(enc["vit"]))
+            out["glob"] = rel(res.stages["glob"], torch.stack(enc["glob"]))
+            out["local"] = rel(res.stages["local_m"], torch.stack(enc["local_m"]))
+            # router probabilities on the CUDA path's own features, then the exact selection rule on them
+            r2 = eng.prefill(px, ids, mask, grids=grids, want_probs=True, want_last=False, run_decoder=False)
+            out["probs"] = max(rel(r2.probs[b], enc["probs"][b]) for b in range(B))
+            for b in range(B):
+                expect = O.top_p_select(r2.probs[b].cpu(), cfg.mm_resampler_topp)
+                k = int(r2.sel_count[b])
+                assert r2.sel_idx[b, :k].cpu().tolist() == expect.tolist()
+            # splice (exact lengths) + decoder against the oracle
+            emb, am, pid, lab, lens = O.splice(sd["model.embed_tokens.weight"].cpu(), ids.cpu(), mask.cpu(), None,
+                                               [f.cpu() for f in enc["feats"]])
+            assert res.lengths == lens
+            last = torch.stack([O.llama_last_logits(sd, cfg, emb[b, :L].cuda()) for b, L in enumerate(lens)])
+            out["logits"] = rel(res.logits_last, last)
+            if floor:
+                # the oracle executed in the 16-bit dtype (same inputs, same teacher-forced selection)
+                sd16 = LazyCastDict(get, dtype)
+                enc16 = O.encode_images(sd16, cfg, px.to(dtype), ids, mask, grids, forced_selection=enc["sel"])
+                fl = dict(vit=rel(torch.cat(enc16["vit"]), torch.cat(enc["vit"])),
+                          glob=rel(torch.stack(enc16["glob"]), torch.stack(enc["glob"])),
+                          local=rel(torch.stack(enc16["local_m"]), torch.stack(enc["local_m"])),
+                          probs=max(rel(enc16["probs"][b], enc["probs"][b]) for b in range(B)))
+                emb16 = O.splice(sd16["model.embed_tokens.weight"], ids, mask, None, enc16["feats"])[0]
+                last16 = torch.stack([O.llama_last_logits(sd16, cfg, emb16[b, :L]) for b, L in enumerate(lens)])
+                fl["logits"] = rel(last16, last)
+                out["floor"] = fl
+        return out
+    finally:
+        eng.cfg.mm_patch_merge_type = "spatial"
+
+
+def _report(tag, out):
+    line = "  ".join(f"{k} {v:.3e}" for k, v in out.items() if k != "floor")
+    print(f"[{tag}] rel-L2 vs fp32 oracle: {line}")
+    if "floor" in out:
+        print(f"[{tag}] oracle executed in 16 bit : " + "  ".join(f"{k} {v:.3e}" for k, v in out["floor"].items()))
 
 
 @pytest.mark.parametrize("name,T,dtype", [("vicuna-7b", 128, torch.bfloat16), ("llama3-8b", 256, torch.bfloat16),
                                           ("llama3-8b", 256, torch.float16)],
                          ids=["vicuna-7b-bf16", "llama3-8b-bf16", "llama3-8b-fp16"])
-def test_fullsize_against_fp32_oracle_on_gpu(name, T, dtype):
+def test_fullsize_against_fp32_oracle_and_floor(name, T, dtype):
+    """Config 2 (Vicuna-7B, T 128) and the headline (Llama3-8B, T 256): 5 crops, 2x2 spatial grid, all 32 layers.
+    (1) absolute bounds = measured x 1.3;  (2) FLOOR: the CUDA path may not be further from fp32 than 1.2 x the
+    oracle itself executed in the same 16-bit dtype (= the reference's own bf16 / fp16 run on this input)."""
+    out = _run_case(name, T, dtype, B=2, n=5, floor=True)
+    _report(f"{name} {dtype} 5 crops", out)
+    tol = TOL[dtype]
+    for k in ("vit", "glob", "local", "probs", "logits"):
+        assert out[k] < tol[k], f"{k}: {out[k]:.3e} above measured x 1.3 = {tol[k]:.3e}"
+        # 1.2 x the floor, with a small absolute allowance where the floor itself is at the 1e-4 level
+        assert out[k] <= 1.2 * out["floor"][k] + 2e-4, f"{k}: {out[k]:.3e} vs 16-bit oracle floor {out['floor'][k]:.3e}"
+
+
+@pytest.mark.parametrize("name,n,T,B,layers", [
+    ("llama3-8b", 10, 256, 8, 4),    # config 3: 1008 px = 10 crops, batch 8 ('flat' merge: 3x3 is not a reference grid)
+    ("llama3-8b", 8, 256, 4, 4),     # config 4: 8 frames = 8 crops (crop 0 global + 7 local, flat), 4 samples per GPU
+    ("vicuna-13b", 17, 512, 2, 4),   # config 5: Vicuna-13B dimensions (H 5120, 40 heads), 17 crops, T = 512
+], ids=["config3-10crops", "config4-8crops", "config5-13b-17crops"])
+def test_baseline_config_shapes_against_fp32_oracle(name, n, T, B, layers):
+    """BASELINE.json configs 3 / 4 / 5 at their crop counts, prompt lengths and model dimensions (decoder sliced to
+    4 layers so the fp32 oracle stays in seconds): every stage and the last-token logits against the fp32 oracle
+    (reference llava_arch.py:233-234 flat merge; eval/video/llava_arch.py:240 for the 8-crop shape)."""
+    out = _run_case(name, T, torch.bfloat16, B=B, n=n, layers=layers, flat=True, floor=True, seed=7)
+    _report(f"{name} {n} crops T={T} B={B} ({layers} layers)", out)
+    tol = TOL[torch.bfloat16]
+    for k in ("vit", "glob", "local", "probs"):
+        assert out[k] < tol[k], f"{k}: {out[k]:.3e} above {tol[k]:.3e}"
+        assert out[k] <= 1.2 * out["floor"][k] + 2e-4, f"{k}: {out[k]:.3e} vs floor {out['floor'][k]:.3e}"
+    # 4 decoder layers accumulate less rounding than 32: bound by the 32-layer figure and by the floor
+    assert out["logits"] < tol["logits"]
+    assert out["logits"] <= 1.2 * out["floor"]["logits"] + 2e-4
+
+
+@pytest.mark.parametrize("B", [1, 16])
+def test_fullsize_decode_parity(B):
+    """Decode step at SliME-Llama3-8B dimensions (32 layers, GQA 32/8, V = 128256, ~1380-token context): every step's
+    logits against (a) a fresh packed prefill of the grown sequence on the CUDA path and (b) the fp32 oracle's
+    last-token logits for the grown sequence (reference llava_llama.py:139 -> HF generation loop)."""
+    import numpy as np
+
     from oracle import slime_oracle as O
     from slime_b200.synth import synth_inputs
 
     torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
-    cfg, eng, get, specs = build(name, dtype=dtype)
-    tol = TOL[dtype]
-    B, n = 2, 5
-    px, ids, mask = synth_inputs(cfg, B, n, T, seed=11, ragged=True)
-    px, ids, mask = px.cuda(), ids.cuda(), mask.cuda()
+    cfg, eng, get, specs = build("llama3-8b")
     sd = LazyFp32Dict(get)
+    px, ids, mask = synth_inputs(cfg, B, 5, 256, seed=21, ragged=True)
     grids = [(2, 2)] * B
-    with torch.no_grad():
-        enc = O.encode_images(sd, cfg, px, ids, mask, grids)           # fp32 oracle, on the GPU
-        res = eng.prefill(px, ids, mask, grids=grids, forced_selection=enc["sel"], keep_stages=True)
-        e_vit = rel(res.stages["vit"], torch.cat(enc["vit"]))
-        e_glob = rel(res.stages["glob"], torch.stack(enc["glob"]))
-        e_loc = rel(res.stages["local_m"], torch.stack(enc["local_m"]))
-        print(f"[{name} {dtype}] full-size rel-L2: vit {e_vit:.3e}  gated-global {e_glob:.3e}  local {e_loc:.3e}")
-        assert e_vit < tol["stage"] and e_glob < tol["stage"] and e_loc < tol["stage"]
-        # router probabilities on the CUDA path's own features, then the exact selection rule on them
-        r2 = eng.prefill(px, ids, mask, grids=grids, want_probs=True, want_last=False, run_decoder=False)
-        for b in range(B):
-            e_p = rel(r2.probs[b], enc["probs"][b])
-            assert e_p < tol["stage"], e_p
-            expect = O.top_p_select(r2.probs[b].cpu(), cfg.mm_resampler_topp)
-            k = int(r2.sel_count[b])
-            assert r2.sel_idx[b, :k].cpu().tolist() == expect.tolist()
-        # splice + decoder (32 layers) against the oracle
-        emb, am, pid, lab, lens = O.splice(sd["model.embed_tokens.weight"].cpu(), ids.cpu(), mask.cpu(), None,
-                                           [f.cpu() for f in enc["feats"]])
-        assert res.lengths == lens
-        # run the oracle decoder per sample on the GPU (fp32) and keep only the last row
-        last = []
-        for b, L in enumerate(lens):
-            lg = _oracle_last_logits(O, sd, cfg, emb[b, :L].cuda())
-            last.append(lg)
-        e_log = rel(res.logits_last, torch.stack(last))
-        print(f"[{name} {dtype}] full-size last-token logits rel-L2 vs fp32 oracle: {e_log:.3e}")
-        assert e_log < tol["logits"]
-
-
-def _oracle_last_logits(O, sd, cfg, x):
-    """oracle.llama_prefill for one sequence, last-token logits only (the all-position lm_head would be
-    L x 128256 fp32); identical arithmetic."""
-    import math
-
-    import torch.nn.functional as F
-
-    nh, nkv, hd = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
-    L = x.shape[0]
-    dev = x.device
-    inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32, device=dev) / hd))
-    ang = torch.arange(L, dtype=torch.float32, device=dev)[:, None] * inv[None]
-    cos, sin = torch.cat([ang, ang], -1).cos()[None], torch.cat([ang, ang], -1).sin()[None]
-    rot = lambda t: torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)  # noqa: E731
-    causal = torch.ones(L, L, dtype=torch.bool, device=dev).tril()
-    for l in range(cfg.num_hidden_layers):
-        p = f"model.layers.{l}."
-        h = O.rms_norm(x, sd[p + "input_layernorm.weight"], cfg.rms_norm_eps)
-        q = (h @ sd[p + "self_attn.q_proj.weight"].t()).view(L, nh, hd).transpose(0, 1)
-        k = (h @ sd[p + "self_attn.k_proj.weight"].t()).view(L, nkv, hd).transpose(0, 1)
-        v = (h @ sd[p + "self_attn.v_proj.weight"].t()).view(L, nkv, hd).transpose(0, 1)
-        q, k = q * cos + rot(q) * sin, k * cos + rot(k) * sin
-        k, v = k.repeat_interleave(nh // nkv, 0), v.repeat_interleave(nh // nkv, 0)
-        s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
-        a = torch.softmax(s.masked_fill(~causal, float("-inf")), -1) @ v
-        x = x + a.transpose(0, 1).reshape(L, nh * hd) @ sd[p + "self_attn.o_proj.weight"].t()
-        h = O.rms_norm(x, sd[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps)
-        g = F.silu(h @ sd[p + "mlp.gate_proj.weight"].t()) * (h @ sd[p + "mlp.up_proj.weight"].t())
-        x = x + g @ sd[p + "mlp.down_proj.weight"].t()
-    x = O.rms_norm(x[-1:], sd["model.norm.weight"], cfg.rms_norm_eps)
-    return (x @ sd["lm_head.weight"].t())[0]
+    steps = 3
+    base = eng.prefill(px, ids, mask, grids=grids, keep_stages=True)
+    cu = base.cu_seqlens.cpu().tolist()
+    seqs = [base.embeds[cu[b]:cu[b + 1]].clone() for b in range(B)]
+    table = eng.weights["llm.embed"]
+    forced = [base.sel_idx[b, :int(base.sel_count[b])] for b in range(B)]
+    eng.attach_kv_cache(B, max(base.lengths) + steps + 2)
+    try:
+        res = eng.prefill(px, ids, mask, grids=grids, forced_selection=forced)
+        assert torch.equal(res.logits_last, base.logits_last)
+        lens_d = torch.tensor(res.lengths, dtype=torch.int32, device="cuda")
+        logits = res.logits_last
+        worst_re, worst_or = 0.0, 0.0
+        for s in range(steps):
+            nxt = logits.argmax(-1)
+            seqs = [torch.cat([seqs[b], table[nxt[b]][None]]) for b in range(B)]
+            logits = eng.decode_step(table[nxt], lens_d)
+            lens_d = lens_d + 1
+            # (a) re-prefill of the grown sequences (cache detached for this call: it must not be overwritten)
+            lens = [x.shape[0] for x in seqs]
+            rows = torch.cat(seqs).contiguous()
+            cu_t = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device="cuda")
+            pos = torch.cat([torch.arange(L) for L in lens]).to(device="cuda", dtype=torch.int32)
+            cache = eng._kv_cache
+            eng.detach_kv_cache()
+            ref, _, _ = eng.decoder_prefill(rows, cu_t, pos, lens)
+            eng._check(eng.lib.slime_decoder_set_kv_cache(eng._ctx, cache.data_ptr(), B, cache.shape[3]), "set_kv_cache")
+            eng._kv_cache = cache
+            worst_re = max(worst_re, rel(logits, ref))
+            # (b) fp32 oracle on the grown sequence of the first and the last sample
+            with torch.no_grad():
+                for b in sorted({0, B - 1}):
+                    lg = O.llama_last_logits(sd, cfg, seqs[b].float())
+                    worst_or = max(worst_or, rel(logits[b], lg))
+        print(f"[llama3-8b decode B={B}] {steps} steps: rel-L2 vs re-prefill {worst_re:.3e}, vs fp32 oracle {worst_or:.3e}")
+        # two bf16 executions with different rounding points (the decode kernels keep the residual + RMSNorm in fp32, the
+        # prefill rounds the stream to bf16 in between) sit ~1.4e-2 from fp32 each and ~1.5e-2 from each other after 32
+        # layers (measured 1.54e-2; bound = x 1.3); against fp32 the decode step obeys the same bound as the prefill
+        assert worst_re < 2.0e-2, worst_re
+        assert worst_or < TOL[torch.bfloat16]["logits"], worst_or
+    finally:
+        eng.detach_kv_cache()
 
 
 @pytest.mark.parametrize("name,n_crops,T,layers", [

@@ -178,7 +178,7 @@ def ref_attention(q, k, v, scale, causal):
     return torch.softmax(s, dim=-1) @ v
 
 
-IMPLS = [pytest.param(2, id="tcgen05"), pytest.param(1, id="mma_sync")]
+IMPLS = [pytest.param(3, id="two_q_tiles"), pytest.param(2, id="one_q_tile")]
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -216,10 +216,13 @@ def test_attention_resampler_shape(nq, impl):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
-def test_attention_decoder_causal_varlen_gqa(impl):
-    """Packed variable-length causal attention with GQA 32/8 heads x 128 (Llama-3 layout)."""
+@pytest.mark.parametrize("h,kvh", [(8, 2), (4, 4), (6, 2)], ids=["gqa4", "mha", "gqa3"])
+def test_attention_decoder_causal_varlen_gqa(impl, h, kvh):
+    """Packed variable-length causal attention, heads x 128: GQA group 4 (Llama-3 layout: the two-tile kernel pairs q
+    heads of a group), MHA (Vicuna: it pairs consecutive query tiles, the earlier one sees its last kv tile fully
+    masked) and an odd group size."""
     torch.manual_seed(8)
-    h, kvh, d = 8, 2, 128
+    d = 128
     lens = [1, 63, 64, 65, 127, 128, 129, 200, 333, 1400]
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), device="cuda", dtype=torch.int32)
     total = sum(lens)

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from slime_b200.parallel import balanced_order, gather_logits, shard_bounds
+from slime_b200.parallel import LogitsGather, balanced_order, gather_logits, shard_bounds
 
 
 def test_shard_bounds_cover_batch():
@@ -40,7 +40,14 @@ def _worker(rank, world, port, n_samples, vocab, q):
     full = torch.arange(n_samples * vocab, dtype=torch.float32).view(n_samples, vocab)
     lo, hi = shard_bounds(n_samples, rank, world)
     got = gather_logits(full[lo:hi].clone(), n_samples)
-    q.put((rank, torch.equal(got, full)))
+    ok = torch.equal(got, full)
+    if n_samples % world == 0:  # the side-stream gatherer of the benchmark (equal blocks), rotating result buffers
+        lg = LogitsGather(n_samples // world, vocab, "cpu")
+        for step in range(3):
+            slot = lg.submit(full[lo:hi] + step)
+            ok = ok and torch.equal(lg.result(slot), full + step)
+        lg.drain()
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
