@@ -36,8 +36,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int SLAB_BYTES = 128 * 128;  // 128 rows x 64 elements
-constexpr int NT = 14 * 32;            // TMA warp + MMA warp + 2 x 4 softmax warps + 4 epilogue warps
-constexpr int MAX_REGS = 144;          // 448 threads x 144 = 64512 registers (ptxas would settle for 128 on its own)
+constexpr int NT = 14 * 32;  // TMA warp + MMA warp + 2 x 4 softmax warps + 4 epilogue warps.  The register file is handed
+                             // out per warpGROUP, so 14 warps count as 16: 128 registers per thread (the softmax walks
+                             // its 128 score columns in 32-column chunks to stay inside that without spilling)
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P stays below 2^8
 
 template <int HD>
@@ -137,35 +138,34 @@ SLIME_DEVINL void st_release_cta(int* p, int v) {
   asm volatile("st.release.cta.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
-// max over 64 score columns held in registers; with `need_mask` columns beyond `limit` are set to -inf first
-SLIME_DEVINL float rowmax64(const uint32_t (&sr)[64], bool need_mask, int col_base, int limit) {
+// max over 32 score columns held in registers; with `need_mask` columns beyond `limit` count as -inf
+SLIME_DEVINL float rowmax32(const uint32_t (&sr)[32], bool need_mask, int col_base, int limit) {
+  float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains
   if (need_mask) {
-    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
+    for (int c = 0; c < 32; ++c) {
       float v = __uint_as_float(sr[c]);
       if (col_base + c > limit) v = -INFINITY;
       mx4[c & 3] = fmaxf(mx4[c & 3], v);
     }
-    return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-  }
-  float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains, FMNMX3: two values per instruction
+  } else {
 #pragma unroll
-  for (int c = 0; c < 64; c += 2)
-    mx4[(c >> 1) & 3] = fmax3(mx4[(c >> 1) & 3], __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+    for (int c = 0; c < 32; c += 2)  // FMNMX3: two values per instruction
+      mx4[(c >> 1) & 3] = fmax3(mx4[(c >> 1) & 3], __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+  }
   return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 }
 
-// P = 2^(s * scale_log2 - m_scaled) for 64 columns -> 32 packed 16-bit pairs; returns the fp32 row sum of the 64 values.
+// P = 2^(s * scale_log2 - m_scaled) for 32 columns -> 16 packed 16-bit pairs; returns the fp32 row sum of the 32 values.
 // `plain` = the tile needs no masking (no -inf inputs), so the packed / polynomial arithmetic of variant P may be used.
 template <int P>
-SLIME_DEVINL float softmax_exp64(const uint32_t (&sr)[64], bool plain, int col_base, int limit, float scale_log2,
-                                 float m_scaled, uint32_t (&pk)[32]) {
+SLIME_DEVINL float softmax_exp32(const uint32_t (&sr)[32], bool plain, int col_base, int limit, float scale_log2,
+                                 float m_scaled, uint32_t (&pk)[16]) {
   if (plain) {
     const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_scaled, -m_scaled);
     float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < 16; ++c) {
       const float2 x = ffma2(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), sc2, nm2);
       float2 pv;
       if (pair_is_poly(c, P)) {
@@ -181,7 +181,7 @@ SLIME_DEVINL float softmax_exp64(const uint32_t (&sr)[64], bool plain, int col_b
   }
   float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
+  for (int c = 0; c < 16; ++c) {
     float s0 = __uint_as_float(sr[2 * c]), s1 = __uint_as_float(sr[2 * c + 1]);
     if (col_base + 2 * c > limit) s0 = -INFINITY;
     if (col_base + 2 * c + 1 > limit) s1 = -INFINITY;
@@ -274,7 +274,7 @@ SLIME_DEVINL Item2 decode_item2(const AttnParams& p, int w, int units, int hsel_
 }
 
 template <int HD, bool CAUSAL, int PV>
-__global__ void __maxnreg__(MAX_REGS)
+__global__ void __launch_bounds__(NT, 1)
 attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const AttnParams p, int units, int hsel_count, int pair_heads,
               int total_items, int per_cta) {
@@ -558,18 +558,18 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           tcgen05_fence_after();
           if (tr) p.trace[gx * 16 + 1] = clock64();
           const bool need_mask = (j * BN + BN > len_k) || (CAUSAL && (j * BN + BN - 1 > it_t * BM + causal_off));
-          // ---- pass 1: row max over the 128 columns
-          float m_tile;
+          // ---- pass 1: row max over the 128 columns, 32 at a time; the load of chunk c+1 is in flight while chunk c
+          //      is reduced
+          float m_tile = -INFINITY;
           {
-            uint32_t sr[64];
-            tmem_ld_32x32b_x32(s_base, sr);
-            tmem_ld_32x32b_x32(s_base + 32, sr + 32);
-            tmem_ld_wait();
-            m_tile = rowmax64(sr, need_mask, j * BN, limit);
-            tmem_ld_32x32b_x32(s_base + 64, sr);
-            tmem_ld_32x32b_x32(s_base + 96, sr + 32);
-            tmem_ld_wait();
-            m_tile = fmaxf(m_tile, rowmax64(sr, need_mask, j * BN + 64, limit));
+            uint32_t sr[2][32];
+            tmem_ld_32x32b_x32(s_base, sr[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld_wait();
+              if (c + 1 < 4) tmem_ld_32x32b_x32(s_base + (c + 1) * 32, sr[(c + 1) & 1]);
+              m_tile = fmaxf(m_tile, rowmax32(sr[c & 1], need_mask, j * BN + c * 32, limit));
+            }
           }
           if (tr) p.trace[gx * 16 + 2] = clock64();
           // ---- lazy rescale: only move the reference max when it grew by more than 2^8 (always on the first tile)
@@ -593,16 +593,19 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           }
           if (grow) m_cur = m_tile;
           const float m_scaled = (m_cur == -INFINITY) ? 0.f : m_cur * scale_log2;
-          // ---- pass 2: exponentials, 64 columns at a time; P (16-bit pairs) overwrites the S columns just consumed
+          // ---- pass 2: exponentials, 32 columns at a time (next chunk's load in flight); P (16-bit pairs) overwrites
+          //      S columns that have already been consumed: chunk c -> columns [16 c, 16 c + 16)
+          {
+            uint32_t sr[2][32];
+            tmem_ld_32x32b_x32(s_base, sr[0]);
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t sr[64];
-            tmem_ld_32x32b_x32(s_base + hh * 64, sr);
-            tmem_ld_32x32b_x32(s_base + hh * 64 + 32, sr + 32);
-            tmem_ld_wait();
-            uint32_t pk[32];
-            l_sum += softmax_exp64<PV>(sr, !need_mask, j * BN + hh * 64, limit, scale_log2, m_scaled, pk);
-            tmem_st_32x32b_x32(s_base + hh * 32, pk);
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld_wait();
+              if (c + 1 < 4) tmem_ld_32x32b_x32(s_base + (c + 1) * 32, sr[(c + 1) & 1]);
+              uint32_t pk[16];
+              l_sum += softmax_exp32<PV>(sr[c & 1], !need_mask, j * BN + c * 32, limit, scale_log2, m_scaled, pk);
+              tmem_st_32x32b_x16(s_base + c * 16, pk);
+            }
           }
           if (tr) p.trace[gx * 16 + 3] = clock64();
           tmem_st_wait();

@@ -83,6 +83,7 @@ class CLIPVisionTower(nn.Module):
         self._args = args
         self.cfg_only = load_clip_config(vision_tower)
         self.image_processor = None
+        self.weights_source = None  # where the tower's weights came from (set by load_model / the checkpoint loader)
         if not delay_load or getattr(args, "unfreeze_mm_vision_tower", False):
             self.load_model()
 
@@ -101,9 +102,29 @@ class CLIPVisionTower(nn.Module):
         self.vision_tower.requires_grad_(False)
         self.is_loaded = True
 
-    def _maybe_load_checkpoint(self):
+    def _resolve_dir(self):
+        """Local directory holding the tower's own files: `mm_vision_tower` itself, or - for a hub id such as
+        'openai/clip-vit-large-patch14-336' (every released SliME config) - its snapshot in the local HF cache
+        (no network: local_files_only).  None when neither exists."""
         d = self.vision_tower_name
-        if not os.path.isdir(d):
+        if os.path.isdir(d):
+            return d, "directory"
+        try:
+            from huggingface_hub import snapshot_download
+
+            return snapshot_download(d, local_files_only=True), "hf-cache"
+        except Exception:
+            return None, None
+
+    def _maybe_load_checkpoint(self):
+        """Loads the tower's own pretrained weights when they can be found and records where they came from in
+        `self.weights_source` ('directory' / 'hf-cache' / None).  None means the parameters are still
+        default-initialised: slime_b200.checkpoint.load_model then requires the model checkpoint to carry the
+        `model.vision_tower.*` tensors and raises otherwise (the reference always loads CLIP from this name after
+        from_pretrained, llava/model/builder.py:160-162)."""
+        self.weights_source = None
+        d, how = self._resolve_dir()
+        if d is None:
             return
         sd = None
         st = os.path.join(d, "model.safetensors")
@@ -120,6 +141,7 @@ class CLIPVisionTower(nn.Module):
         if sd is not None:
             sd = {k: v for k, v in sd.items() if k.startswith("vision_model.") and "position_ids" not in k}
             self.vision_tower.load_state_dict(sd, strict=True)
+            self.weights_source = how
 
     # ------------------------------------------------------------------ engine
     def _engine(self, device):

@@ -8,9 +8,9 @@ timeout 600 python tools/attn_bench.py --impls 2,3 --polys 0,2,3,4 --trace > gpu
 grep -E "^attn|Error|error" gpurun_out/r2_attn_bench.log | head -40
 echo "== whole GPU suite with the two-tile kernel as the default (minus full-size)"
 SLIME_ATTN_IMPL=3 timeout 1500 python -m pytest tests -q -m gpu -x --deselect tests/test_fullsize_gpu.py 2>&1 | tail -8 | tee gpurun_out/r2_suite_impl3.log
-echo "== fullsize parity (default impl)"
-timeout 1500 python -m pytest tests/test_fullsize_gpu.py -q -s -m gpu > gpurun_out/r2_fullsize.log 2>&1
-grep -E "^\[|passed|failed|Error" gpurun_out/r2_fullsize.log | cut -c1-250
+echo "== fullsize parity (impl 3)"
+SLIME_ATTN_IMPL=3 timeout 1500 python -m pytest tests/test_fullsize_gpu.py -q -s -m gpu > gpurun_out/r2_fullsize_impl3.log 2>&1
+grep -E "rel-L2|16 bit|passed|failed|Error" gpurun_out/r2_fullsize_impl3.log | cut -c1-250
 echo "== bench A/B impl 2 vs 3"
 for impl in 2 3; do
   SLIME_ATTN_IMPL=$impl timeout 600 python bench.py --steps 6 --no-cpu-baseline --no-secondary > gpurun_out/r2_bench_impl$impl.json 2> gpurun_out/r2_bench_impl$impl.err
