@@ -440,7 +440,8 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
     SLIME_PROPAGATE(qkv_rope(c, t, L.qkv_w, total, pos_ids, qkv, s));
     if (c->kv_cache != nullptr) {
       // keep K (post-RoPE) and V of every real token for the decode steps that follow the prefill
-      if (l == 0) SLIME_PROPAGATE(slime_launch_cache_rows(cu, pos_ids, B, total, c->kv_cache_len, cache_rows, s));
+      if (l == 0)
+        SLIME_PROPAGATE(slime_launch_cache_rows(cu, pos_ids, B, total, c->kv_cache_batch, c->kv_cache_len, cache_rows, s));
       const size_t plane = static_cast<size_t>(c->kv_cache_batch) * c->kv_cache_len * KD;
       bf16* kc = c->kv_cache + (static_cast<size_t>(l) * 2 + 0) * plane;
       bf16* vc = c->kv_cache + (static_cast<size_t>(l) * 2 + 1) * plane;
@@ -1007,6 +1008,8 @@ int slime_decoder_prefill_fwd(slime_ctx* ctx, const void* embeds, const int32_t*
   SLIME_REQUIRE(embeds && cu_seqlens && pos_ids && ws, "decoder: null pointer");
   SLIME_REQUIRE(max_seqlen <= ctx->d.max_pos, "decoder: sequence length %d exceeds max_pos %d", max_seqlen,
                 ctx->d.max_pos);
+  SLIME_REQUIRE(ctx->kv_cache == nullptr || batch <= ctx->kv_cache_batch,
+                "decoder: batch %d exceeds the attached KV cache's %d sequences", batch, ctx->kv_cache_batch);
   if (total_rows <= 0 || batch <= 0) return SLIME_OK;
   std::lock_guard<std::mutex> lk(ctx->mu);
   Arena a(ws, ws_bytes);

@@ -60,8 +60,9 @@ int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, c
 // kv splits that fill the GPU for this problem (0: the split kernel does not apply / is switched off)
 int slime_decode_attention_splits(int batch, int heads, int kv_heads, int head_dim, int cache_len, int num_sms);
 size_t slime_decode_attention_ws_floats(int batch, int heads, int splits);
-// rows[i] = sample(i) * cache_len + pos_ids[i] for the packed prefill rows (-1 when pos >= cache_len)
-int slime_launch_cache_rows(const int* cu, const int* pos_ids, int B, int total, int cache_len, int* rows,
+// rows[i] = sample(i) * cache_len + pos_ids[i] for the packed prefill rows (-1 when pos is outside [0, cache_len) or the
+// sample outside the cache's batch)
+int slime_launch_cache_rows(const int* cu, const int* pos_ids, int B, int total, int cache_batch, int cache_len, int* rows,
                             cudaStream_t stream);
 // cache[b, lens[b]] = this step's K / V rows (k, v: [B, KD] slices with row stride ld), both planes in one launch
 int slime_launch_kv_append(const bf16* k, const bf16* v, int ld, bf16* kcache, bf16* vcache, int KD, const int* lens,

@@ -537,9 +537,10 @@ int launch_split(const bf16* q, int q_ld, const bf16* kc, const bf16* vc, int ca
   return SLIME_OK;
 }
 
-// cache_rows[i] = sample(i) * cache_len + pos_ids[i]   (packed prefill row -> slot in the per-sequence cache)
+// cache_rows[i] = sample(i) * cache_len + pos_ids[i]   (packed prefill row -> slot in the per-sequence cache); -1 (row
+// dropped) when the position lies outside [0, cache_len) or the sample outside the cache's batch
 __global__ void cache_rows_kernel(const int* __restrict__ cu, const int* __restrict__ pos_ids, int B, int total,
-                                  int cache_len, int* __restrict__ rows) {
+                                  int cache_batch, int cache_len, int* __restrict__ rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int lo = 0, hi = B;
@@ -548,7 +549,7 @@ __global__ void cache_rows_kernel(const int* __restrict__ cu, const int* __restr
     if (cu[mid] <= i) lo = mid; else hi = mid;
   }
   const int pos = pos_ids[i];
-  rows[i] = pos < cache_len ? lo * cache_len + pos : -1;
+  rows[i] = (pos >= 0 && pos < cache_len && lo < cache_batch) ? lo * cache_len + pos : -1;
 }
 
 // rows[b] = b * cache_len + lens[b]   (slot of the token appended in this decode step)
@@ -665,10 +666,10 @@ int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, c
   return SLIME_OK;
 }
 
-int slime_launch_cache_rows(const int* cu, const int* pos_ids, int B, int total, int cache_len, int* rows,
+int slime_launch_cache_rows(const int* cu, const int* pos_ids, int B, int total, int cache_batch, int cache_len, int* rows,
                             cudaStream_t stream) {
   if (total <= 0) return SLIME_OK;
-  cache_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(cu, pos_ids, B, total, cache_len, rows);
+  cache_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(cu, pos_ids, B, total, cache_batch, cache_len, rows);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

@@ -349,16 +349,25 @@ class SlimeEngine:
         return out
 
     # ------------------------------------------------------------------ KV cache + decode step
+    def new_kv_cache(self, batch: int, cache_len: int) -> torch.Tensor:
+        """An (unattached) KV cache tensor [layers, 2, batch, cache_len, kv_heads*head_dim]."""
+        cfg = self.cfg
+        return torch.zeros(cfg.num_hidden_layers, 2, batch, cache_len, cfg.num_key_value_heads * cfg.head_dim,
+                           dtype=self.dtype, device=self.device)
+
     @_locked
+    def use_kv_cache(self, cache: torch.Tensor) -> torch.Tensor:
+        """Attach an existing cache tensor (e.g. the one a `past_key_values` object carries between forward calls)."""
+        assert cache.dim() == 5 and cache.is_contiguous() and cache.dtype == self.dtype and cache.device == self.device
+        self._check(self.lib.slime_decoder_set_kv_cache(self._ctx, L.ptr(cache), cache.shape[2], cache.shape[3]),
+                    "set_kv_cache")
+        self._kv_cache = cache
+        return cache
+
     def attach_kv_cache(self, batch: int, cache_len: int) -> torch.Tensor:
         """Allocate and attach a KV cache [layers, 2, batch, cache_len, kv_heads*head_dim]; while attached, every
         decoder_prefill stores K (post-RoPE) / V of its sequences into it (sequence b -> cache slot b)."""
-        cfg = self.cfg
-        cache = torch.zeros(cfg.num_hidden_layers, 2, batch, cache_len, cfg.num_key_value_heads * cfg.head_dim,
-                            dtype=self.dtype, device=self.device)
-        self._check(self.lib.slime_decoder_set_kv_cache(self._ctx, L.ptr(cache), batch, cache_len), "set_kv_cache")
-        self._kv_cache = cache
-        return cache
+        return self.use_kv_cache(self.new_kv_cache(batch, cache_len))
 
     @_locked
     def detach_kv_cache(self) -> None:

@@ -5,8 +5,11 @@ model.mm_projector.*, model.sampler.*).  The nn.Modules only HOLD the parameters
 runs in libslime_b200 (vision tower, adapter, router, splice, Llama prefill on packed rows).
 
 generate() = packed prefill with the KV cache attached + native decode steps (slime_decoder_decode_fwd); greedy or
-temperature / top-p sampling (the token choice itself is torch plumbing).  Not built: beam search, training (loss is
-provided for parity of the forward signature, computed from the returned logits with torch).
+temperature / top-p sampling (the token choice itself is torch plumbing).  forward(use_cache=True) returns a
+`SlimeKVCache` as `past_key_values`; handing it back with one new token per sequence runs one native decode step (the
+HF generation loop's contract, reference :57-104,146-157).  Not built: beam search (INTEGRATION.md names the callers
+that pass num_beams), training (loss is provided for parity of the forward signature, computed from the returned
+logits with torch).
 """
 from __future__ import annotations
 
@@ -61,6 +64,41 @@ class CausalLMOutputWithPast:
 
     def __getitem__(self, i):
         return tuple(v for v in (self.loss, self.logits) if v is not None)[i]
+
+
+class SlimeKVCache:
+    """`past_key_values` of the drop-in model: the engine's KV cache tensor [layers, 2, B, cache_len, kv_heads*head_dim]
+    (K post-RoPE) plus the number of cached tokens per sequence.  Callers treat it as opaque and hand it back to
+    forward(); get_seq_length() is what HF's generation utilities ask a cache for.  Grows by re-allocation."""
+
+    def __init__(self, engine, cache: torch.Tensor, lens: torch.Tensor):
+        self.engine, self.cache, self.lens = engine, cache, lens
+        self._max_len = int(lens.max()) if lens.numel() else 0
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return self._max_len
+
+    @property
+    def batch(self) -> int:
+        return self.cache.shape[2]
+
+    def reserve(self, extra: int) -> None:
+        """Room for `extra` more tokens per sequence (doubling re-allocation, bounded by the engine's max positions)."""
+        need = self._max_len + extra
+        have = self.cache.shape[3]
+        if need <= have:
+            return
+        limit = self.engine._desc.max_pos
+        if need > limit:
+            raise RuntimeError(f"KV cache would need {need} positions, the engine was built for {limit}")
+        new_len = min(limit, max(need, 2 * have))
+        new = self.engine.new_kv_cache(self.batch, new_len)
+        new[:, :, :, :have] = self.cache
+        self.cache = new
+
+    def advance(self, n: int = 1) -> None:
+        self.lens = self.lens + n
+        self._max_len += n
 
 
 class _Norm(nn.Module):
@@ -122,7 +160,8 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         self.vocab_size = config.vocab_size
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
         # one engine for the whole tree: sub-modules called on their own (tower, projector, sampler) share it
-        bind(self, EngineBinding(self, self._slime_config, "", ("vit", "rs_local", "rs_global", "proj", "llm")))
+        # ("router" is only packed when mm_resampler_type == 'qformer': slime_b200/weights.py)
+        bind(self, EngineBinding(self, self._slime_config, "", ("vit", "rs_local", "rs_global", "proj", "llm", "router")))
 
     # ------------------------------------------------------------------ plumbing
     def get_model(self):
@@ -163,10 +202,26 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
                 images=None, images_mask=None, image_sizes=None, return_dict=None):
         if output_attentions or output_hidden_states:
             raise NotImplementedError("output_attentions / output_hidden_states are not produced by the fused path")
-        if past_key_values is not None:
-            raise NotImplementedError("KV-cache decode is the next scope item (SURVEY.md 8f.1)")
         eng = self._engine(input_ids.device if input_ids is not None else inputs_embeds.device)
         left = getattr(self.config, "tokenizer_padding_side", "right") == "left"
+        if past_key_values is not None:
+            # one decode step: the HF generation loop hands back the cache with ONE new token per sequence
+            # (reference :57-104 passes past_key_values through; llava_arch.py:279 is the early-out for this call)
+            if not isinstance(past_key_values, SlimeKVCache):
+                raise TypeError("past_key_values must be the SlimeKVCache a previous forward(use_cache=True) returned")
+            x = inputs_embeds if inputs_embeds is not None else eng.weights["llm.embed"][input_ids.to(eng.device)]
+            if x.dim() != 3 or x.shape[1] != 1 or x.shape[0] != past_key_values.batch:
+                raise NotImplementedError("with past_key_values, forward() takes exactly one new token per cached sequence "
+                                          f"(got {tuple(x.shape[:2])} for a cache of {past_key_values.batch} sequences)")
+            pkv = past_key_values
+            pkv.reserve(1)
+            eng.use_kv_cache(pkv.cache)
+            try:
+                logits = eng.decode_step(x[:, 0], pkv.lens)
+            finally:
+                eng.detach_kv_cache()
+            pkv.advance(1)
+            return CausalLMOutputWithPast(logits=logits[:, None, :].to(eng.dtype), past_key_values=pkv)
         if inputs_embeds is None:
             if images is None or input_ids.shape[1] == 1:
                 inputs_embeds = eng.weights["llm.embed"][input_ids.to(eng.device)]
@@ -174,7 +229,7 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
                 sp = self._spliced(input_ids, attention_mask, labels, images, image_sizes, images_mask,
                                    padded=True)["splice"]
                 return self._decode_packed(eng, sp["embeds"], sp["cu_seqlens"], sp["pos_ids"], sp["lengths"], left,
-                                           sp["labels"] if labels is not None else None)
+                                           sp["labels"] if labels is not None else None, use_cache)
         # caller-provided embeddings [B, L, H] (+ attention_mask): pack the real rows and run the decoder
         B, Lm, _ = inputs_embeds.shape
         am = torch.ones(B, Lm, dtype=torch.bool, device=inputs_embeds.device) if attention_mask is None \
@@ -185,10 +240,20 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         pos = torch.cat([torch.arange(L) for L in lengths]).to(device=eng.device, dtype=torch.int32)
         if position_ids is not None:
             pos = position_ids.expand(B, Lm)[am].to(device=eng.device, dtype=torch.int32)
-        return self._decode_packed(eng, rows, cu, pos, lengths, left, labels)
+        return self._decode_packed(eng, rows, cu, pos, lengths, left, labels, use_cache)
 
-    def _decode_packed(self, eng, rows, cu, pos, lengths, left, labels):
-        _, allv, _ = eng.decoder_prefill(rows, cu, pos, lengths, want_last=False, want_all=True)
+    def _decode_packed(self, eng, rows, cu, pos, lengths, left, labels, use_cache=None):
+        pkv = None
+        if use_cache:
+            # the prefill stores K (post-RoPE) / V of every real token into the attached cache (sequence b -> slot b)
+            cache = eng.attach_kv_cache(len(lengths), min(eng._desc.max_pos, max(lengths) + 256))
+            try:
+                _, allv, _ = eng.decoder_prefill(rows, cu, pos, lengths, want_last=False, want_all=True)
+            finally:
+                eng.detach_kv_cache()
+            pkv = SlimeKVCache(eng, cache, torch.tensor(list(lengths), dtype=torch.int32, device=eng.device))
+        else:
+            _, allv, _ = eng.decoder_prefill(rows, cu, pos, lengths, want_last=False, want_all=True)
         B, Lmax, V = len(lengths), max(lengths), self.vocab_size
         logits = torch.zeros(B, Lmax, V, dtype=allv.dtype, device=allv.device)
         off = 0
@@ -203,7 +268,7 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             shift_logits = logits[:, :-1].float().reshape(-1, V)
             shift_labels = labels[:, 1:].reshape(-1).to(logits.device)
             loss = torch.nn.functional.cross_entropy(shift_logits, shift_labels, ignore_index=IGNORE_INDEX)
-        return CausalLMOutputWithPast(loss=loss, logits=logits)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=pkv)
 
     # ------------------------------------------------------------------ generate (reference :106-144)
     @torch.no_grad()
@@ -217,7 +282,8 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
         temperature = float(kwargs.pop("temperature", 1.0) or 1.0)
         top_p = kwargs.pop("top_p", None)
         if int(kwargs.pop("num_beams", 1) or 1) != 1:
-            raise NotImplementedError("beam search is not built")
+            raise NotImplementedError("beam search is not built: the reference's eval loops default to num_beams=1 "
+                                      "(llava/eval/model_vqa_loader.py:117,142; run_llava.py:122,146) - see INTEGRATION.md")
         # HF generate() hooks the reference's callers use: serve/cli.py:95-105 and serve/model_worker.py:168-189 read the
         # output through a `streamer`, eval scripts pass `stopping_criteria=[KeywordsStoppingCriteria(...)]` (mm_utils.py:292)
         streamer = kwargs.pop("streamer", None)
@@ -236,8 +302,10 @@ class LlavaLlamaForCausalLM(nn.Module, LlavaMetaForCausalLM):
             rows = torch.cat(seqs).contiguous()
             cu_t = torch.tensor([0] + list(torch.tensor(lengths).cumsum(0)), dtype=torch.int32, device=eng.device)
             pos = torch.cat([torch.arange(L) for L in lengths]).to(device=eng.device, dtype=torch.int32)
+        # sampling follows torch's global RNG (torch.manual_seed), like HF generate(); `seed=` pins one call
         gen = torch.Generator(device=eng.device)
-        gen.manual_seed(int(kwargs.pop("seed", 0)))
+        seed = kwargs.pop("seed", None)
+        gen.manual_seed(int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item()))
 
         def sample(last):
             if not do_sample:

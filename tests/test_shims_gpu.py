@@ -159,3 +159,133 @@ def test_half_model_runs_the_float16_build():
                  image_sizes=[(672, 672)] * 2)
     assert model._engine().dtype == torch.bfloat16
     assert res2.logits.shape[2] == cfg.vocab_size
+
+
+def test_forward_use_cache_then_single_token_steps(setup):
+    """The HF generation loop's contract (reference llava_llama.py:57-104,146-157; llava_arch.py:279 is the early-out of
+    the later calls): forward(..., use_cache=True) returns past_key_values; handing it back with ONE new token per
+    sequence runs one decode step.  Checked against a cache-less forward of the grown sequence."""
+    from slime_b200.model.language_model.llava_llama import SlimeKVCache
+
+    cfg, model, sd, px, ids, mask, ora, gold = setup
+    B = px.shape[0]
+    images = px.cuda().to(torch.bfloat16)
+    plain = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=images, image_sizes=[(672, 672)] * B)
+    assert plain.past_key_values is None
+    out = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=images, image_sizes=[(672, 672)] * B,
+                use_cache=True)
+    pkv = out.past_key_values
+    assert isinstance(pkv, SlimeKVCache) and pkv.batch == B
+    assert torch.equal(out.logits, plain.logits)                      # attaching the cache does not change the prefill
+    lens = pkv.lens.cpu().tolist()
+    assert pkv.get_seq_length() == max(lens)
+    # the spliced embeddings of the prompt (to build the grown sequences for the cache-less check)
+    prep = model.prepare_inputs_labels_for_multimodal(ids.cuda(), None, mask.cuda(), None, None, images,
+                                                      image_sizes=[(672, 672)] * B)
+    emb = prep[4]
+    seqs = [emb[b, :lens[b]] for b in range(B)]
+    table = model.get_input_embeddings().weight
+    logits = torch.stack([out.logits[b, lens[b] - 1] for b in range(B)])
+    for step in range(3):
+        nxt = logits.float().argmax(-1)
+        res = model(input_ids=nxt[:, None], past_key_values=pkv, use_cache=True)
+        assert res.past_key_values is pkv and res.logits.shape == (B, 1, cfg.vocab_size)
+        assert pkv.lens.cpu().tolist() == [n + step + 1 for n in lens]
+        seqs = [torch.cat([seqs[b], table[nxt[b]][None]]) for b in range(B)]
+        Lm = max(s.shape[0] for s in seqs)
+        padded = torch.stack([torch.cat([s, s.new_zeros(Lm - s.shape[0], s.shape[1])]) for s in seqs])
+        am = torch.stack([torch.arange(Lm, device="cuda") < s.shape[0] for s in seqs])
+        ref = model(inputs_embeds=padded, attention_mask=am)
+        ref_last = torch.stack([ref.logits[b, seqs[b].shape[0] - 1] for b in range(B)])
+        logits = res.logits[:, 0]
+        assert rel(logits, ref_last) < 1e-2
+    with pytest.raises(NotImplementedError, match="one new token"):
+        model(input_ids=torch.zeros(B, 2, dtype=torch.long, device="cuda"), past_key_values=pkv)
+    with pytest.raises(TypeError):
+        model(input_ids=nxt[:, None], past_key_values=((None, None),))
+    # growth by re-allocation keeps the cached prefix
+    before = pkv.cache[:, :, :, :pkv.get_seq_length()].clone()
+    have = pkv.cache.shape[3]
+    pkv.reserve(have)  # force a bigger tensor
+    assert pkv.cache.shape[3] > have and torch.equal(pkv.cache[:, :, :, :before.shape[3]], before)
+    res = model(input_ids=nxt[:, None], past_key_values=pkv, use_cache=True)
+    assert torch.isfinite(res.logits.float()).all()
+
+
+def test_sampling_follows_the_global_rng(setup):
+    """generate(do_sample=True) must not return the same sample on every call; torch.manual_seed pins it."""
+    cfg, model, sd, px, ids, mask, ora, gold = setup
+    kw = dict(images=px[:1].cuda().to(torch.bfloat16), image_sizes=[(672, 672)], attention_mask=mask[:1].cuda(),
+              max_new_tokens=8, do_sample=True, temperature=1.5)
+    torch.manual_seed(1)
+    a = model.generate(ids[:1].cuda(), **kw)
+    b = model.generate(ids[:1].cuda(), **kw)
+    torch.manual_seed(1)
+    c = model.generate(ids[:1].cuda(), **kw)
+    assert torch.equal(a, c)
+    assert not torch.equal(a, b)
+    d = model.generate(ids[:1].cuda(), seed=5, **kw)
+    e = model.generate(ids[:1].cuda(), seed=5, **kw)
+    assert torch.equal(d, e)
+
+
+def test_checkpoint_directory_to_prefill_matches_oracle():
+    """SURVEY 8f.3 on the GPU: a synthetic HF checkpoint directory (sharded safetensors + index + config.json + a CLIP
+    directory) is loaded with load_pretrained_model (the reference's entry point, llava/model/builder.py:26; fp16 like
+    the reference, :43) and the loaded model's prefill matches the fp32 oracle on the same weights."""
+    import json
+    import tempfile
+
+    from safetensors.torch import save_file
+
+    from oracle import slime_oracle as O
+    from slime_b200.checkpoint import load_pretrained_model
+    from slime_b200.config import preset
+    from slime_b200.synth import synth_inputs, synth_state_dict
+    from tests.test_checkpoint_cpu import _write_clip, _write_config
+
+    cfg = preset("tiny")
+    sd = synth_state_dict(cfg)
+    sd16 = {k: v.to(torch.float16) for k, v in sd.items()}
+    clip_dir = _write_clip(cfg, sd16)
+    llm = {k: v for k, v in sd16.items() if not k.startswith("model.vision_tower.")}
+    d = tempfile.mkdtemp(prefix="ckpt_gpu_")
+    _write_config(d, cfg, clip_dir)
+    keys = sorted(llm)
+    shards = {"model-00001-of-00002.safetensors": keys[::2], "model-00002-of-00002.safetensors": keys[1::2]}
+    wm = {}
+    for fn, ks in shards.items():
+        save_file({k: llm[k].contiguous() for k in ks}, os.path.join(d, fn))
+        wm.update({k: fn for k in ks})
+    with open(os.path.join(d, "model.safetensors.index.json"), "w") as f:
+        json.dump({"weight_map": wm}, f)
+    tok, model, proc, ctx_len = load_pretrained_model(d, None, "slime-tiny", device="cuda")
+    assert next(model.parameters()).dtype == torch.float16 and model.get_vision_tower().weights_source == "directory"
+    px, ids, mask = synth_inputs(cfg, 2, 5, 24, image_pos=5, ragged=True)
+    sdf = {k: v.float() for k, v in sd16.items()}  # the oracle on exactly the stored (fp16-rounded) weights
+    with torch.no_grad():
+        ora = O.prefill(sdf, cfg, px, ids, mask, [(2, 2)] * 2)
+    eng = model._engine()
+    assert eng.dtype == torch.float16
+    res = eng.prefill(px, ids, mask, grids=[(2, 2)] * 2, forced_selection=ora["sel"])
+    assert res.lengths == ora["lengths"]
+    ref = torch.stack([lg[-1] for lg in ora["logits"]])
+    e = rel(res.logits_last, ref)
+    print(f"checkpoint dir -> load_pretrained_model -> prefill (fp16): last-token logits rel-L2 vs fp32 oracle {e:.3e}")
+    assert e < 3e-3
+    out = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=px.cuda().half(), image_sizes=[(672, 672)] * 2)
+    assert torch.isfinite(out.logits.float()).all()
+
+
+def test_full_model_with_qformer_router_runs():
+    """the root binding must register the 'router' weight group when mm_resampler_type == 'qformer'."""
+    from slime_b200.synth import synth_inputs, synth_state_dict
+    from tests.test_shims_cpu import make_model
+
+    cfg, model = make_model("tiny", mm_resampler_type="qformer")
+    model.load_state_dict(synth_state_dict(cfg), strict=True)
+    model = model.to(device="cuda", dtype=torch.bfloat16).eval()
+    px, ids, mask = synth_inputs(cfg, 2, 5, 24, image_pos=5, ragged=True)
+    out = model(input_ids=ids.cuda(), attention_mask=mask.cuda(), images=px.cuda().to(torch.bfloat16),
+                image_sizes=[(672, 672)] * 2)
+    assert torch.isfinite(out.logits.float()).all() and out.logits.shape[0] == 2
