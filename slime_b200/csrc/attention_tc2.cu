@@ -418,9 +418,20 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
   } else if (warp_idx == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
+    // The WHOLE warp runs this loop converged and one elected lane issues the tcgen05 instructions.  Every value the
+    // descriptors depend on is warp-uniform and known to be so (ring fields go through __shfl_sync), so they live in
+    // uniform registers and consecutive MMAs are a couple of uniform adds apart.  (Issued from inside `if (lane == 0)`
+    // the operands sit in per-thread registers and every tcgen05.mma pays ~14 instructions of R2UR / ELECT / branch:
+    // ~95 cycles per 64-cycle MMA in the first version of this kernel - the issue thread, not the tensor pipe, set the
+    // pace.)
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16_major(BM, BN, 0, 0);   // Q, K both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16_major(BM, HD, 0, 1);  // P from TMEM, V MN-major
+      auto uni = [](int v) { return __shfl_sync(0xffffffffu, v, 0); };
+      const uint32_t sQ_u = static_cast<uint32_t>(uni(static_cast<int>(smem_u32(sQ))));
+      const uint32_t sK_u = sQ_u + 2 * Cfg::TILE_BYTES;
+      const uint32_t sV_u = sK_u + NK * Cfg::TILE_BYTES;
+      const uint32_t tmem_u = static_cast<uint32_t>(uni(static_cast<int>(tmem_base)));
       int gs[2] = {0, 0};  // tiles of slot X so far  (s_full / p_ready / o_done phases)
       int is[2] = {0, 0};  // items of slot X so far  (q_full / o_free phases)
       int g = 0;           // kv ring index of tile 0 of the current item
@@ -430,66 +441,70 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const int gi = g0 + j, st = gi % NK;
         mbar_wait(&k_full[st], (gi / NK) & 1);
         tcgen05_fence_after();
-        const uint32_t sQ_addr = smem_u32(sQ + x * Cfg::TILE_BYTES);
-        const uint32_t sK_addr = smem_u32(sK + st * Cfg::TILE_BYTES);
-        const uint32_t tmem_s = tmem_base + Cfg::S_COL + x * Cfg::SLOT_STRIDE;
+        const uint64_t dq = make_umma_desc_sw128(sQ_u + x * Cfg::TILE_BYTES);
+        const uint64_t dk = make_umma_desc_sw128(sK_u + st * Cfg::TILE_BYTES);
+        const uint32_t tmem_s = tmem_u + Cfg::S_COL + x * Cfg::SLOT_STRIDE;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int s = 0; s < Cfg::SLABS; ++s) {
-          const uint64_t dq = make_umma_desc_sw128(sQ_addr + s * SLAB_BYTES);
-          const uint64_t dk = make_umma_desc_sw128(sK_addr + s * SLAB_BYTES);
+          for (int s = 0; s < Cfg::SLABS; ++s) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem_s, dq + 2 * kk, dk + 2 * kk, idesc_s, (s | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ss(tmem_s, dq + (s * (SLAB_BYTES >> 4) + 2 * kk), dk + (s * (SLAB_BYTES >> 4) + 2 * kk), idesc_s,
+                           (s | kk) != 0 ? 1u : 0u);
+          }
+          if (last_user) umma_commit(&k_empty[st]);
+          umma_commit(&s_full[x]);
+          if (j == n - 1) umma_commit(&q_empty[x]);  // the slot's Q buffer may be reloaded
         }
-        if (last_user) umma_commit(&k_empty[st]);
-        umma_commit(&s_full[x]);
-        if (j == n - 1) umma_commit(&q_empty[x]);  // the slot's Q buffer may be reloaded
+        __syncwarp();
       };
 
       while (ld_acquire_cta(ring_head) <= 0) {
       }
-      Item2 it = ring[0];
+      int n = uni(ring[0].n_tiles), more = uni(ring[0].more);
+      int valid[2] = {uni(ring[0].valid[0]), uni(ring[0].valid[1])};
       bool started[2] = {false, false};  // S_X(0) of the current item already issued
-      for (int k = 0; it.n_tiles > 0; ++k) {
-        const int n = it.n_tiles;
-        const int last_slot = it.valid[1] ? 1 : 0;
+      for (int k = 0; n > 0; ++k) {
+        const int last_slot = valid[1] ? 1 : 0;
         // first score tile of every slot that did not get it at the end of the previous item
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
-          if (it.valid[x] && !started[x]) {
+          if (valid[x] && !started[x]) {
             mbar_wait(&q_full[x], is[x] & 1);
             issue_s(x, g, 0, n, x == last_slot);
           }
           started[x] = false;
         }
-        Item2 nx;
-        nx.n_tiles = 0;
-        nx.valid[0] = nx.valid[1] = 0;
+        int nx_n = 0, nx_more = 0, nx_valid[2] = {0, 0};
         bool have_next = false;
         for (int j = 0; j < n; ++j) {
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
-            if (!it.valid[x]) continue;
+            if (!valid[x]) continue;
             // ---- O_X += P_X(j) V_j
             const int gv = g + j, vs = gv % NV;
             if (j == 0) mbar_wait(&o_free[x], (is[x] & 1) ^ 1);  // epilogue of the slot's previous item has read O_X
-            const bool tr = p.trace != nullptr && blockIdx.x == 0 && x == 0 && gs[0] < 64;
+            const bool tr = p.trace != nullptr && blockIdx.x == 0 && x == 0 && gs[0] < 64 && lane == 0;
             if (tr) p.trace[gs[0] * 16 + 8] = clock64();
             mbar_wait(&p_ready[x], gs[x] & 1);
             if (tr) p.trace[gs[0] * 16 + 9] = clock64();
             mbar_wait(&v_full[vs], (gv / NV) & 1);
             tcgen05_fence_after();
             if (tr) p.trace[gs[0] * 16 + 10] = clock64();
-            const uint32_t tmem_p = tmem_base + Cfg::S_COL + x * Cfg::SLOT_STRIDE;
-            const uint32_t tmem_o = tmem_base + Cfg::O_COL + x * Cfg::SLOT_STRIDE;
-            const uint64_t dv = make_umma_desc_mn_sw128(smem_u32(sV + vs * Cfg::TILE_BYTES), SLAB_BYTES);
+            const uint32_t tmem_p = tmem_u + Cfg::S_COL + x * Cfg::SLOT_STRIDE;
+            const uint32_t tmem_o = tmem_u + Cfg::O_COL + x * Cfg::SLOT_STRIDE;
+            const uint64_t dv = make_umma_desc_mn_sw128(sV_u + vs * Cfg::TILE_BYTES, SLAB_BYTES);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int kk = 0; kk < BN / 16; ++kk) {
-              // A: 16 kv positions = 8 TMEM columns of packed 16-bit pairs;  B: 16 kv rows = 2048 bytes further down
-              umma_bf16_ts(tmem_o, tmem_p + kk * 8, dv + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv,
-                           (j | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < BN / 16; ++kk) {
+                // A: 16 kv positions = 8 TMEM columns of packed 16-bit pairs;  B: 16 kv rows = 2048 bytes further down
+                umma_bf16_ts(tmem_o, tmem_p + kk * 8, dv + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv,
+                             (j | kk) != 0 ? 1u : 0u);
+              }
+              if (x == last_slot) umma_commit(&v_empty[vs]);
+              umma_commit(&o_done[x]);
             }
-            if (x == last_slot) umma_commit(&v_empty[vs]);
-            umma_commit(&o_done[x]);
+            __syncwarp();
             if (tr) p.trace[gs[0] * 16 + 11] = clock64();
             ++gs[x];
             // ---- the slot's next score tile: same item, or tile 0 of the next item (continuous stream)
@@ -497,31 +512,33 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               issue_s(x, g, j + 1, n, x == last_slot);
             } else {
               ++is[x];
-              if (it.more) {
+              if (more) {
                 if (!have_next) {
                   while (ld_acquire_cta(ring_head) <= k + 1) {
                   }
-                  nx = ring[(k + 1) & 7];
+                  const Item2* pn = &ring[(k + 1) & 7];
+                  nx_n = uni(pn->n_tiles);
+                  nx_more = uni(pn->more);
+                  nx_valid[0] = uni(pn->valid[0]);
+                  nx_valid[1] = uni(pn->valid[1]);
                   have_next = true;
                 }
-                if (nx.valid[x]) {
+                if (nx_valid[x]) {
                   mbar_wait(&q_full[x], is[x] & 1);
-                  issue_s(x, g + n, 0, nx.n_tiles, x == (nx.valid[1] ? 1 : 0));
+                  issue_s(x, g + n, 0, nx_n, x == (nx_valid[1] ? 1 : 0));
                   started[x] = true;
                 }
               }
             }
           }
         }
-        if (!it.more) break;
-        if (!have_next) {  // (cannot happen: a valid item has at least one valid slot)
-          while (ld_acquire_cta(ring_head) <= k + 1) {
-          }
-          nx = ring[(k + 1) & 7];
-        }
-        // a slot that sat this item out never advanced its item count
+        if (!more) break;
+        // (have_next is always set here: a valid item has at least one valid slot)
         g += n;
-        it = nx;
+        n = nx_n;
+        more = nx_more;
+        valid[0] = nx_valid[0];
+        valid[1] = nx_valid[1];
       }
     }
   } else if (warp_idx < 10) {

@@ -92,8 +92,12 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp_idx == 1) {
     // ============================ MMA issuer (leader CTA only) ========================
-    if (leader && lane == 0) {
+    // Whole warp converged, one elected lane issues (descriptors stay in uniform registers: see gemm_sm100.cu).
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      const uint32_t smem_a_u = static_cast<uint32_t>(__shfl_sync(0xffffffffu, static_cast<int>(smem_u32(smem_a)), 0));
+      const uint32_t smem_b_u = smem_a_u + STAGES * A_BYTES;
+      const uint32_t tmem_u = static_cast<uint32_t>(__shfl_sync(0xffffffffu, static_cast<int>(tmem_base), 0));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -102,23 +106,26 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d = tmem_u + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t desc_a = make_umma_desc_sw128(smem_u32(smem_a + stage * A_BYTES));
-          const uint64_t desc_b = make_umma_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
+          const uint64_t desc_a = make_umma_desc_sw128(smem_a_u + stage * A_BYTES);
+          const uint64_t desc_b = make_umma_desc_sw128(smem_b_u + stage * B_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_bf16_ss_2sm(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_bf16_ss_2sm(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_2sm(&tmem_full_bar[acc]);
           }
-          umma_commit_2sm(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full_bar[acc]);
       }
     }
   } else {

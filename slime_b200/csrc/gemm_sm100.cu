@@ -134,8 +134,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
+    // The whole warp runs the loop converged and ONE elected lane issues: every descriptor input is then known to be
+    // warp-uniform and lives in uniform registers, so the four MMAs of a k-block are issued back to back (from inside
+    // `if (lane == 0)` each tcgen05.mma costs ~14 instructions of R2UR / ELECT / branch, ~95 cycles - more than a
+    // 128 x 128 x 16 MMA takes to execute).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      const uint32_t smem_a_u = static_cast<uint32_t>(__shfl_sync(0xffffffffu, static_cast<int>(smem_u32(smem_a)), 0));
+      const uint32_t smem_b_u = smem_a_u + STAGES * Cfg::A_BYTES;
+      const uint32_t tmem_u = static_cast<uint32_t>(__shfl_sync(0xffffffffu, static_cast<int>(tmem_base), 0));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -144,24 +151,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d = tmem_u + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t desc_a = make_umma_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES));
-          const uint64_t desc_b = make_umma_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES));
+          const uint64_t desc_a = make_umma_desc_sw128(smem_a_u + stage * Cfg::A_BYTES);
+          const uint64_t desc_b = make_umma_desc_sw128(smem_b_u + stage * Cfg::B_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
-            umma_bf16_ss(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
+              umma_bf16_ss(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
       }
     }
   } else {
