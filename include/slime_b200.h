@@ -156,6 +156,16 @@ size_t slime_splice_plan_ints(int batch, int prompt_len);
 int slime_splice_plan(slime_ctx* ctx, const int64_t* ids, const uint8_t* mask, int batch, int prompt_len,
                       int n_global, int has_sep, const int32_t* sel_count, int32_t* plan_buf,
                       int32_t* host_cu, void* stream);
+/* No-host-sync variant (the syncs it replaces are llava_arch.py:170,378): only enqueues, the spliced lengths
+ * stay on the device (cu_seqlens inside plan_buf).  The caller sizes every later buffer by the UPPER BOUND
+ * batch * ((prompt_len - 1) + n_global + has_sep + local rows per sample) and passes that bound as `total_rows` to
+ * slime_splice_gather (rows past the real total are zero-filled, pos_ids 0) and to slime_decoder_prefill_fwd (zero rows
+ * stay zero through every layer and belong to no sequence).  With no host round trip the whole prefill can be captured
+ * in a CUDA graph.  slime_splice_check reads back the "more than one image placeholder" flag of the last plan
+ * (synchronises the stream; optional). */
+int slime_splice_plan_async(slime_ctx* ctx, const int64_t* ids, const uint8_t* mask, int batch, int prompt_len,
+                            int n_global, int has_sep, const int32_t* sel_count, int32_t* plan_buf, void* stream);
+int slime_splice_check(slime_ctx* ctx, void* stream);
 int slime_splice_gather(slime_ctx* ctx, const int64_t* ids, int batch, int prompt_len,
                         const int32_t* plan_buf, const void* global_feats, int n_global,
                         int64_t global_sample_rows, const void* local_feats, int64_t local_sample_rows,

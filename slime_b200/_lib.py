@@ -119,6 +119,8 @@ SIGNATURES = {
     "slime_router_select": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "slime_splice_plan_ints": (_sz, [_i, _i]),
     "slime_splice_plan": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "slime_splice_plan_async": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "slime_splice_check": (_i, [_vp, _vp]),
     "slime_splice_gather": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "slime_splice_pad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "slime_decoder_workspace_bytes": (_sz, [_vp, _i, _i]),

@@ -955,6 +955,32 @@ int slime_splice_plan(slime_ctx* ctx, const int64_t* ids, const uint8_t* mask, i
   return SLIME_OK;
 }
 
+int slime_splice_plan_async(slime_ctx* ctx, const int64_t* ids, const uint8_t* mask, int batch, int prompt_len,
+                            int n_global, int has_sep, const int32_t* sel_count, int32_t* plan_buf, void* stream) {
+  SLIME_REQUIRE(ctx && ids && plan_buf, "splice_plan_async: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SLIME_CHECK_CUDA(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), s));
+  return slime_launch_splice_plan(reinterpret_cast<const long long*>(ids), mask, batch, prompt_len, ctx->d.image_token,
+                                  n_global, has_sep, sel_count, ctx->d.max_len, plan_valid(plan_buf),
+                                  plan_plan(plan_buf, batch, prompt_len), plan_cu(plan_buf, batch, prompt_len),
+                                  ctx->err_flag, s);
+}
+
+int slime_splice_check(slime_ctx* ctx, void* stream) {
+  SLIME_REQUIRE(ctx != nullptr, "splice_check: null context");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int err = 0;
+  SLIME_CHECK_CUDA(cudaMemcpyAsync(&err, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SLIME_CHECK_CUDA(cudaStreamSynchronize(s));
+  if (err != 0) {
+    slime_set_error("splice: a prompt holds more than one image placeholder; the SliME path pairs exactly "
+                    "one image with each sample (llava_arch.py:222-255)");
+    return SLIME_EINVAL;
+  }
+  return SLIME_OK;
+}
+
 int slime_splice_gather(slime_ctx* ctx, const int64_t* ids, int batch, int prompt_len, const int32_t* plan_buf,
                         const void* global_feats, int n_global, int64_t global_sample_rows,
                         const void* local_feats, int64_t local_sample_rows, const int32_t* sel_idx,

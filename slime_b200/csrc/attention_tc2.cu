@@ -129,6 +129,13 @@ SLIME_DEVINL constexpr bool pair_is_poly(int c, int P) {
   return P == 2 ? ((c & 3) == 1) : P == 3 ? ((c & 7) == 1 || (c & 7) == 4 || (c & 7) == 6) : P == 4 ? ((c & 1) == 1) : false;
 }
 
+// ---- named barriers (id 0 is __syncthreads) ----
+SLIME_DEVINL void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+SLIME_DEVINL void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
 SLIME_DEVINL int ld_acquire_cta(const int* p) {
   int v;
   asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];\n" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -552,6 +559,12 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + X * Cfg::SLOT_STRIDE;
     int gx = 0;  // tiles of this slot so far
     int ix = 0;  // items of this slot so far
+    // Exponential phases of the two slots ALTERNATE (named barriers 1 + X, 256 threads: one slot syncs, the other
+    // arrives): left alone, both warpgroups receive their score tiles at almost the same time, exponentiate at the same
+    // time (sharing the SFUs: each takes ~1.5x as long) and then both wait for the tensor pipe.  Taking turns, one
+    // slot's exponentials run at full SFU rate while the other slot loads / reduces its next tile and its MMAs execute.
+    // Invariant between items: one arrival is pending on slot A's barrier (slot B's last turn, or the one below).
+    if (X == 1) named_bar_arrive(1, 256);
     for (int k = 0;; ++k) {
       if (lane == 0) {
         while (ld_acquire_cta(ring_head) <= k) {
@@ -562,6 +575,7 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const int n_tiles = pi->n_tiles;
       if (n_tiles == 0) break;
       const int more = pi->more;
+      const bool take_turns = pi->valid[0] && pi->valid[1];
       if (pi->valid[X]) {
         const int it_t = pi->t[X], len_k = pi->len_k, causal_off = pi->causal_off;
         const int row = it_t * BM + r_in_tile;  // query index inside the sequence
@@ -574,9 +588,16 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mbar_wait(&s_full[X], gx & 1);
           tcgen05_fence_after();
           if (tr) p.trace[gx * 16 + 1] = clock64();
-          const bool need_mask = (j * BN + BN > len_k) || (CAUSAL && (j * BN + BN - 1 > it_t * BM + causal_off));
-          // ---- pass 1: row max over the 128 columns, 32 at a time; the load of chunk c+1 is in flight while chunk c
-          //      is reduced
+          // Masking by 32-column chunk, decided per WARP: chunks [0, n_full) are visible to every row of the warp (packed
+          // arithmetic), chunks [n_full, n_any) are cut by the causal diagonal / the end of the keys for some row
+          // (per-element compare), chunks [n_any, 4) are invisible to all 32 rows: skipped, P = 0.
+          int n_full = 4, n_any = 4;
+          if ((j * BN + BN > len_k) || (CAUSAL && (j * BN + BN - 1 > it_t * BM + causal_off))) {
+            const int vis = limit - j * BN + 1;  // visible columns of this tile for this row (may be <= 0 or >= 128)
+            n_full = __reduce_min_sync(0xffffffffu, max(0, min(4, vis >> 5)));
+            n_any = __reduce_max_sync(0xffffffffu, max(0, min(4, (vis + 31) >> 5)));
+          }
+          // ---- pass 1: row max, 32 columns at a time; the load of chunk c+1 is in flight while chunk c is reduced
           float m_tile = -INFINITY;
           {
             uint32_t sr[2][32];
@@ -585,7 +606,7 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             for (int c = 0; c < 4; ++c) {
               tmem_ld_wait();
               if (c + 1 < 4) tmem_ld_32x32b_x32(s_base + (c + 1) * 32, sr[(c + 1) & 1]);
-              m_tile = fmaxf(m_tile, rowmax32(sr[c & 1], need_mask, j * BN + c * 32, limit));
+              if (c < n_any) m_tile = fmaxf(m_tile, rowmax32(sr[c & 1], c >= n_full, j * BN + c * 32, limit));
             }
           }
           if (tr) p.trace[gx * 16 + 2] = clock64();
@@ -610,20 +631,28 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           }
           if (grow) m_cur = m_tile;
           const float m_scaled = (m_cur == -INFINITY) ? 0.f : m_cur * scale_log2;
-          // ---- pass 2: exponentials, 32 columns at a time (next chunk's load in flight); P (16-bit pairs) overwrites
-          //      S columns that have already been consumed: chunk c -> columns [16 c, 16 c + 16)
+          // ---- pass 2 (this slot's turn on the SFUs): exponentials, 32 columns at a time (next chunk's load in
+          //      flight); P (16-bit pairs) overwrites S columns that have already been consumed: chunk c -> columns
+          //      [16 c, 16 c + 16)
+          if (take_turns) named_bar_sync(1 + X, 256);
           {
             uint32_t sr[2][32];
             tmem_ld_32x32b_x32(s_base, sr[0]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+              uint32_t pk[16];
               tmem_ld_wait();
               if (c + 1 < 4) tmem_ld_32x32b_x32(s_base + (c + 1) * 32, sr[(c + 1) & 1]);
-              uint32_t pk[16];
-              l_sum += softmax_exp32<PV>(sr[c & 1], !need_mask, j * BN + c * 32, limit, scale_log2, m_scaled, pk);
+              if (c < n_any) {
+                l_sum += softmax_exp32<PV>(sr[c & 1], c < n_full, j * BN + c * 32, limit, scale_log2, m_scaled, pk);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = 0u;
+              }
               tmem_st_32x32b_x16(s_base + c * 16, pk);
             }
           }
+          if (take_turns) named_bar_arrive(2 - X, 256);
           if (tr) p.trace[gx * 16 + 3] = clock64();
           tmem_st_wait();
           tcgen05_fence_before();

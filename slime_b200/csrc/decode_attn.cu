@@ -543,6 +543,10 @@ __global__ void cache_rows_kernel(const int* __restrict__ cu, const int* __restr
                                   int cache_batch, int cache_len, int* __restrict__ rows) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  if (i >= cu[B]) {  // zero rows past the real total (no-host-sync prefill: buffers sized by an upper bound)
+    rows[i] = -1;
+    return;
+  }
   int lo = 0, hi = B;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;

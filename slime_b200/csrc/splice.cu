@@ -91,6 +91,14 @@ __global__ void __launch_bounds__(128) splice_gather_kernel(
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= total_rows) return;
+  if (row >= cu_seqlens[B]) {
+    // no-host-sync mode: the caller sized the buffers by an upper bound; rows past the real total are zero (they belong
+    // to no sequence and stay zero through the decoder)
+    bf16* z = out + static_cast<long long>(row) * H;
+    for (int c = lane; c < (H >> 3); c += 32) *reinterpret_cast<uint4*>(z + c * 8) = make_uint4(0, 0, 0, 0);
+    if (lane == 0 && pos_ids != nullptr) pos_ids[row] = 0;
+    return;
+  }
   const int b = find_sample(cu_seqlens, B, row);
   const int j = row - cu_seqlens[b];
   const int* pl = plan + b * PLAN_STRIDE;

@@ -44,16 +44,24 @@ class PrefillResult:
     logits_last: Optional[torch.Tensor]      # [B, V] fp32: logits of the last real token of each sample
     logits_all: Optional[torch.Tensor]       # [total, V] bf16 packed rows (only if requested)
     cu_seqlens: torch.Tensor                 # [B+1] int32 (device)
-    lengths: List[int]                       # spliced length of every sample (host)
+    lengths: Optional[List[int]]             # spliced length of every sample (host); None after a no-host-sync prefill
+                                             # until resolve_lengths() reads cu_seqlens back
     sel_idx: Optional[torch.Tensor]          # [B, n_per] int32 kept local-token indices (ascending)
     sel_count: Optional[torch.Tensor]        # [B] int32
     probs: Optional[torch.Tensor]            # [B, n_per] fp32 router probabilities (if requested)
     embeds: Optional[torch.Tensor]           # [total, H] bf16 packed spliced embeddings (if requested)
     stages: Optional[dict] = None            # per-stage tensors (if requested)
 
+    def resolve_lengths(self) -> List[int]:
+        """Host copy of the spliced lengths (a no-host-sync prefill leaves them on the device: this synchronises)."""
+        if self.lengths is None:
+            cu = self.cu_seqlens.cpu().tolist()
+            self.lengths = [cu[i + 1] - cu[i] for i in range(len(cu) - 1)]
+        return self.lengths
+
     @property
     def total_tokens(self) -> int:
-        return int(sum(self.lengths))
+        return int(sum(self.resolve_lengths()))
 
 
 class SlimeEngine:
@@ -261,7 +269,7 @@ class SlimeEngine:
 
     @_locked
     def splice(self, ids, mask, glob, local, sel_idx, sel_count, n_global: int, has_sep: bool,
-               labels: Optional[torch.Tensor] = None, padded: bool = False):
+               labels: Optional[torch.Tensor] = None, padded: bool = False, bound_rows: Optional[int] = None):
         """prepare_inputs_labels_for_multimodal's splice (reference llava_arch.py:249-255,361-459).
         Returns packed embeds [total,H], pos_ids [total] int32, cu_seqlens [B+1] int32 (device), lengths (host)
         and, when `padded`, the reference's padded (inputs_embeds, attention_mask, position_ids, labels)."""
@@ -270,12 +278,20 @@ class SlimeEngine:
         ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
         m8 = None if mask is None else (mask != 0).to(device=self.device, dtype=torch.uint8).contiguous()
         plan = torch.empty(int(self.lib.slime_splice_plan_ints(B, T)), dtype=torch.int32, device=self.device)
-        host_cu = (C.c_int32 * (B + 1))()
-        self._check(self.lib.slime_splice_plan(self._ctx, L.ptr(ids), L.ptr(m8), B, T, n_global, int(has_sep),
-                                           L.ptr(sel_count), L.ptr(plan), host_cu, L.stream_ptr()), "splice_plan")
-        cu_host = list(host_cu)
-        lengths = [cu_host[i + 1] - cu_host[i] for i in range(B)]
-        total = cu_host[B]
+        if bound_rows is not None:
+            # no host round trip (slime_splice_plan_async): the lengths stay on the device, every buffer is sized by the
+            # caller's upper bound and the rows past the real total are zero
+            assert not padded, "the padded views need the lengths on the host"
+            self._check(self.lib.slime_splice_plan_async(self._ctx, L.ptr(ids), L.ptr(m8), B, T, n_global, int(has_sep),
+                                                     L.ptr(sel_count), L.ptr(plan), L.stream_ptr()), "splice_plan_async")
+            lengths, total = None, int(bound_rows)
+        else:
+            host_cu = (C.c_int32 * (B + 1))()
+            self._check(self.lib.slime_splice_plan(self._ctx, L.ptr(ids), L.ptr(m8), B, T, n_global, int(has_sep),
+                                               L.ptr(sel_count), L.ptr(plan), host_cu, L.stream_ptr()), "splice_plan")
+            cu_host = list(host_cu)
+            lengths = [cu_host[i + 1] - cu_host[i] for i in range(B)]
+            total = cu_host[B]
         embeds = self._bf16(total, H)
         pos_ids = torch.empty(total, dtype=torch.int32, device=self.device)
         g_rows = glob.shape[1] if glob is not None and glob.dim() == 3 else 0
@@ -300,17 +316,22 @@ class SlimeEngine:
 
     @_locked
     def decoder_prefill(self, embeds: torch.Tensor, cu_seqlens: torch.Tensor, pos_ids: torch.Tensor,
-                        lengths: Sequence[int], want_last: bool = True, want_all: bool = False,
-                        want_hidden: bool = False):
-        """LlamaForCausalLM.forward(inputs_embeds=...) (HF llama/modeling_llama.py:355-507) on packed rows."""
-        total, B = embeds.shape[0], len(lengths)
+                        lengths: Optional[Sequence[int]], want_last: bool = True, want_all: bool = False,
+                        want_hidden: bool = False, batch: Optional[int] = None, max_len: Optional[int] = None):
+        """LlamaForCausalLM.forward(inputs_embeds=...) (HF llama/modeling_llama.py:355-507) on packed rows.
+        `lengths` (host) gives the batch size and the longest sequence; a no-host-sync caller passes `batch` and an
+        upper bound `max_len` instead (embeds may then hold zero rows past cu_seqlens[-1])."""
+        total = embeds.shape[0]
+        B = len(lengths) if lengths is not None else int(batch)
+        if max_len is None:
+            max_len = max(lengths) if lengths else 0
         V = self.cfg.vocab_size
         last = torch.empty(B, V, dtype=torch.float32, device=self.device) if want_last else None
         allv = self._bf16(total, V) if want_all else None
         hid = self._bf16(total, self.cfg.hidden_size) if want_hidden else None
         ws = self._workspace(self.lib.slime_decoder_workspace_bytes(self._ctx, total, B))
         self._check(self.lib.slime_decoder_prefill_fwd(self._ctx, L.ptr(embeds), L.ptr(cu_seqlens), L.ptr(pos_ids), B, total,
-                                                   max(lengths) if lengths else 0, L.ptr(last), L.ptr(allv), L.ptr(hid),
+                                                   int(max_len), L.ptr(last), L.ptr(allv), L.ptr(hid),
                                                    L.ptr(ws), ws.numel(), L.stream_ptr()), "decoder_prefill_fwd")
         return last, allv, hid
 
@@ -469,12 +490,17 @@ class SlimeEngine:
                 image_sizes: Optional[Sequence[Tuple[int, int]]] = None, grids: Optional[Sequence[Tuple[int, int]]] = None,
                 labels: Optional[torch.Tensor] = None, forced_selection: Optional[Sequence[torch.Tensor]] = None,
                 want_last: bool = True, want_all_logits: bool = False, want_probs: bool = False,
-                keep_stages: bool = False, run_decoder: bool = True, run_splice: bool = True) -> PrefillResult:
+                keep_stages: bool = False, run_decoder: bool = True, run_splice: bool = True,
+                sync_free: bool = False) -> PrefillResult:
         """LlavaLlamaForCausalLM.forward(images=...) (reference llava_llama.py:57-104 -> llava_arch.py:274-459).
 
         pixels: [B, n, 3, S, S] tensor or list of per-sample [n_b, 3, S, S] tensors (crop 0 = global view).
         forced_selection: optional per-sample index tensors that replace the router's choice (teacher forcing
-        for logits parity)."""
+        for logits parity).
+        sync_free: no host synchronisation anywhere (the reference syncs per sample, llava_arch.py:170,378; the default
+        path here syncs once for the spliced lengths): buffers are sized by the upper bound "every local token kept",
+        the result's `lengths` stay on the device (PrefillResult.resolve_lengths()).  This is what GraphedPrefill
+        captures into a CUDA graph."""
         cfg = self.cfg
         with self._lock, torch.cuda.device(self.device):
             if isinstance(pixels, (list, tuple)):
@@ -545,14 +571,72 @@ class SlimeEngine:
                     stages.update(vit=feats, glob=glob, local_m=local)
                 return PrefillResult(logits_last=None, logits_all=None, cu_seqlens=None, lengths=[], sel_idx=sel_idx,
                                      sel_count=sel_count, probs=probs, embeds=None, stages=stages)
+            bound_rows = bound_len = None
+            if sync_free:
+                assert not keep_stages and labels is None, "sync_free: no padded views / labels (they need host lengths)"
+                bound_len = ids.shape[1] + n_global + int(has_sep) + (n_per if not cfg.use_global_only else 0)
+                if cfg.tokenizer_model_max_length:
+                    bound_len = min(bound_len, int(cfg.tokenizer_model_max_length))
+                bound_rows = B * bound_len
             sp = self.splice(ids, mask, glob, local, sel_idx, sel_count, n_global, has_sep, labels=labels,
-                             padded=keep_stages)
+                             padded=keep_stages, bound_rows=bound_rows)
             last = allv = None
             if run_decoder:
                 last, allv, _ = self.decoder_prefill(sp["embeds"], sp["cu_seqlens"], sp["pos_ids"], sp["lengths"],
-                                                     want_last=want_last, want_all=want_all_logits)
+                                                     want_last=want_last, want_all=want_all_logits, batch=B,
+                                                     max_len=bound_len)
             if stages is not None:
                 stages.update(vit=feats, glob=glob, local_m=local, splice=sp)
             return PrefillResult(logits_last=last, logits_all=allv, cu_seqlens=sp["cu_seqlens"], lengths=sp["lengths"],
                                  sel_idx=sel_idx, sel_count=sel_count, probs=probs,
                                  embeds=sp["embeds"] if keep_stages else None, stages=stages)
+
+
+class GraphedPrefill:
+    """One prefill for FIXED shapes (batch, crops per image, prompt length) captured in a CUDA graph: a step is three small
+    copies into static input buffers + one cudaGraphLaunch instead of ~400 kernel launches and a host synchronisation.
+    This is the batch-1 latency path (the reference's eval loop is batch 1, llava/eval/model_vqa_loader.py:103-119):
+    at that size the kernels are 10-100 us long and launch gaps / the mid-pipeline sync are a visible share of the step.
+
+        g = GraphedPrefill(engine, batch=1, n_crops=5, prompt_len=256, grids=[(2, 2)])
+        res = g(pixels, input_ids, attention_mask)       # res.logits_last [B, V] fp32 (static buffer, overwritten by
+                                                         # the next call), res.cu_seqlens on the device
+    Built on SlimeEngine.prefill(sync_free=True): buffers are sized by the upper bound "every local token kept", the
+    real lengths stay on the device, rows past them are zero and belong to no sequence."""
+
+    def __init__(self, engine: SlimeEngine, batch: int, n_crops: int, prompt_len: int,
+                 grids: Optional[Sequence[Tuple[int, int]]] = None, warmup: int = 2):
+        cfg = engine.cfg
+        self.engine = engine
+        dev = engine.device
+        S = cfg.vit_image
+        self.pixels = torch.zeros(batch, n_crops, 3, S, S, dtype=engine.dtype, device=dev)
+        self.ids = torch.zeros(batch, prompt_len, dtype=torch.int64, device=dev)
+        self.ids[:, min(1, prompt_len - 1)] = IMAGE_TOKEN_INDEX
+        self.mask = torch.ones(batch, prompt_len, dtype=torch.int64, device=dev)
+        self.grids = list(grids) if grids is not None else None
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up on a side stream: sizes the workspace, fills the tensor-map / row-map
+            for _ in range(max(1, warmup)):  # caches and sets the kernels' attributes before the capture
+                engine.prefill(self.pixels, self.ids, self.mask, grids=self.grids, sync_free=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = engine.prefill(self.pixels, self.ids, self.mask, grids=self.grids, sync_free=True)
+
+    @torch.no_grad()
+    def __call__(self, pixels: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None
+                 ) -> PrefillResult:
+        with self.engine._lock:
+            self.pixels.copy_(pixels.reshape(self.pixels.shape), non_blocking=True)
+            self.ids.copy_(input_ids, non_blocking=True)
+            if attention_mask is not None:
+                self.mask.copy_(attention_mask, non_blocking=True)
+            else:
+                self.mask.fill_(1)
+            self.graph.replay()
+            r = self.result
+            return PrefillResult(logits_last=r.logits_last, logits_all=None, cu_seqlens=r.cu_seqlens, lengths=None,
+                                 sel_idx=r.sel_idx, sel_count=r.sel_count, probs=None, embeds=None)
