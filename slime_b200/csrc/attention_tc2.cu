@@ -22,6 +22,10 @@
 //   warps 10..13 : epilogue of both slots: O_X / l -> 16 bit -> registers (O_X is handed back to the tensor pipe right
 //                  after this read), then transposed through shared memory and stored with coalesced 64-byte row pieces
 // TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,256+HD)  O_B [384,384+HD).
+// hd 128 fills TMEM, so P_X overwrites the first 64 columns of S_X and S_X(j+1) has to follow PV_X(j) on the tensor pipe.
+// hd 64 leaves room: P_X gets its own 64 columns behind O_X ([320,384) / [448,512)), the softmax releases S_X as soon as it
+// has READ the tile (half way through its exponentials) and S_X(j+1) is computed while softmax_X(j) is still running -
+// the MMA round trip leaves the softmax-bound critical path of the ViT shape (EARLY_S).
 //
 // Shapes on the SliME path: CLIP (16 heads x 64, S = 577, non-causal), Resampler cross-attention (8 x 128, 144 / 576
 // shared queries x 576 keys), Llama decoder (h x 128, causal, GQA, packed variable-length rows).
@@ -56,6 +60,9 @@ struct Cfg2 {
   static constexpr int SMEM_BYTES = SMEM_RAW > 120 * 1024 ? SMEM_RAW : 120 * 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int S_COL = 0, O_COL = 256, SLOT_STRIDE = 128;
+  // hd 64: P in its own columns behind O, S released early (see the header comment)
+  static constexpr bool EARLY_S = HD == 64;
+  static constexpr int P_COL = EARLY_S ? O_COL + 64 : S_COL;
 };
 static_assert(Cfg2<128>::SMEM_BYTES <= 232448, "shared memory budget (hd 128)");
 
@@ -129,13 +136,6 @@ SLIME_DEVINL constexpr bool pair_is_poly(int c, int P) {
   return P == 2 ? ((c & 3) == 1) : P == 3 ? ((c & 7) == 1 || (c & 7) == 4 || (c & 7) == 6) : P == 4 ? ((c & 1) == 1) : false;
 }
 
-// ---- named barriers (id 0 is __syncthreads) ----
-SLIME_DEVINL void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-SLIME_DEVINL void named_bar_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
 SLIME_DEVINL int ld_acquire_cta(const int* p) {
   int v;
   asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];\n" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -305,8 +305,9 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* k_empty = bars + 18;  // [NK]
   uint64_t* v_full = bars + 22;   // [NV <= 4]
   uint64_t* v_empty = bars + 26;  // [NV]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 30);
-  int* ring_head = reinterpret_cast<int*>(bars + 31);  // items posted so far
+  uint64_t* s_free = bars + 30;   // [2] EARLY_S: the slot's softmax has read S_X (it may be overwritten by the next score MMA)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32);
+  int* ring_head = reinterpret_cast<int*>(bars + 33);  // items posted so far
   float* lsum = reinterpret_cast<float*>(aux + Cfg::BAR_BYTES);                       // [2][128]
   uint8_t* stage_all = aux + Cfg::BAR_BYTES + Cfg::LSUM_BYTES;                        // [4 warps][32 rows][64 B]
   Item2* ring = reinterpret_cast<Item2*>(aux + Cfg::BAR_BYTES + Cfg::LSUM_BYTES + Cfg::STAGE_BYTES);  // [8] x 64 B
@@ -326,6 +327,7 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(&o_done[s], 1);
       mbar_init(&o_free[s], 128);
       mbar_init(&l_ready[s], 128);
+      mbar_init(&s_free[s], 128);
     }
     for (int s = 0; s < NK; ++s) {
       mbar_init(&k_full[s], 1);
@@ -444,9 +446,9 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       int g = 0;           // kv ring index of tile 0 of the current item
 
       // S_X(j) of the item whose tile 0 has ring index g0; `last_user`: no later score MMA reads this K tile
-      auto issue_s = [&](int x, int g0, int j, int n, bool last_user) {
+      auto issue_s = [&](int x, int g0, int j, int n, bool last_user, bool k_waited = false) {
         const int gi = g0 + j, st = gi % NK;
-        mbar_wait(&k_full[st], (gi / NK) & 1);
+        if (!k_waited) mbar_wait(&k_full[st], (gi / NK) & 1);
         tcgen05_fence_after();
         const uint64_t dq = make_umma_desc_sw128(sQ_u + x * Cfg::TILE_BYTES);
         const uint64_t dk = make_umma_desc_sw128(sK_u + st * Cfg::TILE_BYTES);
@@ -462,6 +464,23 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (last_user) umma_commit(&k_empty[st]);
           umma_commit(&s_full[x]);
           if (j == n - 1) umma_commit(&q_empty[x]);  // the slot's Q buffer may be reloaded
+        }
+        __syncwarp();
+      };
+      // O_X += P_X(j) V_j; P_X(j) and V(j) have been waited for
+      auto issue_pv = [&](int x, int vs, bool first, bool last_user) {
+        const uint32_t tmem_p = tmem_u + (Cfg::EARLY_S ? Cfg::P_COL : Cfg::S_COL) + x * Cfg::SLOT_STRIDE;
+        const uint32_t tmem_o = tmem_u + Cfg::O_COL + x * Cfg::SLOT_STRIDE;
+        const uint64_t dv = make_umma_desc_mn_sw128(sV_u + vs * Cfg::TILE_BYTES, SLAB_BYTES);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            // A: 16 kv positions = 8 TMEM columns of packed 16-bit pairs;  B: 16 kv rows = 2048 bytes further down
+            umma_bf16_ts(tmem_o, tmem_p + kk * 8, dv + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv,
+                         (!first || kk != 0) ? 1u : 0u);
+          }
+          if (last_user) umma_commit(&v_empty[vs]);
+          umma_commit(&o_done[x]);
         }
         __syncwarp();
       };
@@ -484,59 +503,60 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         int nx_n = 0, nx_more = 0, nx_valid[2] = {0, 0};
         bool have_next = false;
+        // the slot's next score tile: same item, or tile 0 of the next item (one continuous stream)
+        auto next_s = [&](int x, int j) {
+          if (j + 1 < n) {
+            issue_s(x, g, j + 1, n, x == last_slot, !Cfg::EARLY_S);
+          } else {
+            ++is[x];
+            if (more) {
+              if (!have_next) {
+                while (ld_acquire_cta(ring_head) <= k + 1) {
+                }
+                const Item2* pn = &ring[(k + 1) & 7];
+                nx_n = uni(pn->n_tiles);
+                nx_more = uni(pn->more);
+                nx_valid[0] = uni(pn->valid[0]);
+                nx_valid[1] = uni(pn->valid[1]);
+                have_next = true;
+              }
+              if (nx_valid[x]) {
+                mbar_wait(&q_full[x], is[x] & 1);
+                issue_s(x, g + n, 0, nx_n, x == (nx_valid[1] ? 1 : 0));
+                started[x] = true;
+              }
+            }
+          }
+        };
         for (int j = 0; j < n; ++j) {
+          const int gv = g + j, vs = gv % NV;
+          if constexpr (Cfg::EARLY_S) {
+            // S_X(j+1) as soon as the slot's softmax has READ S_X(j) - it is still exponentiating
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              if (!valid[x]) continue;
+              mbar_wait(&s_free[x], (gs[x] + 0) & 1);
+              next_s(x, j);
+            }
+          }
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
             if (!valid[x]) continue;
-            // ---- O_X += P_X(j) V_j
-            const int gv = g + j, vs = gv % NV;
-            if (j == 0) mbar_wait(&o_free[x], (is[x] & 1) ^ 1);  // epilogue of the slot's previous item has read O_X
+            // everything this step needs besides P is waited for FIRST (it arrived long ago, but every mbarrier wait
+            // costs ~100 cycles of latency): once P_X(j) lands, PV_X(j) (and S_X(j+1)) go out back to back
+            const int isx = Cfg::EARLY_S ? (j + 1 < n ? is[x] : is[x] - 1) : is[x];  // items before this one
+            if (j == 0) mbar_wait(&o_free[x], (isx & 1) ^ 1);  // epilogue of the slot's previous item has read O_X
+            mbar_wait(&v_full[vs], (gv / NV) & 1);
+            if (!Cfg::EARLY_S && j + 1 < n) mbar_wait(&k_full[(gv + 1) % NK], ((gv + 1) / NK) & 1);
             const bool tr = p.trace != nullptr && blockIdx.x == 0 && x == 0 && gs[0] < 64 && lane == 0;
             if (tr) p.trace[gs[0] * 16 + 8] = clock64();
             mbar_wait(&p_ready[x], gs[x] & 1);
             if (tr) p.trace[gs[0] * 16 + 9] = clock64();
-            mbar_wait(&v_full[vs], (gv / NV) & 1);
             tcgen05_fence_after();
-            if (tr) p.trace[gs[0] * 16 + 10] = clock64();
-            const uint32_t tmem_p = tmem_u + Cfg::S_COL + x * Cfg::SLOT_STRIDE;
-            const uint32_t tmem_o = tmem_u + Cfg::O_COL + x * Cfg::SLOT_STRIDE;
-            const uint64_t dv = make_umma_desc_mn_sw128(sV_u + vs * Cfg::TILE_BYTES, SLAB_BYTES);
-            if (elect_one_sync()) {
-#pragma unroll
-              for (int kk = 0; kk < BN / 16; ++kk) {
-                // A: 16 kv positions = 8 TMEM columns of packed 16-bit pairs;  B: 16 kv rows = 2048 bytes further down
-                umma_bf16_ts(tmem_o, tmem_p + kk * 8, dv + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv,
-                             (j | kk) != 0 ? 1u : 0u);
-              }
-              if (x == last_slot) umma_commit(&v_empty[vs]);
-              umma_commit(&o_done[x]);
-            }
-            __syncwarp();
+            issue_pv(x, vs, j == 0, x == last_slot);
             if (tr) p.trace[gs[0] * 16 + 11] = clock64();
             ++gs[x];
-            // ---- the slot's next score tile: same item, or tile 0 of the next item (continuous stream)
-            if (j + 1 < n) {
-              issue_s(x, g, j + 1, n, x == last_slot);
-            } else {
-              ++is[x];
-              if (more) {
-                if (!have_next) {
-                  while (ld_acquire_cta(ring_head) <= k + 1) {
-                  }
-                  const Item2* pn = &ring[(k + 1) & 7];
-                  nx_n = uni(pn->n_tiles);
-                  nx_more = uni(pn->more);
-                  nx_valid[0] = uni(pn->valid[0]);
-                  nx_valid[1] = uni(pn->valid[1]);
-                  have_next = true;
-                }
-                if (nx_valid[x]) {
-                  mbar_wait(&q_full[x], is[x] & 1);
-                  issue_s(x, g + n, 0, nx_n, x == (nx_valid[1] ? 1 : 0));
-                  started[x] = true;
-                }
-              }
-            }
+            if constexpr (!Cfg::EARLY_S) next_s(x, j);  // P_X aliases S_X: the next score tile follows PV_X(j)
           }
         }
         if (!more) break;
@@ -556,15 +576,10 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const float scale_log2 = p.scale * 1.4426950408889634f;
     const uint32_t s_base = tmem_base + lane_addr + Cfg::S_COL + X * Cfg::SLOT_STRIDE;
+    const uint32_t p_base = tmem_base + lane_addr + Cfg::P_COL + X * Cfg::SLOT_STRIDE;  // == s_base unless EARLY_S
     const uint32_t o_addr = tmem_base + lane_addr + Cfg::O_COL + X * Cfg::SLOT_STRIDE;
     int gx = 0;  // tiles of this slot so far
     int ix = 0;  // items of this slot so far
-    // Exponential phases of the two slots ALTERNATE (named barriers 1 + X, 256 threads: one slot syncs, the other
-    // arrives): left alone, both warpgroups receive their score tiles at almost the same time, exponentiate at the same
-    // time (sharing the SFUs: each takes ~1.5x as long) and then both wait for the tensor pipe.  Taking turns, one
-    // slot's exponentials run at full SFU rate while the other slot loads / reduces its next tile and its MMAs execute.
-    // Invariant between items: one arrival is pending on slot A's barrier (slot B's last turn, or the one below).
-    if (X == 1) named_bar_arrive(1, 256);
     for (int k = 0;; ++k) {
       if (lane == 0) {
         while (ld_acquire_cta(ring_head) <= k) {
@@ -575,7 +590,6 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const int n_tiles = pi->n_tiles;
       if (n_tiles == 0) break;
       const int more = pi->more;
-      const bool take_turns = pi->valid[0] && pi->valid[1];
       if (pi->valid[X]) {
         const int it_t = pi->t[X], len_k = pi->len_k, causal_off = pi->causal_off;
         const int row = it_t * BM + r_in_tile;  // query index inside the sequence
@@ -631,28 +645,33 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           }
           if (grow) m_cur = m_tile;
           const float m_scaled = (m_cur == -INFINITY) ? 0.f : m_cur * scale_log2;
-          // ---- pass 2 (this slot's turn on the SFUs): exponentials, 32 columns at a time (next chunk's load in
-          //      flight); P (16-bit pairs) overwrites S columns that have already been consumed: chunk c -> columns
-          //      [16 c, 16 c + 16)
-          if (take_turns) named_bar_sync(1 + X, 256);
+          // ---- pass 2: exponentials, 32 columns at a time (next chunk's load in flight); P (16-bit pairs): chunk c ->
+          //      columns [16 c, 16 c + 16) of P_X.  Without EARLY_S P_X is the head of S_X (columns already consumed);
+          //      with it P_X is a buffer of its own: it must have been read by PV_X(j-1), and S_X is handed back to the
+          //      tensor pipe as soon as its last chunk is in registers (half way through the exponentials).
+          if (Cfg::EARLY_S && gx > 0) mbar_wait(&o_done[X], (gx - 1) & 1);
           {
             uint32_t sr[2][32];
             tmem_ld_32x32b_x32(s_base, sr[0]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t pk[16];
-              tmem_ld_wait();
+              if (!(Cfg::EARLY_S && c == 3)) tmem_ld_wait();
               if (c + 1 < 4) tmem_ld_32x32b_x32(s_base + (c + 1) * 32, sr[(c + 1) & 1]);
+              if (Cfg::EARLY_S && c == 2) {
+                tmem_ld_wait();  // chunk 3 is in registers too: S_X(j) is no longer needed
+                tcgen05_fence_before();
+                mbar_arrive(&s_free[X]);
+              }
               if (c < n_any) {
                 l_sum += softmax_exp32<PV>(sr[c & 1], c < n_full, j * BN + c * 32, limit, scale_log2, m_scaled, pk);
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] = 0u;
               }
-              tmem_st_32x32b_x16(s_base + c * 16, pk);
+              tmem_st_32x32b_x16(p_base + c * 16, pk);
             }
           }
-          if (take_turns) named_bar_arrive(2 - X, 256);
           if (tr) p.trace[gx * 16 + 3] = clock64();
           tmem_st_wait();
           tcgen05_fence_before();

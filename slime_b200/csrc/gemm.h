@@ -59,6 +59,11 @@ struct GemmParams {
 #define SLIME_GEMM_2CTA_DEFAULT 2
 #endif
 
+// L2 cache hints of the 2-CTA kernel's operand loads (bit 0: A evict_last, bit 1: W evict_first); SLIME_GEMM_L2HINT overrides
+#ifndef SLIME_GEMM_L2HINT_DEFAULT
+#define SLIME_GEMM_L2HINT_DEFAULT 0
+#endif
+
 // Returns 0 on success; negative SLIME_E* otherwise (message via slime_set_error).
 int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                       int num_sms, cudaStream_t stream);

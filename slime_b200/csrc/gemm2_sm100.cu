@@ -10,6 +10,8 @@
 //   warp 1 (leader)   : issues tcgen05.mma.cta_group::2; commits multicast to both CTAs' barriers
 //   warps 2..9 (both) : epilogue of the CTA's own 128 rows (gemm_epilogue.cuh), arriving on the leader's
 //                       tmem_empty barrier
+#include <cstdlib>
+
 #include "errors.h"
 #include "gemm.h"
 
@@ -20,7 +22,7 @@ namespace {
 template <int EPI, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmParams p, const int group_m) {
+                         const GemmParams p, const int group_m, const int l2_hint) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
@@ -70,6 +72,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 cache hints of the operand loads (SLIME_GEMM_L2HINT, measurement knob; 0 = none): bit 0 = the A panel of the
+      // rasterisation group is re-read by every n-tile -> evict_last; bit 1 = W streams past once per group -> evict_first
+      const uint64_t pol_a = (l2_hint & 1) ? l2_policy_evict_last() : 0, pol_b = (l2_hint & 2) ? l2_policy_evict_first() : 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const TileCoord tc = tile_coord(t, num_m, num_n, group_m);
         const int m_row = tc.m_blk * 2 * BLOCK_M + rank * BLOCK_M;          // this CTA's 128 rows of A
@@ -81,8 +86,10 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           } else {
             mbar_arrive_leader(&full_bar[stage]);
           }
-          tma_load_2d_2sm(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row);
-          tma_load_2d_2sm(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row);
+          if (l2_hint & 1) tma_load_2d_2sm_hint(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row, pol_a);
+          else tma_load_2d_2sm(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row);
+          if (l2_hint & 2) tma_load_2d_2sm_hint(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row, pol_b);
+          else tma_load_2d_2sm(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -169,7 +176,12 @@ int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, 
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   slime_prof_begin(0, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-  kern<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, slime_gemm_group_m(p.K, 2 * BLOCK_M));
+  static int l2_hint = -1;
+  if (l2_hint < 0) {
+    const char* e = getenv("SLIME_GEMM_L2HINT");
+    l2_hint = e != nullptr ? atoi(e) & 3 : SLIME_GEMM_L2HINT_DEFAULT;
+  }
+  kern<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, slime_gemm_group_m(p.K, 2 * BLOCK_M), l2_hint);
   slime_prof_end(stream);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;

@@ -479,3 +479,27 @@ def test_qkv_rope_fused_epilogue(rows, two_cta):
     assert_close_bf16(outs[True], ref, f"fused qkv+rope rows={rows}")
     assert_close_bf16(outs[False], ref, f"unfused qkv+rope rows={rows}", tol=6e-3)
     assert torch.equal(outs[True][:, (nh + nkv) * hd:], outs[False][:, (nh + nkv) * hd:]), "v columns must not change"
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("causal,d", [(0, 128), (1, 128), (0, 64)])
+def test_attention_scores_growing_along_the_keys(impl, causal, d):
+    """Scores that grow by hundreds of nats from the first key tile to the last one: every tile moves the reference max
+    by far more than the lazy-rescale threshold (2^8), so O and the row sums are rescaled tile after tile - on the hd-64
+    path while the next score tile is already being computed.  Must match the fp32 softmax (which concentrates on the
+    last visible keys)."""
+    torch.manual_seed(13)
+    B, h, S = 2, 4, 700
+    q = (torch.rand(B * S, h * d, device="cuda") * 0.5 + 0.75).to(torch.bfloat16)            # positive, O(1)
+    ramp = torch.arange(S, device="cuda", dtype=torch.float32).repeat(B)[:, None] / S          # 0 .. 1 along the keys
+    k = (ramp * 3.0 * torch.ones(1, h * d, device="cuda")).to(torch.bfloat16)                  # q.k grows to ~ 3 d
+    v = rnd(B * S, h * d)
+    scale = d ** -0.5 * 8.0
+    o = attention(q, k, v, B * S, h * d, q_ld=h * d, k_ld=h * d, v_ld=h * d, seqlen_q=S, seqlen_k=S, q_batch_rows=S,
+                  k_batch_rows=S, o_batch_rows=S, batch=B, heads=h, kv_heads=h, head_dim=d, scale=scale,
+                  causal=causal, impl=impl)
+    qf = q.float().view(B, S, h, d).permute(0, 2, 1, 3)
+    kf = k.float().view(B, S, h, d).permute(0, 2, 1, 3)
+    vf = v.float().view(B, S, h, d).permute(0, 2, 1, 3)
+    ref = ref_attention(qf, kf, vf, scale, bool(causal)).permute(0, 2, 1, 3).reshape(B * S, h * d)
+    assert_close_bf16(o, ref, f"attention growing scores causal={causal} d={d}")
