@@ -181,8 +181,21 @@ SLIME_DEVINL float softmax_exp32(const uint32_t (&sr)[32], bool plain, int col_b
         pv.x = fast_exp2(x.x);
         pv.y = fast_exp2(x.y);
       }
+#ifdef SLIME_FP16
       acc[c & 1] = fadd2(acc[c & 1], pv);
       pk[c] = pack_bf16x2(pv.x, pv.y);
+#else
+      // fp32 -> bf16 WITHOUT the conversion instruction: F2FP shares the quarter-rate XU pipe with MUFU.EX2 (8 cycles
+      // per warp instruction), which made the exponential phase 1.5 x as long as its 128 ex2 per row.  Veltkamp split
+      // with C = 2^16 + 1: hi = C p - (C p - p) is p rounded to nearest with 8 significant bits - bit-identical to
+      // cvt.rn.bf16.f32 - in three FFMA2 on the FMA pipe; its low 16 bits are zero, so a byte permute packs the pair.
+      // The row sum is taken over the rounded values (what the PV MMA sees).
+      const float2 t = ffma2(pv, make_float2(65537.0f, 65537.0f), make_float2(0.f, 0.f));
+      const float2 dlt = ffma2(pv, make_float2(-1.0f, -1.0f), t);
+      const float2 hi = ffma2(dlt, make_float2(-1.0f, -1.0f), t);
+      acc[c & 1] = fadd2(acc[c & 1], hi);
+      pk[c] = __byte_perm(__float_as_uint(hi.x), __float_as_uint(hi.y), 0x7632);
+#endif
     }
     return (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
   }

@@ -28,6 +28,14 @@ struct GemmParams {
   int rope_half = 0;                   // head_dim / 2
   int rope_cols = 0;                   // columns [0, rope_cols) are rotated (q and k heads), the rest (v) is not
   int rope_max_pos = 0;
+  // ---- norm folding (prefill): the RMSNorm in front of a projection is folded into it - gamma is multiplied into the
+  // weight columns at load, the GEMM runs on the UN-normalised residual stream and the epilogue scales every output row
+  // by its 1/rms (HF llama/modeling_llama.py:62-67).  The 1/rms values come from per-row partial sums of squares that
+  // the PREVIOUS residual GEMM's epilogue writes (one partial per 64 output columns, of the bf16-rounded values) and a
+  // tiny finishing kernel turns into rstd[row]: the separate RMSNorm pass over the stream (read + write) disappears.
+  const float* row_scale = nullptr;  // [M] multiplied into the accumulators first (before RoPE / bias / activation)
+  float* sumsq_out = nullptr;        // [M][sumsq_parts] partial sums of squares of this GEMM's bf16 output rows (EPI_NONE)
+  int sumsq_parts = 0;               // = N / 64
   int epi_mode = 0;    // HBM access pattern of the epilogue (gemm_epilogue.cuh): 0 direct, 1 staged through shared
                        // memory (coalesced stores and residual loads); filled in by slime_launch_gemm
   // ---- decode-step problems (M <= 32 rows; gemm_skinny.cu) ----

@@ -37,7 +37,9 @@ struct EpiRow {
   bool store_ok;
   int out_row;
   int res_row;
-  int pos;  // GEMM_EPI_ROPE: position id of this row
+  int pos;      // GEMM_EPI_ROPE: position id of this row
+  float scale;  // GemmParams::row_scale of this row (1 when absent)
+  float ssq;    // GemmParams::sumsq_out: running sum of squares of the (bf16-rounded) outputs of the current 64 columns
 };
 
 // Row bookkeeping of the coalesced phases: in iteration i a lane handles row r_i = i * (32 / SLOTS) + lane / SLOTS
@@ -115,7 +117,7 @@ template <int EPI>
 SLIME_DEVINL void epi_math8(const GemmParams& p, const EpiRow& er, int col, const uint32_t* r8, const uint4& resq,
                             const uint4& b, float (&v)[8]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r8[j]);
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r8[j]) * er.scale;
   if constexpr (EPI == GEMM_EPI_ROPE) {
     // columns (2i, 2i+1) of a head hold features (i, i + half): out_i = x_i cos_i - x_{i+half} sin_i,
     // out_{i+half} = x_{i+half} cos_i + x_i sin_i, on the fp32 accumulators (one rounding instead of two)
@@ -162,16 +164,22 @@ SLIME_DEVINL uint4 epi_pack8(const float (&v)[8]) {
 }
 
 // SwiGLU on 16 interleaved (gate, up) accumulator columns -> 8 outputs
-SLIME_DEVINL uint4 epi_swiglu8(const uint32_t* r16) {
+SLIME_DEVINL uint4 epi_swiglu8(const uint32_t* r16, float scale) {
   float o[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = act_silu(__uint_as_float(r16[2 * j])) * __uint_as_float(r16[2 * j + 1]);
+  for (int j = 0; j < 8; ++j)
+    o[j] = act_silu(__uint_as_float(r16[2 * j]) * scale) * (__uint_as_float(r16[2 * j + 1]) * scale);
   return epi_pack8(o);
+}
+// sum of squares of 8 packed 16-bit outputs (the values the next layer will actually read)
+SLIME_DEVINL float epi_sumsq8(const uint4& pk) {
+  const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y), c = unpack_bf16x2(pk.z), d = unpack_bf16x2(pk.w);
+  return (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y) + (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
 }
 
 // ---- mode 0: every thread stores its own row ----
 template <int EPI>
-SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, const EpiRow& er, int col0, const uint32_t (&r)[32],
+SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, EpiRow& er, int col0, const uint32_t (&r)[32],
                                            const uint4 (&res)[4], const uint4 (&bia)[4]) {
   if (!er.store_ok || col0 >= p.N) return;
   if constexpr (EPI == GEMM_EPI_SWIGLU) {
@@ -180,7 +188,8 @@ SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, const EpiRow& er
     for (int g = 0; g < 2; ++g) {
       const int col = col0 + g * 16;
       if (col >= p.N) break;
-      *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(er.out_row) * p.out_ld + (col >> 1)) = epi_swiglu8(r + g * 16);
+      *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(er.out_row) * p.out_ld + (col >> 1)) =
+          epi_swiglu8(r + g * 16, er.scale);
     }
   } else {
 #pragma unroll
@@ -194,7 +203,9 @@ SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, const EpiRow& er
         dst[0] = make_float4(v[0], v[1], v[2], v[3]);
         dst[1] = make_float4(v[4], v[5], v[6], v[7]);
       } else {
-        *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(er.out_row) * p.out_ld + col) = epi_pack8(v);
+        const uint4 pk = epi_pack8(v);
+        *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(er.out_row) * p.out_ld + col) = pk;
+        if (p.sumsq_out != nullptr) er.ssq += epi_sumsq8(pk);
       }
     }
   }
@@ -211,7 +222,7 @@ SLIME_DEVINL void epi_process_chunk_staged(const GemmParams& p, const EpiRow& er
   if constexpr (EPI == GEMM_EPI_SWIGLU) {
 #pragma unroll
     for (int g = 0; g < 2; ++g)
-      *reinterpret_cast<uint4*>(stage_out + epi_stage_off<2>(lane, g)) = epi_swiglu8(r + g * 16);
+      *reinterpret_cast<uint4*>(stage_out + epi_stage_off<2>(lane, g)) = epi_swiglu8(r + g * 16, er.scale);
   } else {
     uint4 own[4];
     if (p.residual != nullptr) {
@@ -272,6 +283,8 @@ SLIME_DEVINL void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m0, 
   if constexpr (EPI == GEMM_EPI_ROPE) {
     if (row_ok) er.pos = min(max(p.rope_pos[row], 0), p.rope_max_pos - 1);
   }
+  er.scale = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.0f;
+  er.ssq = 0.f;
   EpiCoal ec = {};
   if constexpr (STAGED) ec = epi_make_coal<SLOTS>(er, lane);
 
@@ -296,6 +309,14 @@ SLIME_DEVINL void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m0, 
       epi_process_chunk_staged<EPI>(p, er, ec, lane, col_begin + i * 32, acc[i & 1], res[i & 1], bia[i & 1], stage);
     } else {
       epi_process_chunk_direct<EPI>(p, er, col_begin + i * 32, acc[i & 1], res[i & 1], bia[i & 1]);
+      if constexpr (EPI == GEMM_EPI_NONE) {
+        // one partial per 64 output columns (two chunks): [row][column / 64]
+        if (p.sumsq_out != nullptr && (i & 1) == 1) {
+          const int part = (col_begin + i * 32) >> 6;
+          if (er.store_ok && part < p.sumsq_parts) p.sumsq_out[static_cast<size_t>(row) * p.sumsq_parts + part] = er.ssq;
+          er.ssq = 0.f;
+        }
+      }
     }
     if (i + 1 < NCH) tmem_ld_wait();
   }
