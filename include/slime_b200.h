@@ -46,6 +46,9 @@ extern "C" {
  * "router.*") instead of the cosine router.  Like the reference, its softmax output is soft-maxed once more by the
  * sampler (builder.py:160 and :258) before the top-p rule. */
 #define SLIME_FLAG_ROUTER_QFORMER 16u
+#define SLIME_FLAG_NORM_FOLDED 32u /* the Llama RMSNorm weights are already multiplied into the columns of the qkv / gate-up
+                                     weights (slime_b200/weights.py): the prefill applies 1/rms in those GEMMs' epilogues
+                                     instead of running separate RMSNorm passes; the decode step normalises without gamma */
 
 typedef struct slime_ctx slime_ctx;
 

@@ -40,6 +40,7 @@ SLIME_FLAG_USE_GLOBAL_ONLY = 2
 SLIME_FLAG_USE_LOCAL_ONLY = 4
 SLIME_FLAG_ROPE_INTERLEAVED = 8
 SLIME_FLAG_ROUTER_QFORMER = 16
+SLIME_FLAG_NORM_FOLDED = 32
 
 EPI_NONE, EPI_QUICK_GELU, EPI_GELU_ERF, EPI_SWIGLU, EPI_ROPE = 0, 1, 2, 3, 4
 

@@ -138,6 +138,9 @@ struct GemmExtra {
   bf16* norm_out = nullptr;
   int norm_ld = 0;
   float norm_eps = 0.f;
+  // prefill norm folding (gemm.h): per-row 1/rms applied by the epilogue; partial sums of squares of the output rows
+  const float* row_scale = nullptr;
+  float* sumsq_out = nullptr;
 };
 
 int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
@@ -153,6 +156,9 @@ int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, in
     p.norm_out = ex->norm_out;
     p.norm_ld = ex->norm_ld;
     p.norm_eps = ex->norm_eps;
+    p.row_scale = ex->row_scale;
+    p.sumsq_out = ex->sumsq_out;
+    p.sumsq_parts = ex->sumsq_out != nullptr ? N / 64 : 0;
   }
   p.M = M; p.N = N; p.K = K;
   p.bias = bias;
@@ -196,6 +202,7 @@ int qkv_rope(slime_ctx* c, const bf16* x, const bf16* qkv_w, int rows, const int
     p.kv_cache_len = ex->kv_cache_len;
     p.kv_dim = d.kv_heads * hd;
     p.kv_q_cols = d.heads * hd;
+    p.row_scale = ex->row_scale;
   }
   p.M = rows; p.N = QKV; p.K = H;
   p.bias = nullptr;
@@ -429,15 +436,25 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
   int* last_rows = a.get<int>(B);
   bf16* last_h = a.get<bf16>(static_cast<size_t>(B) * H);
   int* cache_rows = a.get<int>(total);  // packed row -> slot of the per-sequence KV cache (when one is attached)
+  float* rstd = a.get<float>(total);    // norm folding: 1/rms of every row of the residual stream
+  float* sumsq = a.get<float>(static_cast<size_t>(total) * (H / 64 + 1));  // ... and the partials a residual GEMM writes
   ARENA_CHECK(a, "decoder");
   if (a.dry || total <= 0) return SLIME_OK;
 
   SLIME_CHECK_CUDA(cudaMemcpyAsync(h, embeds, static_cast<size_t>(total) * H * sizeof(bf16),
                                    cudaMemcpyDeviceToDevice, s));
+  // SLIME_FLAG_NORM_FOLDED: the two RMSNorms of a layer live inside the projections that follow them (gamma in the weight
+  // columns, 1/rms in the epilogue; gemm.h) - the GEMMs read the residual stream h directly, `t` is not used
+  const bool folded = (d.flags & SLIME_FLAG_NORM_FOLDED) != 0 && H % 64 == 0;
+  const int parts = H / 64;
+  if (folded) SLIME_PROPAGATE(slime_launch_row_rstd(h, H, rstd, total, H, d.rms_eps, s));
   for (int l = 0; l < d.layers; ++l) {
     const LlmLayer& L = c->llm[l];
-    SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.in_norm_w, t, H, total, H, d.rms_eps, nullptr, s));
-    SLIME_PROPAGATE(qkv_rope(c, t, L.qkv_w, total, pos_ids, qkv, s));
+    GemmExtra exs, exq;  // exs: residual GEMM that also writes the partials; exq: projection scaled by 1/rms
+    exs.sumsq_out = folded ? sumsq : nullptr;
+    exq.row_scale = folded ? rstd : nullptr;
+    if (!folded) SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.in_norm_w, t, H, total, H, d.rms_eps, nullptr, s));
+    SLIME_PROPAGATE(qkv_rope(c, folded ? h : t, L.qkv_w, total, pos_ids, qkv, s, folded ? &exq : nullptr));
     if (c->kv_cache != nullptr) {
       // keep K (post-RoPE) and V of every real token for the decode steps that follow the prefill
       if (l == 0)
@@ -458,11 +475,18 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
     ap.scale = 1.0f / sqrtf(static_cast<float>(hd)); ap.causal = 1;
     ap.total_q_rows = ap.total_k_rows = total;
     SLIME_PROPAGATE(slime_launch_attention(ap, s));
-    SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, total, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s));
-    SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.post_norm_w, t, H, total, H, d.rms_eps, nullptr, s));
-    SLIME_PROPAGATE(gemm(c, t, H, L.gate_up_w, H, total, 2 * I, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_SWIGLU,
-                         act, nullptr, I, s));
-    SLIME_PROPAGATE(gemm(c, act, I, L.down_w, I, total, H, I, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s));
+    SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, total, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s,
+                         folded ? &exs : nullptr));
+    if (folded) {
+      SLIME_PROPAGATE(slime_launch_sumsq_to_rstd(sumsq, parts, rstd, total, H, d.rms_eps, s));
+    } else {
+      SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.post_norm_w, t, H, total, H, d.rms_eps, nullptr, s));
+    }
+    SLIME_PROPAGATE(gemm(c, folded ? h : t, H, L.gate_up_w, H, total, 2 * I, H, nullptr, nullptr, 0, 0, nullptr,
+                         GEMM_EPI_SWIGLU, act, nullptr, I, s, folded ? &exq : nullptr));
+    SLIME_PROPAGATE(gemm(c, act, I, L.down_w, I, total, H, I, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s,
+                         folded && l + 1 < d.layers ? &exs : nullptr));
+    if (folded && l + 1 < d.layers) SLIME_PROPAGATE(slime_launch_sumsq_to_rstd(sumsq, parts, rstd, total, H, d.rms_eps, s));
   }
   if (logits_last != nullptr) {
     SLIME_PROPAGATE(slime_launch_last_rows(cu, B, last_rows, s));

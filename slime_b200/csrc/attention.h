@@ -8,10 +8,13 @@
 #define SLIME_ATTN_DEFAULT_IMPL 2
 #endif
 // attention_tc2.cu: how many of every 8 score-column pairs are exponentiated by a polynomial on the FMA pipe
-// instead of MUFU.EX2 (0, 2, 3 or 4)
+// instead of MUFU.EX2 (0, 2, 3 or 4).  Measured on B200 (profiles/r02_attention_experiments.txt): no share of polynomial
+// exponentials beats plain MUFU - the FFMA2 chain of the polynomial costs the FMA pipe as much as the two ex2 cost the XU.
 #ifndef SLIME_ATTN_POLY_DEFAULT
-#define SLIME_ATTN_POLY_DEFAULT 2
+#define SLIME_ATTN_POLY_DEFAULT 0
 #endif
+#undef SLIME_ATTN_DEFAULT_IMPL
+#define SLIME_ATTN_DEFAULT_IMPL 3
 
 // softmax arithmetic variant of the tcgen05 kernel (attention_tc.cu: 0 scalar MUFU, 1 + 2*P packed pairs with P of
 // every 8 pairs exponentiated on the FMA pipe)

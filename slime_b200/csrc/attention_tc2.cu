@@ -32,6 +32,7 @@
 #include "attention.h"
 #include "errors.h"
 #include <cstdlib>
+#include <type_traits>
 
 #include "gemm.h"
 
@@ -146,9 +147,10 @@ SLIME_DEVINL void st_release_cta(int* p, int v) {
 }
 
 // max over 32 score columns held in registers; with `need_mask` columns beyond `limit` count as -inf
-SLIME_DEVINL float rowmax32(const uint32_t (&sr)[32], bool need_mask, int col_base, int limit) {
+template <bool MASKED>
+SLIME_DEVINL float rowmax32(const uint32_t (&sr)[32], int col_base, int limit) {
   float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains
-  if (need_mask) {
+  if (MASKED) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
       float v = __uint_as_float(sr[c]);
@@ -165,10 +167,10 @@ SLIME_DEVINL float rowmax32(const uint32_t (&sr)[32], bool need_mask, int col_ba
 
 // P = 2^(s * scale_log2 - m_scaled) for 32 columns -> 16 packed 16-bit pairs; returns the fp32 row sum of the 32 values.
 // `plain` = the tile needs no masking (no -inf inputs), so the packed / polynomial arithmetic of variant P may be used.
-template <int P>
-SLIME_DEVINL float softmax_exp32(const uint32_t (&sr)[32], bool plain, int col_base, int limit, float scale_log2,
+template <int P, bool MASKED>
+SLIME_DEVINL float softmax_exp32(const uint32_t (&sr)[32], int col_base, int limit, float scale_log2,
                                  float m_scaled, uint32_t (&pk)[16]) {
-  if (plain) {
+  if (!MASKED) {
     const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_scaled, -m_scaled);
     float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
@@ -181,21 +183,8 @@ SLIME_DEVINL float softmax_exp32(const uint32_t (&sr)[32], bool plain, int col_b
         pv.x = fast_exp2(x.x);
         pv.y = fast_exp2(x.y);
       }
-#ifdef SLIME_FP16
       acc[c & 1] = fadd2(acc[c & 1], pv);
       pk[c] = pack_bf16x2(pv.x, pv.y);
-#else
-      // fp32 -> bf16 WITHOUT the conversion instruction: F2FP shares the quarter-rate XU pipe with MUFU.EX2 (8 cycles
-      // per warp instruction), which made the exponential phase 1.5 x as long as its 128 ex2 per row.  Veltkamp split
-      // with C = 2^16 + 1: hi = C p - (C p - p) is p rounded to nearest with 8 significant bits - bit-identical to
-      // cvt.rn.bf16.f32 - in three FFMA2 on the FMA pipe; its low 16 bits are zero, so a byte permute packs the pair.
-      // The row sum is taken over the rounded values (what the PV MMA sees).
-      const float2 t = ffma2(pv, make_float2(65537.0f, 65537.0f), make_float2(0.f, 0.f));
-      const float2 dlt = ffma2(pv, make_float2(-1.0f, -1.0f), t);
-      const float2 hi = ffma2(dlt, make_float2(-1.0f, -1.0f), t);
-      acc[c & 1] = fadd2(acc[c & 1], hi);
-      pk[c] = __byte_perm(__float_as_uint(hi.x), __float_as_uint(hi.y), 0x7632);
-#endif
     }
     return (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
   }
@@ -624,18 +613,28 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             n_full = __reduce_min_sync(0xffffffffu, max(0, min(4, vis >> 5)));
             n_any = __reduce_max_sync(0xffffffffu, max(0, min(4, (vis + 31) >> 5)));
           }
-          // ---- pass 1: row max, 32 columns at a time; the load of chunk c+1 is in flight while chunk c is reduced
-          float m_tile = -INFINITY;
-          {
+          // ---- pass 1: row max, 32 columns at a time; the load of chunk c+1 is in flight while chunk c is reduced.
+          //      (`mt` = this tile needs masking at all: a compile-time split, so the common unmasked tile carries no
+          //      per-chunk tests - as a run-time flag the compiler predicated BOTH variants into one instruction stream.)
+          const bool masked_tile = n_full < 4;  // warp-uniform
+          auto pass1 = [&](auto mt) {
+            constexpr bool MT = decltype(mt)::value;
+            float m = -INFINITY;
             uint32_t sr[2][32];
             tmem_ld_32x32b_x32(s_base, sr[0]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               tmem_ld_wait();
               if (c + 1 < 4) tmem_ld_32x32b_x32(s_base + (c + 1) * 32, sr[(c + 1) & 1]);
-              if (c < n_any) m_tile = fmaxf(m_tile, rowmax32(sr[c & 1], c >= n_full, j * BN + c * 32, limit));
+              if (!MT) {
+                m = fmaxf(m, rowmax32<false>(sr[c & 1], 0, 0));
+              } else if (c < n_any) {
+                m = fmaxf(m, c < n_full ? rowmax32<false>(sr[c & 1], 0, 0) : rowmax32<true>(sr[c & 1], j * BN + c * 32, limit));
+              }
             }
-          }
+            return m;
+          };
+          const float m_tile = masked_tile ? pass1(std::true_type{}) : pass1(std::false_type{});
           if (tr) p.trace[gx * 16 + 2] = clock64();
           // ---- lazy rescale: only move the reference max when it grew by more than 2^8 (always on the first tile)
           bool grow = (m_tile - m_cur) * scale_log2 > RESCALE_THRESHOLD;
@@ -663,7 +662,9 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           //      with it P_X is a buffer of its own: it must have been read by PV_X(j-1), and S_X is handed back to the
           //      tensor pipe as soon as its last chunk is in registers (half way through the exponentials).
           if (Cfg::EARLY_S && gx > 0) mbar_wait(&o_done[X], (gx - 1) & 1);
-          {
+          auto pass2 = [&](auto mt) {
+            constexpr bool MT = decltype(mt)::value;
+            float l = 0.f;
             uint32_t sr[2][32];
             tmem_ld_32x32b_x32(s_base, sr[0]);
 #pragma unroll
@@ -676,15 +677,21 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 tcgen05_fence_before();
                 mbar_arrive(&s_free[X]);
               }
-              if (c < n_any) {
-                l_sum += softmax_exp32<PV>(sr[c & 1], c < n_full, j * BN + c * 32, limit, scale_log2, m_scaled, pk);
+              if (!MT) {
+                l += softmax_exp32<PV, false>(sr[c & 1], 0, 0, scale_log2, m_scaled, pk);
+              } else if (c < n_full) {
+                l += softmax_exp32<PV, false>(sr[c & 1], 0, 0, scale_log2, m_scaled, pk);
+              } else if (c < n_any) {
+                l += softmax_exp32<PV, true>(sr[c & 1], j * BN + c * 32, limit, scale_log2, m_scaled, pk);
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) pk[i] = 0u;
               }
               tmem_st_32x32b_x16(p_base + c * 16, pk);
             }
-          }
+            return l;
+          };
+          l_sum += masked_tile ? pass2(std::true_type{}) : pass2(std::false_type{});
           if (tr) p.trace[gx * 16 + 3] = clock64();
           tmem_st_wait();
           tcgen05_fence_before();

@@ -394,6 +394,34 @@ int grid_for(long long total, int block) {
   return static_cast<int>(g);
 }
 
+// one warp per row: rstd = rsqrt(mean(x^2) + eps) (the squares are taken of the 16-bit values, summed in fp32)
+__global__ void __launch_bounds__(256) row_rstd_kernel(const bf16* __restrict__ x, int x_ld, float* __restrict__ rstd,
+                                                       int rows, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* xr = x + static_cast<size_t>(row) * x_ld;
+  float acc = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + c);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    acc += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y) + (cc.x * cc.x + cc.y * cc.y) + (d.x * d.x + d.y * d.y);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) rstd[row] = rsqrtf(acc / static_cast<float>(D) + eps);
+}
+
+// one warp per row: sums the row's partials in a fixed order (lane-strided, then the shuffle tree)
+__global__ void __launch_bounds__(256) sumsq_to_rstd_kernel(const float* __restrict__ partials, int parts,
+                                                            float* __restrict__ rstd, int rows, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* pr = partials + static_cast<size_t>(row) * parts;
+  float acc = 0.f;
+  for (int i = lane; i < parts; i += 32) acc += pr[i];
+  acc = warp_sum(acc);
+  if (lane == 0) rstd[row] = rsqrtf(acc / static_cast<float>(D) + eps);
+}
+
 }  // namespace
 
 int slime_launch_layernorm(const bf16* x, int x_ld, const bf16* w, const bf16* b, bf16* y, int y_ld,
@@ -411,6 +439,23 @@ int slime_launch_layernorm(const bf16* x, int x_ld, const bf16* w, const bf16* b
     layernorm_kernel<128, 8><<<rows, NT, 0, stream>>>(x, x_ld, w, b, y, y_ld, rows, D, eps, in_group,
                                                       in_group_stride, in_offset);
   }
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
+
+int slime_launch_row_rstd(const bf16* x, int x_ld, float* rstd, int rows, int D, float eps, cudaStream_t stream) {
+  SLIME_REQUIRE(D % 8 == 0 && x_ld % 8 == 0, "row_rstd: bad D=%d", D);
+  if (rows <= 0) return SLIME_OK;
+  row_rstd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, x_ld, rstd, rows, D, eps);
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
+
+int slime_launch_sumsq_to_rstd(const float* partials, int parts, float* rstd, int rows, int D, float eps,
+                               cudaStream_t stream) {
+  SLIME_REQUIRE(parts > 0 && parts <= 1024, "sumsq_to_rstd: bad parts=%d", parts);
+  if (rows <= 0) return SLIME_OK;
+  sumsq_to_rstd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(partials, parts, rstd, rows, D, eps);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

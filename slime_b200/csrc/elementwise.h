@@ -13,6 +13,13 @@ int slime_launch_layernorm(const bf16* x, int x_ld, const bf16* w, const bf16* b
 int slime_launch_rmsnorm(const bf16* x, int x_ld, const bf16* w, bf16* y, int y_ld, int rows, int D,
                          float eps, const int* src_rows, cudaStream_t stream);
 
+// Norm folding (gemm.h GemmParams::row_scale / sumsq_out):
+//   row_rstd        : rstd[r] = rsqrt(mean(x[r, :]^2) + eps) straight from the rows (first layer: no GEMM produced them)
+//   sumsq_to_rstd   : rstd[r] = rsqrt(sum(partials[r, 0..parts)) / D + eps) from the partials a residual GEMM's epilogue wrote
+int slime_launch_row_rstd(const bf16* x, int x_ld, float* rstd, int rows, int D, float eps, cudaStream_t stream);
+int slime_launch_sumsq_to_rstd(const float* partials, int parts, float* rstd, int rows, int D, float eps,
+                               cudaStream_t stream);
+
 // pixels [Nc,3,336,336] -> patches [Nc*576, Kpad] (k = c*196 + ky*14 + kx, zero padded to Kpad)
 int slime_launch_im2col(const bf16* pixels, bf16* patches, int Nc, int image, int patch, int Kpad,
                         cudaStream_t stream);

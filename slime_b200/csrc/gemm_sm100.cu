@@ -399,8 +399,16 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
                       p.row_map == nullptr && p.norm_ld % 8 == 0,
                   "gemm: bad fused-RMSNorm configuration");
 
+  const bool norm_fold = p.row_scale != nullptr || p.sumsq_out != nullptr;
+  if (norm_fold) {
+    SLIME_REQUIRE(p.out != nullptr && p.out_f32 == nullptr && p.row_map == nullptr,
+                  "gemm: norm folding needs a 16-bit output and no row map");
+    SLIME_REQUIRE(p.sumsq_out == nullptr || (epi == GEMM_EPI_NONE && p.N % 64 == 0 && p.sumsq_parts == p.N / 64),
+                  "gemm: sum-of-squares partials need EPI_NONE and N %% 64 == 0 (N=%d parts=%d)", p.N, p.sumsq_parts);
+    p.epi_mode = 0;  // the direct epilogue carries the hooks
+  }
   // Decode-step problems (M <= 32): HBM-bound weight streaming instead of 128-row tensor-core tiles.
-  if (p.M <= 32 && slime_gemm_skinny_applies(A, lda, W, ldw, p, epi, num_sms))
+  if (p.M <= 32 && !norm_fold && slime_gemm_skinny_applies(A, lda, W, ldw, p, epi, num_sms))
     return slime_launch_gemm_skinny(A, lda, W, ldw, p, epi, num_sms, stream);
   if (p.norm_w != nullptr) {  // not fusable here: GEMM, then the RMSNorm of its output rows
     GemmParams q = p_in;

@@ -25,6 +25,7 @@ from .weights import ALL_GROUPS, pack_weights
 
 
 FUSED_ROPE_DEFAULT = "1"  # RoPE in the QKV GEMM epilogue (SLIME_FUSED_ROPE=0: separate in-place pass)
+NORM_FOLD_DEFAULT = "1"   # Llama RMSNorms folded into the projections that follow them (SLIME_NORM_FOLD=0: separate passes)
 
 
 def _locked(fn):
@@ -66,7 +67,7 @@ class PrefillResult:
 
 class SlimeEngine:
     def __init__(self, cfg: SlimeConfig, device: int | str | torch.device = 0, max_pos: Optional[int] = None,
-                 dtype=torch.bfloat16, fused_rope: Optional[bool] = None):
+                 dtype=torch.bfloat16, fused_rope: Optional[bool] = None, norm_fold: Optional[bool] = None):
         cfg.validate()
         self.cfg = cfg
         self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
@@ -98,10 +99,15 @@ class SlimeEngine:
         if fused_rope is None:
             fused_rope = os.environ.get("SLIME_FUSED_ROPE", FUSED_ROPE_DEFAULT) not in ("0", "")
         self.fused_rope = bool(fused_rope)
+        # RMSNorm folding (weights.py / csrc/gemm.h): gamma into the qkv / gate-up weight columns, 1/rms in their epilogues
+        if norm_fold is None:
+            norm_fold = os.environ.get("SLIME_NORM_FOLD", NORM_FOLD_DEFAULT) not in ("0", "")
+        self.norm_fold = bool(norm_fold) and cfg.hidden_size % 64 == 0
         d.flags = ((L.SLIME_FLAG_LEFT_PAD if cfg.tokenizer_padding_side == "left" else 0)
                    | (L.SLIME_FLAG_USE_GLOBAL_ONLY if cfg.use_global_only else 0)
                    | (L.SLIME_FLAG_USE_LOCAL_ONLY if cfg.use_local_only else 0)
                    | (L.SLIME_FLAG_ROPE_INTERLEAVED if self.fused_rope else 0)
+                   | (L.SLIME_FLAG_NORM_FOLDED if self.norm_fold else 0)
                    | (L.SLIME_FLAG_ROUTER_QFORMER if cfg.mm_resampler_type == "qformer" else 0))
         self._desc = d
         self._ctx = C.c_void_p()
@@ -128,7 +134,8 @@ class SlimeEngine:
         """groups: which weight groups to register ("vit", "rs_local", "rs_global", "proj", "llm"); a stage
         whose group is absent fails loudly (used by the stand-alone module shims of slime_b200/model)."""
         with self._lock, torch.cuda.device(self.device):
-            self._register(pack_weights(self.cfg, get, self.device, groups, self.dtype, rope_interleaved=self.fused_rope))
+            self._register(pack_weights(self.cfg, get, self.device, groups, self.dtype, rope_interleaved=self.fused_rope,
+                                        norm_folded=self.norm_fold))
 
     def _register(self, weights: Dict[str, torch.Tensor]) -> None:
         """Hand the packed tensors to the library (borrowed pointers: self.weights keeps them alive) and let it
@@ -146,7 +153,7 @@ class SlimeEngine:
         """A second context over the SAME packed weights (no copy) with some configuration attributes changed -
         top-p, merge type, padding side, ... (everything that lives in slime_model_desc rather than in the weights)."""
         other = SlimeEngine(self.cfg.replace(**cfg_overrides), self.device, max_pos=self._desc.max_pos, dtype=self.dtype,
-                            fused_rope=self.fused_rope)
+                            fused_rope=self.fused_rope, norm_fold=self.norm_fold)
         other._register(self.weights)
         return other
 

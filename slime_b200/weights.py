@@ -8,6 +8,10 @@ Packing = one-time, load-time layout work done with torch tensor ops (plumbing):
   * Llama q/k (rope_interleaved): inside every head, rows (i, i + hd/2) made adjacent so the RoPE pair of
     HF's rotate_half (llama/modeling_llama.py:152-176) sits in adjacent accumulator columns and the rotation
     runs in the QKV GEMM's epilogue (SLIME_FLAG_ROPE_INTERLEAVED); q.k is invariant under the common permutation
+  * Llama RMSNorm weights (norm_folded): gamma of input_layernorm / post_attention_layernorm multiplied into the COLUMNS
+    of the qkv / gate-up weights (in fp32, rounded once); the prefill GEMMs then run on the un-normalised residual stream
+    and scale their output rows by 1/rms (SLIME_FLAG_NORM_FOLDED, csrc/gemm.h), the registered norm weights become ones
+    (the decode step's fused residual + RMSNorm multiplies by them)
   * CLIP patch conv [D,3,14,14] -> [D, 588] zero-padded to K = 640 (TMA needs 16-byte row strides)
   * Resampler key positions: the bicubic 12x12 -> 24x24 resize of the constant sincos table
     (reference multimodal_resampler/sampler.py:27-36,149-155) is input independent -> done here once
@@ -48,7 +52,7 @@ def rope_interleave_rows(w: torch.Tensor, head_dim: int) -> torch.Tensor:
 
 def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device,
                  groups=ALL_GROUPS, dtype: torch.dtype = torch.bfloat16,
-                 rope_interleaved: bool = False) -> Dict[str, torch.Tensor]:
+                 rope_interleaved: bool = False, norm_folded: bool = False) -> Dict[str, torch.Tensor]:
     """get(name) returns the reference tensor `name` (any dtype/device); returns canonical-name ->
     contiguous CUDA tensor (2-D) in the engine's 16-bit element type.  Tensors are pulled one at a time so a lazy source (e.g. the
     on-GPU synthetic generator) never holds two copies of the model."""
@@ -64,7 +68,7 @@ def pack_weights(cfg: SlimeConfig, get: Callable[[str], torch.Tensor], device,
         _pack_vit(cfg, g, out)
     _pack_adapter(cfg, g, out, device, groups, bf)
     if "llm" in groups:
-        _pack_llm(cfg, g, out, rope_interleaved)
+        _pack_llm(cfg, g, out, rope_interleaved, norm_folded)
     if "router" in groups and cfg.mm_resampler_type == "qformer":
         _pack_router(cfg, g, out)
     for k, t in out.items():
@@ -144,8 +148,14 @@ def _pack_router(cfg, g, out):
     out["router.fc2_b"] = g(r + "prob_proj.2.bias").reshape(1, 1)
 
 
-def _pack_llm(cfg, g, out, rope_interleaved=False):
+def _fold_gamma(w: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    """W[:, k] * gamma[k] in fp32, rounded once to W's dtype (norm folding)."""
+    return (w.float() * gamma.float().reshape(1, -1)).to(w.dtype).contiguous()
+
+
+def _pack_llm(cfg, g, out, rope_interleaved=False, norm_folded=False):
     H = cfg.hidden_size
+    ones = None
     perm = (lambda w: rope_interleave_rows(w, cfg.head_dim)) if rope_interleaved else (lambda w: w)
     out["llm.embed"] = g("model.embed_tokens.weight").contiguous()
     out["llm.norm_w"] = g("model.norm.weight").reshape(1, -1)
@@ -161,3 +171,10 @@ def _pack_llm(cfg, g, out, rope_interleaved=False):
         out[c + "down_w"] = g(p + "mlp.down_proj.weight").contiguous()
         out[c + "in_norm_w"] = g(p + "input_layernorm.weight").reshape(1, -1)
         out[c + "post_norm_w"] = g(p + "post_attention_layernorm.weight").reshape(1, -1)
+        if norm_folded:
+            out[c + "qkv_w"] = _fold_gamma(out[c + "qkv_w"], out[c + "in_norm_w"])
+            out[c + "gate_up_w"] = _fold_gamma(out[c + "gate_up_w"], out[c + "post_norm_w"])
+            if ones is None:
+                ones = torch.ones_like(out[c + "in_norm_w"])
+            out[c + "in_norm_w"] = ones
+            out[c + "post_norm_w"] = ones
