@@ -288,6 +288,18 @@ int slime_set_pdl_mode(int mode);
  * QKV weights, 4 / 8 = the attention kernel / the o-projection's finishing kernel pull 32 MB of gate/up each;
  * -1 = back to SLIME_DECODE_PREFETCH / the build default (0: measured slower than no prefetch in every variant). */
 int slime_set_decode_prefetch(int mask);
+/* ---- multi-GPU: the path's ONE collective - samples are independent, every rank runs the whole prefill on its
+ * shard of the batch, and the last-token logits are all-gathered over NCCL (NVLink 5 / NVSwitch).  The reference has no
+ * collective (N independent processes, outputs concatenated: scripts/llama/eval/gqa.sh:20-43).  NCCL is bound at run time
+ * (dlopen libnccl.so.2).  Bootstrap: rank 0 -> slime_comm_unique_id -> the 128 bytes travel by any side channel -> every rank
+ * slime_comm_init on its own device.  slime_allgather_logits only enqueues on `stream` (use a side stream: the next
+ * prefill does not depend on it): out [world * rows_local, vocab] fp32 in rank order. */
+typedef struct slime_comm slime_comm;
+int slime_comm_unique_id(void* out_128_bytes);
+int slime_comm_init(slime_comm** out, const void* id_128_bytes, int rank, int world);
+int slime_comm_nccl_version(void);
+int slime_allgather_logits(slime_comm* comm, const float* local_logits, float* out, int rows_local, int vocab, void* stream);
+void slime_comm_destroy(slime_comm* comm);
 /* debug: CTA 0 of the tcgen05 attention kernel stamps clock64() of its first 64 tiles into buf [64][16] (NULL = off) */
 int slime_attention_set_trace(long long* buf);
 /* softmax arithmetic of the tcgen05 attention kernel: 0 = scalar FFMA + MUFU.EX2; 5 / 9 = packed fp32 pairs

@@ -151,6 +151,11 @@ SIGNATURES = {
     "slime_attention_set_trace": (_i, [_vp]),
     "slime_attention_set_variant": (_i, [_i]),
     "slime_attention_set_poly": (_i, [_i]),
+    "slime_comm_unique_id": (_i, [_vp]),
+    "slime_comm_init": (_i, [C.POINTER(_vp), _vp, _i, _i]),
+    "slime_comm_nccl_version": (_i, []),
+    "slime_allgather_logits": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "slime_comm_destroy": (None, [_vp]),
     "slime_launch_count": (C.c_longlong, []),
     "slime_profile_enable": (_i, [_i]),
     "slime_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -82,7 +82,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         if _needs_rebuild(lib_path, vobjs):
             # -Bsymbolic: both libraries export the same names; each must bind its internal calls to itself
             cmd = [_nvcc(), "-shared", "-o", str(lib_path), *map(str, vobjs),
-                   "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic"]
+                   "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic", "-ldl"]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

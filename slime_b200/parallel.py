@@ -52,22 +52,71 @@ def gather_logits(local_logits: torch.Tensor, n_samples: int, group=None) -> tor
     return torch.cat([out[r * width: r * width + sizes[r]] for r in range(world)])
 
 
+class SlimeComm:
+    """NCCL communicator owned by libslime_b200 (include/slime_b200.h: slime_comm_*; NCCL bound with dlopen).  The 128-byte
+    unique id is created on rank 0 and reaches the other ranks through the torch.distributed store (bootstrap plumbing:
+    `dist.broadcast_object_list`, which works on any backend)."""
+
+    def __init__(self, device, dtype=None, group=None):
+        import ctypes as C
+
+        from . import _lib as L
+
+        self.lib = L.load(dtype)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_char * 128)()
+        if self.rank == 0:
+            L.check(self.lib.slime_comm_unique_id(buf), "comm_unique_id", self.lib)
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (C.c_char * 128).from_buffer_copy(box[0])
+        self._h = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(self.lib.slime_comm_init(C.byref(self._h), ident, self.rank, self.world), "comm_init", self.lib)
+
+    def allgather_logits(self, local: torch.Tensor, out: torch.Tensor, stream: "torch.cuda.Stream") -> None:
+        import ctypes as C
+
+        from . import _lib as L
+
+        assert local.dtype == torch.float32 and out.dtype == torch.float32 and local.is_contiguous() and out.is_contiguous()
+        assert out.shape[0] == self.world * local.shape[0] and out.shape[1] == local.shape[1]
+        L.check(self.lib.slime_allgather_logits(self._h, L.ptr(local), L.ptr(out), local.shape[0], local.shape[1],
+                                                C.c_void_p(stream.cuda_stream)), "allgather_logits", self.lib)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.slime_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LogitsGather:
     """The path's one exchange step, taken OFF the compute stream: the all-gather of the [B_local, V] last-token logits
     is issued on a side stream behind an event, so a rank's next prefill never waits for the slowest rank's previous
     one (on the compute stream the collective acts as a per-step barrier: every step then runs at the pace of the most
     power-throttled GPU).  `depth` result buffers rotate; result(slot) makes the calling stream wait for that gather.
     Equal block sizes on every rank (the benchmark's weak-scaling layout); gather_logits() handles ragged blocks.
+    On CUDA the collective is the library's own entry point (slime_allgather_logits over its NCCL communicator, SlimeComm);
+    `use_lib=False` falls back to torch.distributed's all_gather_into_tensor (same NCCL underneath).
     On CPU tensors (gloo tests) the gather simply runs synchronously."""
 
-    def __init__(self, rows: int, vocab: int, device, dtype=torch.float32, group=None, depth: int = 2):
+    def __init__(self, rows: int, vocab: int, device, dtype=torch.float32, group=None, depth: int = 2, use_lib: bool = True):
         self.group = group
+        self.comm = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = torch.device(device).type == "cuda"
         self.bufs = [torch.empty(self.world * rows, vocab, dtype=dtype, device=device) for _ in range(depth)]
         self.done = [None] * depth
         self.count = 0
         self.stream = torch.cuda.Stream(device) if self.cuda else None
+        if self.cuda and self.world > 1 and use_lib and dtype == torch.float32:
+            self.comm = SlimeComm(device, group=group)
 
     def submit(self, local_logits: torch.Tensor) -> int:
         slot = self.count % len(self.bufs)
@@ -83,7 +132,10 @@ class LogitsGather:
         self.stream.wait_event(ready)
         local_logits.record_stream(self.stream)  # allocated on the compute stream, consumed on the side stream
         with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(self.bufs[slot], local_logits, group=self.group)
+            if self.comm is not None:
+                self.comm.allgather_logits(local_logits.contiguous(), self.bufs[slot], self.stream)
+            else:
+                dist.all_gather_into_tensor(self.bufs[slot], local_logits, group=self.group)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self.done[slot] = ev
