@@ -302,11 +302,6 @@ int slime_allgather_logits(slime_comm* comm, const float* local_logits, float* o
 void slime_comm_destroy(slime_comm* comm);
 /* debug: CTA 0 of the tcgen05 attention kernel stamps clock64() of its first 64 tiles into buf [64][16] (NULL = off) */
 int slime_attention_set_trace(long long* buf);
-/* softmax arithmetic of the tcgen05 attention kernel: 0 = scalar FFMA + MUFU.EX2; 5 / 9 = packed fp32 pairs
- * (FFMA2 / FADD2) with 2 / 4 of every 8 pairs exponentiated by a polynomial on the FMA pipe instead of the SFU
- * (5 is the default); 21 = variant 5 with the kv tiles alternating between two softmax warp groups; 32 = measurement
- * only (no softmax, garbage output); -1 = back to the default (SLIME_ATTN_VARIANT / build default). */
-int slime_attention_set_variant(int variant);
 /* two-query-tile attention kernel (csrc/attention_tc2.cu): how many of every 8 score-column pairs are exponentiated by a
  * polynomial on the FMA pipe instead of MUFU.EX2 (0, 2, 3 or 4; -1 = back to SLIME_ATTN_POLY / the build default). */
 int slime_attention_set_poly(int pairs_of_8);

@@ -149,7 +149,6 @@ SIGNATURES = {
     "slime_set_pdl_mode": (_i, [_i]),
     "slime_set_decode_prefetch": (_i, [_i]),
     "slime_attention_set_trace": (_i, [_vp]),
-    "slime_attention_set_variant": (_i, [_i]),
     "slime_attention_set_poly": (_i, [_i]),
     "slime_comm_unique_id": (_i, [_vp]),
     "slime_comm_init": (_i, [C.POINTER(_vp), _vp, _i, _i]),

@@ -1186,7 +1186,8 @@ int slime_op_attention(const void* q, const void* k, const void* v, void* o, int
   ap.q_batch_rows = q_batch_rows; ap.k_batch_rows = k_batch_rows; ap.o_batch_rows = o_batch_rows;
   ap.batch = batch; ap.num_heads = heads; ap.num_kv_heads = kv_heads; ap.head_dim = head_dim;
   ap.scale = scale; ap.causal = causal;
-  ap.total_q_rows = total_q_rows; ap.total_k_rows = total_k_rows; ap.impl = impl;
+  ap.total_q_rows = total_q_rows; ap.total_k_rows = total_k_rows;
+  (void)impl;  // (kept in the signature: there is one prefill attention kernel now)
   return slime_launch_attention(ap, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,6 +1,6 @@
-// Dispatcher of the fused prefill attention (attention.h): argument checks + choice of the tcgen05 kernel.
-//   impl 3 (default): two query tiles per CTA sharing one K/V stream (attention_tc2.cu)
-//   impl 2          : one query tile per CTA (attention_tc.cu; round-1 kernel, kept for A/B until round 2 closes)
+// Entry of the fused prefill attention (attention.h): argument checks, then the tcgen05 kernel with two query tiles
+// per CTA sharing one K/V stream (attention_tc2.cu).  (The round-1 kernel - one query tile per CTA - lost on every shape
+// of the path and was removed: profiles/r02_attention_experiments.txt.)
 #include <cstdlib>
 
 #include "attention.h"
@@ -25,17 +25,11 @@ int slime_launch_attention(const AttnParams& p_in, cudaStream_t stream) {
                   reinterpret_cast<uintptr_t>(p.v) | reinterpret_cast<uintptr_t>(p.o)) & 15) == 0,
                 "attention: tensors must be 16-byte aligned");
   if (p.batch <= 0 || p.seqlen_q <= 0) return SLIME_OK;
-  static int env_impl = -1;
   static int num_sms = 0;
-  if (env_impl < 0) {
-    const char* e = getenv("SLIME_ATTN_IMPL");
-    env_impl = (e == nullptr || e[0] < '2' || e[0] > '3') ? SLIME_ATTN_DEFAULT_IMPL : e[0] - '0';
+  if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int impl = p.impl != 0 ? p.impl : env_impl;
-  SLIME_REQUIRE(impl == 2 || impl == 3, "attention: unknown implementation %d (2 = one query tile per CTA, 3 = two)", impl);
-  if (impl == 2) return slime_launch_attention_tc(p, num_sms, stream);
   return slime_launch_attention_tc2(p, num_sms, stream);
 }

@@ -1,25 +1,12 @@
-// Host-side interface of the fused attention kernels (attention_tc.cu, attention_tc2.cu, decode_attn.cu).
+// Host-side interface of the fused attention kernels (attention_tc2.cu, decode_attn.cu).
 #pragma once
 #include "common.cuh"
 
-// default implementation when neither AttnParams::impl nor SLIME_ATTN_IMPL selects one:
-// 2 = tcgen05 kernel with one query tile per CTA (attention_tc.cu), 3 = two query tiles per CTA (attention_tc2.cu)
-#ifndef SLIME_ATTN_DEFAULT_IMPL
-#define SLIME_ATTN_DEFAULT_IMPL 2
-#endif
 // attention_tc2.cu: how many of every 8 score-column pairs are exponentiated by a polynomial on the FMA pipe
 // instead of MUFU.EX2 (0, 2, 3 or 4).  Measured on B200 (profiles/r02_attention_experiments.txt): no share of polynomial
-// exponentials beats plain MUFU - the FFMA2 chain of the polynomial costs the FMA pipe as much as the two ex2 cost the XU.
+// 2 of 8 is the best share on every shape of the path (decoder 0.367 -> 0.315 ms, ViT 0.271 -> 0.242 ms).
 #ifndef SLIME_ATTN_POLY_DEFAULT
-#define SLIME_ATTN_POLY_DEFAULT 0
-#endif
-#undef SLIME_ATTN_DEFAULT_IMPL
-#define SLIME_ATTN_DEFAULT_IMPL 3
-
-// softmax arithmetic variant of the tcgen05 kernel (attention_tc.cu: 0 scalar MUFU, 1 + 2*P packed pairs with P of
-// every 8 pairs exponentiated on the FMA pipe)
-#ifndef SLIME_ATTN_VARIANT_DEFAULT
-#define SLIME_ATTN_VARIANT_DEFAULT 5
+#define SLIME_ATTN_POLY_DEFAULT 2
 #endif
 
 struct AttnParams {
@@ -41,13 +28,11 @@ struct AttnParams {
   int causal;    // 1: query i attends keys <= i + (seqlen_k - seqlen_q)
   long long total_q_rows = 0;  // rows of the q matrix (needed for the TMA map when cu_q != nullptr; 0 = derive)
   long long total_k_rows = 0;  // rows of the k / v matrices (same)
-  int impl = 0;                // 0 = default, 2 = one query tile per CTA, 3 = two query tiles per CTA
   long long* trace = nullptr;  // debug: CTA 0 writes clock64() stamps of its first 64 tiles here ([64][16])
 };
 
 int slime_launch_attention(const AttnParams& p, cudaStream_t stream);
-// tcgen05 / TMEM implementations (attention_tc.cu, attention_tc2.cu)
-int slime_launch_attention_tc(const AttnParams& p, int num_sms, cudaStream_t stream);
+// tcgen05 / TMEM implementation (attention_tc2.cu)
 int slime_launch_attention_tc2(const AttnParams& p, int num_sms, cudaStream_t stream);
 
 // ---- decode step (decode_attn.cu) ----

@@ -87,7 +87,7 @@ def _ref_attention(q, k, v, scale, causal):
     return torch.softmax(s, dim=-1) @ v
 
 
-@pytest.mark.parametrize("impl", [3, 2], ids=["two_q_tiles", "one_q_tile"])
+@pytest.mark.parametrize("impl", [0], ids=["two_q_tiles"])
 @pytest.mark.parametrize("shape", ["clip", "decoder_gqa"])
 def test_attention_fp16(impl, shape):
     torch.manual_seed(6)

@@ -1,9 +1,8 @@
-"""A/B on the GPU box: GEMM epilogue modes (direct vs staged) on the GEMM shapes of the path, and the softmax
-variants of the tcgen05 attention kernel on the decoder / ViT shapes.  Every alternative is first compared with
-the baseline output (max abs / rel-L2 difference), then timed with CUDA events (L2 flushed between repetitions by
-the working set itself: every shape moves > 126 MB).
+"""A/B on the GPU box: GEMM epilogue modes (direct vs staged) on the GEMM shapes of the path.  The staged output is first
+compared with the direct one (bit-identical), then both are timed with CUDA events (L2 flushed between repetitions by
+the working set itself: every shape moves > 126 MB).  (Attention: tools/attn_bench.py.)
 
-    python tools/ab_kernels.py [gemm] [attn]
+    python tools/ab_kernels.py
 """
 import os
 import sys
@@ -85,56 +84,6 @@ def gemm_ab():
     lib.slime_gemm_set_epi_mode(0)
 
 
-def attn_ab():
-    torch.manual_seed(0)
-    cases = []
-    L_, B, h, kvh, d = 1380, 16, 32, 8, 128
-    W = (h + 2 * kvh) * d
-    qkv = torch.randn(B * L_, W, device=dev).to(torch.bfloat16)
-    o = torch.empty(B * L_, h * d, device=dev, dtype=torch.bfloat16)
-    cu = torch.arange(0, (B + 1) * L_, L_, device=dev, dtype=torch.int32)
-    cases.append(("decoder 16x1380 causal 32/8x128", o, 4.0 * B * h * L_ * L_ * d * 0.5,
-                  (L.ptr(qkv), L.ptr(qkv[:, h * d:]), L.ptr(qkv[:, (h + kvh) * d:]), L.ptr(o), W, W, W, h * d, L.ptr(cu),
-                   L.ptr(cu), L_, L_, 0, 0, 0, B, h, kvh, d, d ** -0.5, 1, B * L_, B * L_, 2, L.stream_ptr()), (qkv, cu)))
-    S, Bv, hv, dv = 577, 80, 16, 64
-    D = hv * dv
-    qkv2 = torch.randn(Bv * S, 3 * D, device=dev).to(torch.bfloat16)
-    o2 = torch.empty(Bv * S, D, device=dev, dtype=torch.bfloat16)
-    cases.append(("vit 80x577 16x64", o2, 4.0 * Bv * hv * S * S * dv,
-                  (L.ptr(qkv2), L.ptr(qkv2[:, D:]), L.ptr(qkv2[:, 2 * D:]), L.ptr(o2), 3 * D, 3 * D, 3 * D, D, None, None, S, S,
-                   S, S, S, Bv, hv, hv, dv, dv ** -0.5, 0, 0, 0, 2, L.stream_ptr()), (qkv2,)))
-    # peaked scores (large logits) exercise the lazy rescale and very negative exponents in the polynomial path
-    qkv3 = (torch.randn(B * L_, W, device=dev) * 3.0).to(torch.bfloat16)
-    o3 = torch.empty(B * L_, h * d, device=dev, dtype=torch.bfloat16)
-    cases.append(("decoder, logits x9 (peaked)", o3, 4.0 * B * h * L_ * L_ * d * 0.5,
-                  (L.ptr(qkv3), L.ptr(qkv3[:, h * d:]), L.ptr(qkv3[:, (h + kvh) * d:]), L.ptr(o3), W, W, W, h * d, L.ptr(cu),
-                   L.ptr(cu), L_, L_, 0, 0, 0, B, h, kvh, d, d ** -0.5, 1, B * L_, B * L_, 2, L.stream_ptr()), (qkv3, cu)))
-    for name, out, fl, args, _keep in cases:
-        base = None
-        for var in [int(v) for v in os.environ.get("AB_VARIANTS", "0,5,9,21,32").split(",")]:
-            assert lib.slime_attention_set_variant(var) == 0
-
-            def f():
-                rc = lib.slime_op_attention(*args)
-                assert rc == 0, L.last_error()
-
-            out.zero_()
-            f()
-            torch.cuda.synchronize()
-            cur = out.clone()
-            if base is None:
-                base = cur
-            ms = timeit(f)
-            print(f"attn {name:34s} variant {var}: {ms:7.4f} ms ({fl / ms / 1e9:6.0f} TF/s)  vs variant 0: rel-L2 "
-                  f"{rel(cur, base):.2e} max|d| {float((cur.float() - base.float()).abs().max()):.3e} "
-                  f"finite={bool(torch.isfinite(cur.float()).all())}", flush=True)
-    lib.slime_attention_set_variant(-1)
-
-
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["gemm", "attn"]
     print(torch.cuda.get_device_name(0))
-    if "gemm" in what:
-        gemm_ab()
-    if "attn" in what:
-        attn_ab()
+    gemm_ab()

@@ -1,9 +1,9 @@
 """Attention kernels on the GPU box: correctness vs fp32 torch, CUDA-event timing and (optionally) the per-tile clock
 trace, for the shapes of the SliME path.
 
-    python tools/attn_bench.py [--impls 2,3] [--polys 0,2,3,4] [--trace]
+    python tools/attn_bench.py [--polys 0,2,3,4] [--trace]
 
-impl 2 = one query tile per CTA (attention_tc.cu), impl 3 = two query tiles per CTA (attention_tc2.cu).
+--polys: shares of polynomial exp2 to time (pairs of every 8 on the FMA pipe instead of MUFU.EX2).
 """
 import argparse
 import os
@@ -106,17 +106,15 @@ def cases():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--impls", default="2,3")
     ap.add_argument("--polys", default="2")
     ap.add_argument("--trace", action="store_true")
     a = ap.parse_args()
     print(torch.cuda.get_device_name(0))
     for name, out, fl, args, ref, nref, _keep in cases():
         r = ref()
-        for impl in [int(x) for x in a.impls.split(",")]:
-            for poly in ([int(x) for x in a.polys.split(",")] if impl == 3 else [None]):
-                if poly is not None:
-                    assert lib.slime_attention_set_poly(poly) == 0
+        for impl in (0,):
+            for poly in [int(x) for x in a.polys.split(",")]:
+                assert lib.slime_attention_set_poly(poly) == 0
 
                 def f():
                     rc = lib.slime_op_attention(*args(impl))
@@ -128,13 +126,13 @@ def main():
                 err = rel(out[:nref], r)
                 ms = timeit(f)
                 tf = fl / ms / 1e9
-                print(f"attn {name:40s} impl {impl} poly {poly}: {ms:7.4f} ms  {tf:6.0f} TF/s = {tf / PEAK_SUSTAINED:.2f} of "
+                print(f"attn {name:40s} poly {poly}: {ms:7.4f} ms  {tf:6.0f} TF/s = {tf / PEAK_SUSTAINED:.2f} of "
                       f"sustained peak   rel-L2 vs fp32 {err:.2e} finite={bool(torch.isfinite(out.float()).all())}", flush=True)
         lib.slime_attention_set_poly(-1)
         if a.trace and name.startswith(("decoder llama3", "vit")):
             tr = torch.zeros(64, 16, dtype=torch.int64, device=dev)
             lib.slime_attention_set_trace(L.ptr(tr))
-            lib.slime_op_attention(*args(3))
+            lib.slime_op_attention(*args(0))
             torch.cuda.synchronize()
             lib.slime_attention_set_trace(None)
             t = tr.cpu()

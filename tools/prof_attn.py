@@ -5,7 +5,7 @@ import torch
 from slime_b200 import _lib as L
 lib = L.load()
 which = sys.argv[1] if len(sys.argv) > 1 else "decoder"
-IMPL = int(sys.argv[2]) if len(sys.argv) > 2 else 3  # 3 = two query tiles per CTA, 2 = one
+IMPL = 0
 if which == "decoder":
     L_, B, h, kvh, d = 1380, 16, 32, 8, 128
     W = (h + 2 * kvh) * d
