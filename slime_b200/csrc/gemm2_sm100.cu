@@ -19,10 +19,13 @@ namespace {
 
 #include "gemm2_common.cuh"
 
-template <int EPI, bool STAGED>
+template <int BLOCK_N, int EPI, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p, const int group_m, const int l2_hint) {
+  using Cfg = Gemm2Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, TMEM_COLS = Cfg::TMEM_COLS,
+                EPI_OFF = Cfg::EPI_OFF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
@@ -33,7 +36,6 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint8_t* epi_stage = smem + EPI_OFF;  // [NUM_EPI_WARPS][EPI_STAGE_BYTES]
-  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block");
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,9 +164,10 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
-template <int EPI, bool STAGED>
+template <int BLOCK_N, int EPI, bool STAGED>
 int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_tn_2cta_kernel<EPI, STAGED>;
+  constexpr int SMEM_BYTES = Gemm2Cfg<BLOCK_N>::SMEM_BYTES;
+  auto kern = gemm_bf16_tn_2cta_kernel<BLOCK_N, EPI, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     SLIME_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -187,32 +190,51 @@ int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, 
   return SLIME_OK;
 }
 
-template <int EPI>
+template <int BLOCK_N, int EPI>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  if (p.epi_mode != 0 && p.out_f32 == nullptr) return launch2s<EPI, true>(ta, tb, p, num_sms, stream);
-  return launch2s<EPI, false>(ta, tb, p, num_sms, stream);
+  if (p.epi_mode != 0 && p.out_f32 == nullptr) return launch2s<BLOCK_N, EPI, true>(ta, tb, p, num_sms, stream);
+  return launch2s<BLOCK_N, EPI, false>(ta, tb, p, num_sms, stream);
+}
+
+template <int BLOCK_N>
+int launch2n(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  SLIME_PROPAGATE(slime_get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
+  SLIME_PROPAGATE(slime_get_tmap(W, p.N, p.K, ldw, BLOCK_N / 2, &tb));
+  switch (epi) {
+    case GEMM_EPI_NONE:
+      return launch2<BLOCK_N, GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_QUICK_GELU:
+      return launch2<BLOCK_N, GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_GELU_ERF:
+      return launch2<BLOCK_N, GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_SWIGLU:
+      return launch2<BLOCK_N, GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_ROPE:
+      return launch2<BLOCK_N, GEMM_EPI_ROPE>(ta, tb, p, num_sms, stream);
+    default:
+      slime_set_error("unknown GEMM epilogue %d", epi);
+      return SLIME_EINVAL;
+  }
 }
 
 }  // namespace
 
 int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms,
                            cudaStream_t stream) {
-  CUtensorMap ta, tb;
-  SLIME_PROPAGATE(slime_get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
-  SLIME_PROPAGATE(slime_get_tmap(W, p.N, p.K, ldw, BLOCK_N / 2, &tb));
-  switch (epi) {
-    case GEMM_EPI_NONE:
-      return launch2<GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
-    case GEMM_EPI_QUICK_GELU:
-      return launch2<GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
-    case GEMM_EPI_GELU_ERF:
-      return launch2<GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
-    case GEMM_EPI_SWIGLU:
-      return launch2<GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
-    case GEMM_EPI_ROPE:
-      return launch2<GEMM_EPI_ROPE>(ta, tb, p, num_sms, stream);
-    default:
-      slime_set_error("unknown GEMM epilogue %d", epi);
-      return SLIME_EINVAL;
+  // 256 x 256 cluster tiles unless they leave the last wave so empty that half-width tiles (three short waves instead of
+  // two long ones, ...) finish sooner; the half-width tile is ~8 % less efficient per FLOP (SLIME_GEMM2_BN forces one)
+  static int force_bn = -1;
+  if (force_bn < 0) {
+    const char* e = getenv("SLIME_GEMM2_BN");
+    force_bn = e != nullptr ? atoi(e) : 0;
   }
+  const int clusters = num_sms / 2;
+  const long long m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const long long t256 = m_tiles * ((p.N + 255) / 256), t128 = m_tiles * ((p.N + 127) / 128);
+  const double waves256 = static_cast<double>((t256 + clusters - 1) / clusters);        // in units of a 256-wide tile
+  const double waves128 = static_cast<double>((t128 + clusters - 1) / clusters) * 0.5 * 1.08;
+  const bool use128 = force_bn == 128 || (force_bn != 256 && waves128 < waves256 && p.N >= 128);
+  if (use128) return launch2n<128>(A, lda, W, ldw, p, epi, num_sms, stream);
+  return launch2n<256>(A, lda, W, ldw, p, epi, num_sms, stream);
 }
