@@ -2,11 +2,13 @@
 #pragma once
 #include "common.cuh"
 
-// attention_tc2.cu: how many of every 8 score-column pairs are exponentiated by a polynomial on the FMA pipe
-// instead of MUFU.EX2 (0, 2, 3 or 4).  Measured on B200 (profiles/r02_attention_experiments.txt): no share of polynomial
-// 2 of 8 is the best share on every shape of the path (decoder 0.367 -> 0.315 ms, ViT 0.271 -> 0.242 ms).
-#ifndef SLIME_ATTN_POLY_DEFAULT
-#define SLIME_ATTN_POLY_DEFAULT 2
+// attention_tc2.cu: how many of every 8 score-column pairs are exponentiated by a polynomial on the FMA pipe instead of
+// MUFU.EX2 (0, 2, 3 or 4), by head dim - the measured optimum on B200 (profiles/r02_attention_experiments.txt)
+#ifndef SLIME_ATTN_POLY_HD128
+#define SLIME_ATTN_POLY_HD128 3
+#endif
+#ifndef SLIME_ATTN_POLY_HD64
+#define SLIME_ATTN_POLY_HD64 2
 #endif
 
 struct AttnParams {

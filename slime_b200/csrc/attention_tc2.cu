@@ -836,21 +836,24 @@ int launch2q_var(const AttnParams& p, int num_sms, cudaStream_t stream) {
   return SLIME_OK;
 }
 
-int g_poly = -1;  // pairs of every 8 exponentiated on the FMA pipe (-1: SLIME_ATTN_POLY or the compile-time default)
+int g_poly = -2;  // pairs of every 8 exponentiated on the FMA pipe (-2: not read yet; -1: by head dim; SLIME_ATTN_POLY)
 
 template <int HD, bool CAUSAL>
 int launch2q(const AttnParams& p, int num_sms, cudaStream_t stream) {
-  if (g_poly < 0) {
+  if (g_poly == -2) {
     const char* e = getenv("SLIME_ATTN_POLY");
-    g_poly = e != nullptr ? atoi(e) : SLIME_ATTN_POLY_DEFAULT;
+    g_poly = e != nullptr ? atoi(e) : -1;
   }
-  switch (g_poly) {
+  // measured best share (profiles/r02_attention_experiments.txt): 3 of 8 at hd 128 (decoder 0.370 / 0.317 / 0.298 / 0.342 ms
+  // for 0 / 2 / 3 / 4), 2 of 8 at hd 64 (ViT 0.291 / 0.260 / 0.269 / 0.288 ms)
+  const int poly = g_poly >= 0 ? g_poly : (HD == 128 ? SLIME_ATTN_POLY_HD128 : SLIME_ATTN_POLY_HD64);
+  switch (poly) {
     case 0: return launch2q_var<HD, CAUSAL, 0>(p, num_sms, stream);
     case 2: return launch2q_var<HD, CAUSAL, 2>(p, num_sms, stream);
     case 3: return launch2q_var<HD, CAUSAL, 3>(p, num_sms, stream);
     case 4: return launch2q_var<HD, CAUSAL, 4>(p, num_sms, stream);
     default:
-      slime_set_error("attention: unknown polynomial share %d (0, 2, 3 or 4 of every 8 pairs)", g_poly);
+      slime_set_error("attention: unknown polynomial share %d (0, 2, 3 or 4 of every 8 pairs)", poly);
       return SLIME_EINVAL;
   }
 }

@@ -67,11 +67,6 @@ struct GemmParams {
 #define SLIME_GEMM_2CTA_DEFAULT 2
 #endif
 
-// L2 cache hints of the 2-CTA kernel's operand loads (bit 0: A evict_last, bit 1: W evict_first); SLIME_GEMM_L2HINT overrides
-#ifndef SLIME_GEMM_L2HINT_DEFAULT
-#define SLIME_GEMM_L2HINT_DEFAULT 0
-#endif
-
 // Returns 0 on success; negative SLIME_E* otherwise (message via slime_set_error).
 int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                       int num_sms, cudaStream_t stream);
@@ -85,9 +80,9 @@ bool slime_gemm_skinny_applies(const bf16* A, int lda, const bf16* W, int ldw, c
 int slime_launch_gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                              int num_sms, cudaStream_t stream);
 
-// Epilogue access pattern used by slime_launch_gemm (SLIME_GEMM_EPI_MODE overrides the compile-time default).
+// Epilogue access pattern used by slime_launch_gemm: 0 direct, 1 staged, 2 chosen by shape (SLIME_GEMM_EPI_MODE overrides).
 #ifndef SLIME_GEMM_EPI_MODE_DEFAULT
-#define SLIME_GEMM_EPI_MODE_DEFAULT 0
+#define SLIME_GEMM_EPI_MODE_DEFAULT 2
 #endif
 
 // m-tiles per rasterisation group for a problem with reduction length K (see gemm_sm100.cu)

@@ -4,28 +4,19 @@
 #pragma once
 
 constexpr int BLOCK_M = 128;      // rows per CTA (256 per cluster tile)
+constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
+constexpr int STAGES = 6;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
+constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KB: this CTA's half of the W tile
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TMEM_COLS = 2 * BLOCK_N;
+constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;  // barriers + TMEM holder live in the 256 bytes before it
+constexpr int SMEM_BYTES = 1024 + EPI_OFF + NUM_EPI_WARPS * 4096;  // + the epilogue staging tiles
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0
-
-// Cluster tile 256 x BLOCK_N.  256 columns is the throughput shape (UMMA 256 x 256 x 16, 64 B/clk of operand traffic per
-// SM); 128 columns halves the tile for problems whose 256-wide tiles leave the last wave nearly empty (a batch-1 prefill:
-// M = 1379 rows x N = 4096 is 96 tiles for 74 clusters - two waves, the second 30 % full; as 192 half tiles it is three
-// waves of half the length).
-template <int BLOCK_N>
-struct Gemm2Cfg {
-  static constexpr int STAGES = BLOCK_N == 256 ? 6 : 8;
-  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the W tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;  // barriers + TMEM holder live in the 256 bytes before it
-  static constexpr int SMEM_BYTES = 1024 + EPI_OFF + NUM_EPI_WARPS * 4096;  // + the epilogue staging tiles
-  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block");
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-};
 
 #include "gemm_epilogue.cuh"
 
@@ -63,24 +54,6 @@ SLIME_DEVINL void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t
       " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
       : "memory");
-}
-SLIME_DEVINL void tma_load_2d_2sm_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                       uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-SLIME_DEVINL uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
-  return p;
-}
-SLIME_DEVINL uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
-  return p;
 }
 SLIME_DEVINL void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                    uint32_t accumulate) {

@@ -10,8 +10,6 @@
 //   warp 1 (leader)   : issues tcgen05.mma.cta_group::2; commits multicast to both CTAs' barriers
 //   warps 2..9 (both) : epilogue of the CTA's own 128 rows (gemm_epilogue.cuh), arriving on the leader's
 //                       tmem_empty barrier
-#include <cstdlib>
-
 #include "errors.h"
 #include "gemm.h"
 
@@ -19,13 +17,10 @@ namespace {
 
 #include "gemm2_common.cuh"
 
-template <int BLOCK_N, int EPI, bool STAGED>
+template <int EPI, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmParams p, const int group_m, const int l2_hint) {
-  using Cfg = Gemm2Cfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, TMEM_COLS = Cfg::TMEM_COLS,
-                EPI_OFF = Cfg::EPI_OFF;
+                         const GemmParams p, const int group_m) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
@@ -36,6 +31,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint8_t* epi_stage = smem + EPI_OFF;  // [NUM_EPI_WARPS][EPI_STAGE_BYTES]
+  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block");
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,9 +70,6 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // L2 cache hints of the operand loads (SLIME_GEMM_L2HINT, measurement knob; 0 = none): bit 0 = the A panel of the
-      // rasterisation group is re-read by every n-tile -> evict_last; bit 1 = W streams past once per group -> evict_first
-      const uint64_t pol_a = (l2_hint & 1) ? l2_policy_evict_last() : 0, pol_b = (l2_hint & 2) ? l2_policy_evict_first() : 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const TileCoord tc = tile_coord(t, num_m, num_n, group_m);
         const int m_row = tc.m_blk * 2 * BLOCK_M + rank * BLOCK_M;          // this CTA's 128 rows of A
@@ -88,10 +81,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           } else {
             mbar_arrive_leader(&full_bar[stage]);
           }
-          if (l2_hint & 1) tma_load_2d_2sm_hint(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row, pol_a);
-          else tma_load_2d_2sm(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row);
-          if (l2_hint & 2) tma_load_2d_2sm_hint(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row, pol_b);
-          else tma_load_2d_2sm(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row);
+          tma_load_2d_2sm(smem_a + stage * A_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_row);
+          tma_load_2d_2sm(smem_b + stage * B_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_row);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -164,10 +155,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
-template <int BLOCK_N, int EPI, bool STAGED>
+template <int EPI, bool STAGED>
 int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  constexpr int SMEM_BYTES = Gemm2Cfg<BLOCK_N>::SMEM_BYTES;
-  auto kern = gemm_bf16_tn_2cta_kernel<BLOCK_N, EPI, STAGED>;
+  auto kern = gemm_bf16_tn_2cta_kernel<EPI, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     SLIME_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -179,62 +169,38 @@ int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, 
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   slime_prof_begin(0, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-  static int l2_hint = -1;
-  if (l2_hint < 0) {
-    const char* e = getenv("SLIME_GEMM_L2HINT");
-    l2_hint = e != nullptr ? atoi(e) & 3 : SLIME_GEMM_L2HINT_DEFAULT;
-  }
-  kern<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, slime_gemm_group_m(p.K, 2 * BLOCK_M), l2_hint);
+  kern<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, slime_gemm_group_m(p.K, 2 * BLOCK_M));
   slime_prof_end(stream);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
 
-template <int BLOCK_N, int EPI>
+template <int EPI>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  if (p.epi_mode != 0 && p.out_f32 == nullptr) return launch2s<BLOCK_N, EPI, true>(ta, tb, p, num_sms, stream);
-  return launch2s<BLOCK_N, EPI, false>(ta, tb, p, num_sms, stream);
-}
-
-template <int BLOCK_N>
-int launch2n(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms, cudaStream_t stream) {
-  CUtensorMap ta, tb;
-  SLIME_PROPAGATE(slime_get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
-  SLIME_PROPAGATE(slime_get_tmap(W, p.N, p.K, ldw, BLOCK_N / 2, &tb));
-  switch (epi) {
-    case GEMM_EPI_NONE:
-      return launch2<BLOCK_N, GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
-    case GEMM_EPI_QUICK_GELU:
-      return launch2<BLOCK_N, GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
-    case GEMM_EPI_GELU_ERF:
-      return launch2<BLOCK_N, GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
-    case GEMM_EPI_SWIGLU:
-      return launch2<BLOCK_N, GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
-    case GEMM_EPI_ROPE:
-      return launch2<BLOCK_N, GEMM_EPI_ROPE>(ta, tb, p, num_sms, stream);
-    default:
-      slime_set_error("unknown GEMM epilogue %d", epi);
-      return SLIME_EINVAL;
-  }
+  if (p.epi_mode != 0 && p.out_f32 == nullptr) return launch2s<EPI, true>(ta, tb, p, num_sms, stream);
+  return launch2s<EPI, false>(ta, tb, p, num_sms, stream);
 }
 
 }  // namespace
 
 int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms,
                            cudaStream_t stream) {
-  // 256 x 256 cluster tiles unless they leave the last wave so empty that half-width tiles (three short waves instead of
-  // two long ones, ...) finish sooner; the half-width tile is ~8 % less efficient per FLOP (SLIME_GEMM2_BN forces one)
-  static int force_bn = -1;
-  if (force_bn < 0) {
-    const char* e = getenv("SLIME_GEMM2_BN");
-    force_bn = e != nullptr ? atoi(e) : 0;
+  CUtensorMap ta, tb;
+  SLIME_PROPAGATE(slime_get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
+  SLIME_PROPAGATE(slime_get_tmap(W, p.N, p.K, ldw, BLOCK_N / 2, &tb));
+  switch (epi) {
+    case GEMM_EPI_NONE:
+      return launch2<GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_QUICK_GELU:
+      return launch2<GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_GELU_ERF:
+      return launch2<GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_SWIGLU:
+      return launch2<GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
+    case GEMM_EPI_ROPE:
+      return launch2<GEMM_EPI_ROPE>(ta, tb, p, num_sms, stream);
+    default:
+      slime_set_error("unknown GEMM epilogue %d", epi);
+      return SLIME_EINVAL;
   }
-  const int clusters = num_sms / 2;
-  const long long m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  const long long t256 = m_tiles * ((p.N + 255) / 256), t128 = m_tiles * ((p.N + 127) / 128);
-  const double waves256 = static_cast<double>((t256 + clusters - 1) / clusters);        // in units of a 256-wide tile
-  const double waves128 = static_cast<double>((t128 + clusters - 1) / clusters) * 0.5 * 1.08;
-  const bool use128 = force_bn == 128 || (force_bn != 256 && waves128 < waves256 && p.N >= 128);
-  if (use128) return launch2n<128>(A, lda, W, ldw, p, epi, num_sms, stream);
-  return launch2n<256>(A, lda, W, ldw, p, epi, num_sms, stream);
 }

@@ -346,8 +346,8 @@ static int g_mode_2cta = -1;  // -1: read SLIME_GEMM_2CTA / the compile-time def
 static int g_epi_mode = -1;   // -1: read SLIME_GEMM_EPI_MODE / the compile-time default on first use
 
 extern "C" int slime_gemm_set_epi_mode(int mode) {
-  if (mode < 0 || mode > 1) {
-    slime_set_error("gemm epilogue mode %d not in {0,1}", mode);
+  if (mode < -1 || mode > 2) {
+    slime_set_error("gemm epilogue mode %d not in {-1 (default), 0 direct, 1 staged, 2 by shape}", mode);
     return SLIME_EINVAL;
   }
   g_epi_mode = mode;
@@ -367,10 +367,16 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
                       int num_sms, cudaStream_t stream) {
   if (g_epi_mode < 0) {
     const char* e = getenv("SLIME_GEMM_EPI_MODE");
-    g_epi_mode = (e != nullptr && e[0] >= '0' && e[0] <= '1') ? e[0] - '0' : SLIME_GEMM_EPI_MODE_DEFAULT;
+    g_epi_mode = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : SLIME_GEMM_EPI_MODE_DEFAULT;
   }
   GemmParams p = p_in;
-  p.epi_mode = p.out_f32 != nullptr ? 0 : g_epi_mode;  // fp32 outputs always go direct
+  // epilogue access pattern: 0 direct, 1 staged through shared memory (coalesced), 2 = by shape - staged where the A/B on
+  // B200 shows it ahead: the ViT-sized problems (tens of thousands of rows with K <= 1024 or N <= 1024, whose epilogue
+  // traffic is large next to their few k-blocks: qkv +12 %, fc2 +5 %, fc1 +2 %), direct for the decoder's K >= 4096
+  // GEMMs (down-projection -17 % when staged) and for small M (profiles/r02_gemm_epilogue_ab.txt)
+  int mode = g_epi_mode;
+  if (mode == 2) mode = (p_in.M >= 16384 && (p_in.K <= 1024 || p_in.N <= 1024)) ? 1 : 0;
+  p.epi_mode = p.out_f32 != nullptr ? 0 : mode;  // fp32 outputs always go direct
   SLIME_REQUIRE(A != nullptr && W != nullptr, "gemm: null operand");
   SLIME_REQUIRE(p.out != nullptr || p.out_f32 != nullptr, "gemm: no output pointer");
   SLIME_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
