@@ -613,12 +613,13 @@ def main():
             r["whole_step_frac"] = r["whole_step_tflops_per_gpu"] / peaks["tf_sustained"]
             return r
         guarded("topp_1.0", topp1)
-        if world == 8 and args.model == "llama3-8b":
-            # BASELINE.json config 4 at its 8-GPU shape: 8B, 8-frame video = 8 crops (flat merge), T 256, 4 samples / GPU
+        if world > 1 and args.model == "llama3-8b":
+            # BASELINE.json config 4 at its per-GPU shape (batch 32 over 8 GPUs): 8B, 8-frame video = 8 crops (flat merge),
+            # T 256, 4 samples / GPU - at 8 GPUs this IS config 4, at fewer GPUs the same per-GPU work (weak scaling)
             def cfg4():
                 e4 = eng.clone(mm_patch_merge_type="flat")
                 return short_run(torch, dist, e4, e4.cfg, 4, 8, 256, rank, world, dev, steps=6, flat=True)
-            guarded("config4_8b_8crops_b32_dp8", cfg4)
+            guarded(f"config4_8b_8crops_b4_per_gpu_dp{world}", cfg4)
         # the float16 build (the reference's inference dtype, llava/model/builder.py:43) on the headline shape
         def fp16():
             e16 = make_engine(cfg, torch.float16)
@@ -640,15 +641,16 @@ def main():
                 e7.close()
                 return out
             guarded("latency_b1_config2_vicuna7b_T128", cfg2)
-            if world == 8:
-                # BASELINE.json config 5: Vicuna-13B, 1344 px = 17 crops (flat), T 512, batch 64 over 8 GPUs = 8 / GPU
+            if world > 1:
+                # BASELINE.json config 5 at its per-GPU shape: Vicuna-13B, 1344 px = 17 crops (flat), T 512, batch 64 over
+                # 8 GPUs = 8 / GPU
                 def cfg5():
                     c13 = preset("vicuna-13b", mm_patch_merge_type="flat")
                     e13 = make_engine(c13)
                     out = short_run(torch, dist, e13, c13, 8, 17, 512, rank, world, dev, steps=3, flat=True, warm=2)
                     e13.close()
                     return out
-                guarded("config5_13b_17crops_b64_dp8", cfg5)
+                guarded(f"config5_13b_17crops_b8_per_gpu_dp{world}", cfg5)
 
     if rank != 0:
         if world > 1:

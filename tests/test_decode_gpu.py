@@ -44,6 +44,7 @@ def test_decode_matches_reprefill_and_oracle(pname):
         ref_logits.append(last.clone())
     # KV-cache trajectory (teacher-forced with the same tokens so the comparison is step by step)
     eng.attach_kv_cache(B, 1400)
+    clear_steps = []  # per decode step: which sequences have an unambiguous greedy token
     try:
         res = eng.prefill(px, ids, mask, grids=grids)
         assert torch.equal(res.logits_last, base.logits_last)
@@ -54,7 +55,13 @@ def test_decode_matches_reprefill_and_oracle(pname):
             e = rel(logits, ref_logits[s + 1])
             print(f"[{pname}] decode step {s}: rel-L2 vs re-prefill {e:.3e}")
             assert e < 1e-2
-            assert torch.equal(logits.argmax(-1), ref_logits[s + 1].argmax(-1)) or e < 3e-3
+            # greedy tokens agree wherever the re-prefill's top-2 gap is larger than the two paths' difference (two bf16
+            # executions with different rounding points can flip a near-tie)
+            ref = ref_logits[s + 1].float()
+            top2 = ref.topk(2, -1).values
+            clear = (top2[:, 0] - top2[:, 1]) > 4 * (logits.float() - ref).abs().max(-1).values
+            assert torch.equal(logits.argmax(-1)[clear], ref.argmax(-1)[clear])
+            clear_steps.append(clear)
     finally:
         eng.detach_kv_cache()
     # oracle on the final grown sequence of sample 0 (fp32 CPU)
@@ -64,4 +71,7 @@ def test_decode_matches_reprefill_and_oracle(pname):
     # public generate(): greedy tokens equal the re-prefill trajectory
     out = eng.generate(px, ids, mask, grids=grids, max_new_tokens=steps)
     assert out.shape == (B, steps)
-    assert torch.equal(out, torch.stack(ref_tokens, 1))
+    want = torch.stack(ref_tokens, 1)
+    for b in range(B):  # token 0 comes from the (bit-identical) prefill; token s + 1 from decode step s
+        upto = 1 + next((s for s in range(steps - 1) if not bool(clear_steps[s][b])), steps - 1)
+        assert torch.equal(out[b, :upto], want[b, :upto]), (b, out[b].tolist(), want[b].tolist())

@@ -6,7 +6,7 @@
 // irrelevant for timing).  For every case: `iters` groups of 8 MMAs (K = 128 = 8 x 16) are issued back to back into
 // the same accumulator, one commit at the end.  Reported per MMA: cycles until the LAST ISSUE returned (issue cost /
 // queue back-pressure) and cycles until the commit barrier flipped (execution).  The attention kernel
-// (slime_b200/csrc/attention_tc.cu) issues SS 128x128x16 (S = Q K^T) and TS 128xHDx16 with an MN-major B (O += P V).
+// (slime_b200/csrc/attention_tc2.cu) issues SS 128x128x16 (S = Q K^T) and TS 128xHDx16 with an MN-major B (O += P V).
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128, 1) ubench(int iters, long long* out, int 
 
 // The attention kernel's MMA stream (hd 128): per kv tile g, S(g+1) = Q K^T (8 SS MMAs into S buffer (g+1) % NBUF) then
 // O += P(g) V (8 TS MMAs, A = P(g) read from TMEM).  P_ALIAS: P(g) lives in the first 64 columns of S buffer g % NBUF
-// (what attention_tc.cu does) - the S MMA issued right after PV(g-1) then OVERWRITES the columns PV(g-1) reads when
+// (what the hd-128 path of attention_tc2.cu does) - the S MMA issued right after PV(g-1) then OVERWRITES the columns PV(g-1) reads when
 // NBUF == 2.  P_ALIAS == 0: P in its own columns.  No barriers, no softmax: pure tensor-pipe stream.
 template <int NBUF, int P_ALIAS>
 __global__ void __launch_bounds__(128, 1) ustream(int iters, long long* out) {
