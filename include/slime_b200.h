@@ -242,12 +242,24 @@ int slime_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, int m, 
                          int splits, float* ws, size_t ws_floats, const void* norm_w, void* norm_out, float norm_eps,
                          const int32_t* rope_pos, const float* rope_table, int rope_half, int rope_cols, int rope_max_pos,
                          void* stream);
+/* Same with the fused decode chain's options: tile_counters ([n / 8] ints, zero on entry, zero again on exit) finishes
+ * the split-K sum inside the kernel; a_norm_w ([k]) applies RMSNorm(a_norm_eps) to the rows of a while they are staged. */
+int slime_op_gemm_skinny_fused(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
+                               const void* residual, int res_ld, int epilogue, void* out, float* out_f32, int out_ld,
+                               int splits, float* ws, size_t ws_floats, const void* norm_w, void* norm_out, float norm_eps,
+                               const int32_t* rope_pos, const float* rope_table, int rope_half, int rope_cols,
+                               int rope_max_pos, int32_t* tile_counters, const void* a_norm_w, float a_norm_eps,
+                               void* stream);
 /* Single-query attention over a KV cache [batch, cache_len, kv_heads * head_dim]: sequence b attends its first
  * lens[b] + 1 positions.  splits >= 1: split-KV kernel (ws = batch * heads * splits * (head_dim + 2) floats when
  * splits > 1); splits == 0: one CTA per (q head, sequence). */
 int slime_op_decode_attention(const void* q, int q_ld, const void* kcache, const void* vcache, int cache_len,
                               const int32_t* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
                               void* out, int out_ld, int splits, float* ws, void* stream);
+/* merge_counters ([batch * kv_heads] ints, zero on entry and exit): the kv splits are merged inside the kernel. */
+int slime_op_decode_attention_fused(const void* q, int q_ld, const void* kcache, const void* vcache, int cache_len,
+                                    const int32_t* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
+                                    void* out, int out_ld, int splits, float* ws, int32_t* merge_counters, void* stream);
 int slime_op_attention(const void* q, const void* k, const void* v, void* o, int q_ld, int k_ld, int v_ld,
                        int o_ld, const int32_t* cu_q, const int32_t* cu_k, int seqlen_q, int seqlen_k,
                        int64_t q_batch_rows, int64_t k_batch_rows, int64_t o_batch_rows, int batch,
@@ -288,6 +300,11 @@ int slime_set_pdl_mode(int mode);
  * QKV weights, 4 / 8 = the attention kernel / the o-projection's finishing kernel pull 32 MB of gate/up each;
  * -1 = back to SLIME_DECODE_PREFETCH / the build default (0: measured slower than no prefetch in every variant). */
 int slime_set_decode_prefetch(int mask);
+/* Decode-step launch chain: 1 (default) = fused - 5 launches per layer, split-K partials and attention kv splits are
+ * finished inside the producing kernels (atomic ticket, fixed summation order), RMSNorm applied while the consuming
+ * projection stages its rows; 0 = one finishing launch per split reduction (9 per layer); -1 = back to the default /
+ * SLIME_DECODE_FUSED. */
+int slime_set_decode_fused(int on);
 /* ---- multi-GPU: the path's ONE collective - samples are independent, every rank runs the whole prefill on its
  * shard of the batch, and the last-token logits are all-gathered over NCCL (NVLink 5 / NVSwitch).  The reference has no
  * collective (N independent processes, outputs concatenated: scripts/llama/eval/gqa.sh:20-43).  NCCL is bound at run time

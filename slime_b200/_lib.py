@@ -135,7 +135,10 @@ SIGNATURES = {
     "slime_op_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "slime_op_gemm_skinny": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _f,
                                   _vp, _vp, _i, _i, _i, _vp]),
+    "slime_op_gemm_skinny_fused": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp,
+                                        _f, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _vp]),
     "slime_op_decode_attention": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _i, _vp, _vp]),
+    "slime_op_decode_attention_fused": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp]),
     "slime_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i64, _i64, _i64, _i, _i, _i,
                                 _i, _f, _i, _i64, _i64, _i, _vp]),
     "slime_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
@@ -148,6 +151,7 @@ SIGNATURES = {
     "slime_decode_attention_set_mode": (_i, [_i]),
     "slime_set_pdl_mode": (_i, [_i]),
     "slime_set_decode_prefetch": (_i, [_i]),
+    "slime_set_decode_fused": (_i, [_i]),
     "slime_attention_set_trace": (_i, [_vp]),
     "slime_attention_set_poly": (_i, [_i]),
     "slime_comm_unique_id": (_i, [_vp]),

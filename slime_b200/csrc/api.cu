@@ -141,6 +141,10 @@ struct GemmExtra {
   // prefill norm folding (gemm.h): per-row 1/rms applied by the epilogue; partial sums of squares of the output rows
   const float* row_scale = nullptr;
   float* sumsq_out = nullptr;
+  // fused decode chain (gemm.h): in-kernel split-K finish, RMSNorm of the A rows while they are staged
+  int* tile_counters = nullptr;
+  const bf16* a_norm_w = nullptr;
+  float a_norm_eps = 0.f;
 };
 
 int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
@@ -159,6 +163,9 @@ int gemm(slime_ctx* c, const bf16* A, int lda, const bf16* W, int ldw, int M, in
     p.row_scale = ex->row_scale;
     p.sumsq_out = ex->sumsq_out;
     p.sumsq_parts = ex->sumsq_out != nullptr ? N / 64 : 0;
+    p.tile_counters = ex->tile_counters;
+    p.a_norm_w = ex->a_norm_w;
+    p.a_norm_eps = ex->a_norm_eps;
   }
   p.M = M; p.N = N; p.K = K;
   p.bias = bias;
@@ -203,6 +210,9 @@ int qkv_rope(slime_ctx* c, const bf16* x, const bf16* qkv_w, int rows, const int
     p.kv_dim = d.kv_heads * hd;
     p.kv_q_cols = d.heads * hd;
     p.row_scale = ex->row_scale;
+    p.tile_counters = ex->tile_counters;
+    p.a_norm_w = ex->a_norm_w;
+    p.a_norm_eps = ex->a_norm_eps;
   }
   p.M = rows; p.N = QKV; p.K = H;
   p.bias = nullptr;
@@ -519,6 +529,21 @@ int decode_prefetch_mask() {
 // gemm_skinny.cu for B <= 32, attention on the split-KV kernel of decode_attn.cu; 7-8 launches per layer -
 //   qkv (+RoPE, K/V append) [+ split-K finish] | attention [+ split merge] | o-proj + finish(residual, RMSNorm) |
 //   gate/up (SwiGLU) | down-proj + finish(residual, next layer's RMSNorm).
+// Fused chain (default, SLIME_DECODE_FUSED=0 / slime_set_decode_fused(0) restores the chain above): 5 launches per layer.
+// The finishing kernels disappear - split-K partials are summed by the warp that delivers a tile's last partial and the
+// kv splits of the attention by the last CTA of a (sequence, kv head), both by atomic ticket and in a fixed order - and
+// the RMSNorms move into the activation staging of the projection that consumes them (every CTA normalises the <= 32
+// rows it stages; the residual stream h is the only activation buffer between layers):
+//   qkv (RMSNorm in, RoPE, K/V append) | attention | o-proj (+residual) | gate/up (RMSNorm in, SwiGLU) | down (+residual).
+int g_decode_fused = -1;
+bool decode_fused_mode() {
+  if (g_decode_fused < 0) {
+    const char* e = getenv("SLIME_DECODE_FUSED");
+    g_decode_fused = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_decode_fused != 0;
+}
+
 int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B, float* logits, cudaStream_t s) {
   const slime_model_desc& d = c->d;
   const int H = d.hidden, I = d.mlp, hd = d.head_dim;
@@ -540,14 +565,48 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
   const int asplits = slime_decode_attention_splits(B, d.heads, d.kv_heads, hd, cache_len, c->num_sms);
   const int asplits_max = slime_decode_attention_splits(B, d.heads, d.kv_heads, hd, d.max_pos, c->num_sms);
   float* aws = a.get<float>(slime_decode_attention_ws_floats(B, d.heads, asplits_max > asplits ? asplits_max : asplits));
+  // tickets of the fused chain: one int per 8-column tile of the widest projection + one per (sequence, kv head)
+  const size_t n_tile_cnt = wide / 8 + 1;
+  const size_t n_cnt = n_tile_cnt + static_cast<size_t>(B > 0 ? B : 1) * d.kv_heads;
+  int* counters = a.get<int>(n_cnt);
   ARENA_CHECK(a, "decode");
   if (a.dry || B <= 0) return SLIME_OK;
+  const bool fused = decode_fused_mode() && B <= 32 && asplits >= 1 && H % 32 == 0 && I % 32 == 0 && slime_gemm_skinny_enabled();
   SLIME_CHECK_CUDA(cudaMemcpyAsync(h, x_in, static_cast<size_t>(B) * H * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+  if (fused) SLIME_CHECK_CUDA(cudaMemsetAsync(counters, 0, n_cnt * sizeof(int), s));
   const size_t plane = static_cast<size_t>(c->kv_cache_batch) * c->kv_cache_len * KD;
   GemmExtra ex;
   ex.splitk_ws = skws;
   ex.splitk_ws_floats = sk_floats;
   const int pf = decode_prefetch_mask();
+  if (fused) {
+    ex.tile_counters = counters;
+    GemmExtra exa = ex;  // projections that read the residual stream through an RMSNorm
+    exa.a_norm_eps = d.rms_eps;
+    for (int l = 0; l < d.layers; ++l) {
+      const LlmLayer& L = c->llm[l];
+      bf16* kc = c->kv_cache + (static_cast<size_t>(l) * 2 + 0) * plane;
+      bf16* vc = c->kv_cache + (static_cast<size_t>(l) * 2 + 1) * plane;
+      GemmExtra exq = exa;
+      exq.a_norm_w = L.in_norm_w;
+      exq.kv_k = kc;
+      exq.kv_v = vc;
+      exq.kv_lens = lens;
+      exq.kv_cache_len = c->kv_cache_len;
+      SLIME_PROPAGATE(qkv_rope(c, h, L.qkv_w, B, lens, qkv, s, &exq));
+      SLIME_PROPAGATE(slime_launch_decode_attention(qkv, QKV, kc, vc, c->kv_cache_len, lens, B, d.heads, d.kv_heads, hd,
+                                                    1.0f / sqrtf(static_cast<float>(hd)), att, QD, asplits, aws, nullptr, 0, s,
+                                                    counters + n_tile_cnt));
+      SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, B, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s, &ex));
+      exa.a_norm_w = L.post_norm_w;
+      SLIME_PROPAGATE(gemm(c, h, H, L.gate_up_w, H, B, 2 * I, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_SWIGLU, act,
+                           nullptr, I, s, &exa));
+      SLIME_PROPAGATE(gemm(c, act, I, L.down_w, I, B, H, I, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s, &ex));
+    }
+    exa.a_norm_w = c->llm_norm_w;
+    return gemm(c, h, H, c->llm_lm_head, H, B, d.vocab, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_NONE, nullptr, logits,
+                d.vocab, s, &exa);
+  }
   SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, c->llm[0].in_norm_w, t, H, B, H, d.rms_eps, nullptr, s));
   for (int l = 0; l < d.layers; ++l) {
     const LlmLayer& L = c->llm[l];
@@ -1127,12 +1186,31 @@ int slime_set_decode_prefetch(int mask) {
   return SLIME_OK;
 }
 
+int slime_set_decode_fused(int on) {
+  g_decode_fused = on < 0 ? -1 : (on != 0 ? 1 : 0);
+  return SLIME_OK;
+}
+
 int slime_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
                          const void* residual, int res_ld, int epilogue, void* out, float* out_f32, int out_ld,
                          int splits, float* ws, size_t ws_floats, const void* norm_w, void* norm_out, float norm_eps,
                          const int32_t* rope_pos, const float* rope_table, int rope_half, int rope_cols, int rope_max_pos,
                          void* stream) {
+  return slime_op_gemm_skinny_fused(a, lda, w, ldw, m, n, k, bias, residual, res_ld, epilogue, out, out_f32, out_ld, splits,
+                                    ws, ws_floats, norm_w, norm_out, norm_eps, rope_pos, rope_table, rope_half, rope_cols,
+                                    rope_max_pos, nullptr, nullptr, 0.f, stream);
+}
+
+int slime_op_gemm_skinny_fused(const void* a, int lda, const void* w, int ldw, int m, int n, int k, const void* bias,
+                               const void* residual, int res_ld, int epilogue, void* out, float* out_f32, int out_ld,
+                               int splits, float* ws, size_t ws_floats, const void* norm_w, void* norm_out, float norm_eps,
+                               const int32_t* rope_pos, const float* rope_table, int rope_half, int rope_cols,
+                               int rope_max_pos, int32_t* tile_counters, const void* a_norm_w, float a_norm_eps,
+                               void* stream) {
   GemmParams p;
+  p.tile_counters = tile_counters;
+  p.a_norm_w = static_cast<const bf16*>(a_norm_w);
+  p.a_norm_eps = a_norm_eps;
   p.M = m; p.N = n; p.K = k;
   p.bias = static_cast<const bf16*>(bias);
   p.residual = static_cast<const bf16*>(residual);
@@ -1165,10 +1243,17 @@ int slime_op_gemm_skinny(const void* a, int lda, const void* w, int ldw, int m, 
 int slime_op_decode_attention(const void* q, int q_ld, const void* kcache, const void* vcache, int cache_len,
                               const int32_t* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
                               void* out, int out_ld, int splits, float* ws, void* stream) {
+  return slime_op_decode_attention_fused(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, head_dim, scale,
+                                         out, out_ld, splits, ws, nullptr, stream);
+}
+
+int slime_op_decode_attention_fused(const void* q, int q_ld, const void* kcache, const void* vcache, int cache_len,
+                                    const int32_t* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
+                                    void* out, int out_ld, int splits, float* ws, int32_t* merge_counters, void* stream) {
   return slime_launch_decode_attention(static_cast<const bf16*>(q), q_ld, static_cast<const bf16*>(kcache),
                                        static_cast<const bf16*>(vcache), cache_len, lens, batch, heads, kv_heads,
                                        head_dim, scale, static_cast<bf16*>(out), out_ld, splits, ws, nullptr, 0,
-                                       static_cast<cudaStream_t>(stream));
+                                       static_cast<cudaStream_t>(stream), merge_counters);
 }
 
 int slime_op_attention(const void* q, const void* k, const void* v, void* o, int q_ld, int k_ld, int v_ld, int o_ld,

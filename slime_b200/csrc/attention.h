@@ -45,7 +45,9 @@ int slime_launch_attention_tc2(const AttnParams& p, int num_sms, cudaStream_t st
 int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, const bf16* vcache, int cache_len,
                                   const int* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
                                   bf16* out, int out_ld, int splits, float* ws, const void* pf_ptr, size_t pf_bytes,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, int* merge_counters = nullptr);
+// merge_counters: [batch * kv_heads] ints, zero on entry and on exit - the mma.sync split-KV kernel then merges the kv
+// splits itself (last CTA of a (sequence, kv head) by atomic ticket, fixed split order) and no merge kernel is launched.
 // (pf_ptr, pf_bytes): optional immutable region (a later projection's weights) the split-KV kernel pulls into L2
 // kv splits that fill the GPU for this problem (0: the split kernel does not apply / is switched off)
 int slime_decode_attention_splits(int batch, int heads, int kv_heads, int head_dim, int cache_len, int num_sms);

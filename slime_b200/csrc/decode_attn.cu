@@ -318,8 +318,10 @@ __global__ void __launch_bounds__(NT) decode_attn_mma_kernel(const bf16* __restr
                                                              const bf16* __restrict__ vcache, int cache_len,
                                                              const int* __restrict__ lens, int heads, int kv_heads, int G,
                                                              float scale_log2, int splits, float* __restrict__ part,
-                                                             bf16* __restrict__ out, int out_ld) {
+                                                             bf16* __restrict__ out, int out_ld,
+                                                             int* __restrict__ counters) {
   extern __shared__ __align__(16) uint8_t ds_smem[];
+  __shared__ int s_last;
   pdl_trigger();
   pdl_wait();  // q, the cache rows appended in this step and lens come from the kernels before
 
@@ -467,6 +469,50 @@ __global__ void __launch_bounds__(NT) decode_attn_mma_kernel(const bf16* __restr
       }
     }
   }
+  if (part == nullptr || counters == nullptr) return;
+  // ---- in-kernel merge of the kv splits (no merge launch): the CTA that takes the last ticket of its (sequence, kv head)
+  //      combines the partial states of ALL splits in split order - same arithmetic whoever comes last ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counters + b * kv_heads + kvh, 1) == splits - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float* s_w = reinterpret_cast<float*>(ds_smem);  // [8][32] per-split weight 2^(m_s - M); first the raw m_s
+  float* s_ls = s_w + 8 * 32;                      // [8][32] l_s
+  float* s_lt = s_ls + 8 * 32;                     // [8]
+  const float* pbase = part + (static_cast<long long>(b) * heads + kvh * G) * splits * (DS_HD + 2);
+  for (int idx = threadIdx.x; idx < G * splits; idx += NT) {  // round trip 1: (m_s, l_s) of every head and split
+    const int gi = idx / splits, sp = idx - gi * splits;
+    const float* pp = pbase + (static_cast<long long>(gi) * splits + sp) * (DS_HD + 2);
+    s_w[gi * 32 + sp] = __ldcg(pp + DS_HD);
+    s_ls[gi * 32 + sp] = __ldcg(pp + DS_HD + 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int gi = threadIdx.x;
+    float mt = -INFINITY;
+    for (int sp = 0; sp < splits; ++sp) mt = fmaxf(mt, s_w[gi * 32 + sp]);
+    float lt = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {  // fixed order over the splits: deterministic
+      const float ms = s_w[gi * 32 + sp];
+      const float a = (ms == -INFINITY) ? 0.f : exp2f(ms - mt);
+      s_w[gi * 32 + sp] = a;
+      lt += s_ls[gi * 32 + sp] * a;
+    }
+    s_lt[gi] = lt;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * DS_HD; idx += NT) {  // round trip 2: the partial accumulators
+    const int gi = idx / DS_HD, e = idx % DS_HD;
+    const float* pp = pbase + static_cast<long long>(gi) * splits * (DS_HD + 2) + e;
+    float val = 0.f;
+#pragma unroll 8
+    for (int sp = 0; sp < splits; ++sp) val += __ldcg(pp + sp * (DS_HD + 2)) * s_w[gi * 32 + sp];
+    const float lt = s_lt[gi];
+    out[static_cast<long long>(b) * out_ld + (kvh * G + gi) * DS_HD + e] = float_to_elem(lt > 0.f ? val / lt : 0.f);
+  }
+  if (threadIdx.x == 0) counters[b * kv_heads + kvh] = 0;  // zero again for the next launch
 }
 
 // out[b, head] = sum_s acc_s 2^(m_s - M) / sum_s l_s 2^(m_s - M)   (fixed order over the splits)
@@ -615,7 +661,7 @@ size_t slime_decode_attention_ws_floats(int batch, int heads, int splits) {
 int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, const bf16* vcache, int cache_len,
                                   const int* lens, int batch, int heads, int kv_heads, int head_dim, float scale,
                                   bf16* out, int out_ld, int splits, float* ws, const void* pf_ptr, size_t pf_bytes,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, int* merge_counters) {
   SLIME_REQUIRE(head_dim == 64 || head_dim == 128, "decode attention: head_dim %d unsupported", head_dim);
   if (batch <= 0) return SLIME_OK;
   const float sl2 = scale * 1.4426950408889634f;
@@ -637,10 +683,12 @@ int slime_launch_decode_attention(const bf16* q, int q_ld, const bf16* kcache, c
       }
       const cudaError_t le = slime_launch_kernel(decode_attn_mma_kernel, dim3(kv_heads, batch, splits), dim3(NT), DM_SMEM, stream,
                                                  true, q, q_ld, kcache, vcache, cache_len, lens, heads, kv_heads, G, sl2,
-                                                 splits, splits > 1 ? ws : static_cast<float*>(nullptr), out, out_ld);
+                                                 splits, splits > 1 ? ws : static_cast<float*>(nullptr), out, out_ld,
+                                                 splits > 1 ? merge_counters : static_cast<int*>(nullptr));
       slime_prof_end(stream);
       SLIME_CHECK_CUDA(le);
       SLIME_AFTER_LAUNCH();
+      if (merge_counters != nullptr) return SLIME_OK;  // the kv splits were merged inside the kernel
     } else {
     switch (G) {
       case 1: rc = launch_split<1>(q, q_ld, kcache, vcache, cache_len, lens, batch, heads, kv_heads, sl2, splits, ws, out, out_ld, pf_ptr, pf_bytes, stream); break;

@@ -42,6 +42,15 @@ struct GemmParams {
   float* splitk_ws = nullptr;   // optional fp32 scratch for split-K partial sums [splits, M, N]
   size_t splitk_ws_floats = 0;  // its capacity; too small / absent: the problem runs unsplit
   int force_splits = 0;         // tests: > 0 forces the weight-streaming kernel with this many k-splits
+  // In-kernel split-K finish (no finishing launch): [N / 8] ints, ZERO on entry and zero again on exit.  The warp that
+  // delivers the last partial of an 8-column tile (atomic ticket) adds all partials in split order - so the result does
+  // not depend on which warp came last - and runs the epilogue.
+  int* tile_counters = nullptr;
+  // RMSNorm of the A rows on their way into shared memory (weight-streaming path only; the decode step's
+  // input_layernorm / post_attention_layernorm / final norm, HF modeling_llama.py:62-67):
+  //   staged row = a_norm_w * elem(A[m] * rsqrt(mean(A[m]^2) + a_norm_eps)), the mean over all K columns.
+  const bf16* a_norm_w = nullptr;
+  float a_norm_eps = 0.f;
   // optional RMSNorm of the output rows (EPI_NONE, bf16 out): norm_out = norm_w * bf16(out * rsqrt(mean(out^2) + eps)).
   // Fused into the split-K finishing kernel on the weight-streaming path, a separate rmsnorm launch otherwise.
   const bf16* norm_w = nullptr;
@@ -76,6 +85,7 @@ int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const
 
 // Weight-streaming kernel for M <= 32 rows (gemm_skinny.cu; the decode step).  slime_launch_gemm routes to it when
 // slime_gemm_skinny_applies(); SLIME_GEMM_SKINNY=0 / slime_gemm_set_skinny_mode(0) keep such problems on the tcgen05 path.
+bool slime_gemm_skinny_enabled();
 bool slime_gemm_skinny_applies(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms);
 int slime_launch_gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                              int num_sms, cudaStream_t stream);

@@ -112,8 +112,9 @@ SLIME_DEVINL void skinny_store(const GemmParams& p, int epi, int m, int n, float
 template <int MT, bool HALF>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, const GemmParams p,
-                   int epi, int splits, int kc, int xs_stride, float* __restrict__ partial) {
+                   int epi, int splits, int kc, int xs_stride, float* __restrict__ partial, int* __restrict__ counters) {
   extern __shared__ __align__(16) uint8_t sk_smem[];
+  __shared__ float s_rstd[32];
   bf16* xs = reinterpret_cast<bf16*>(sk_smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
   const int split = blockIdx.x % splits, cta = blockIdx.x / splits, ctas = gridDim.x / splits;
@@ -138,6 +139,29 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
   pdl_trigger();
   pdl_wait();
 
+  // ---- optional RMSNorm of the A rows (a_norm_w): 1/rms of every FULL row (all K columns, not only this k-split),
+  //      one warp per row, every load of a lane issued before the first use ----
+  const bool a_norm = p.a_norm_w != nullptr;
+  if (a_norm) {
+    const int chunks_k = p.K >> 3;
+    for (int r = warp; r < p.M; r += SK_WARPS) {
+      const uint4* row = reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * lda);
+      float sq = 0.f;
+      for (int c0 = lane; c0 < chunks_k; c0 += 32 * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (c0 + 32 * j < chunks_k) ? __ldcg(row + c0 + 32 * j) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = unpack_bf16x2(v[j].x), b = unpack_bf16x2(v[j].y), c2 = unpack_bf16x2(v[j].z), d = unpack_bf16x2(v[j].w);
+          sq += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c2.x * c2.x + c2.y * c2.y + d.x * d.x + d.y * d.y;
+        }
+      }
+      sq = warp_sum(sq);
+      if (lane == 0) s_rstd[r] = rsqrtf(sq / static_cast<float>(p.K) + p.a_norm_eps);
+    }
+    __syncthreads();
+  }
   // ---- stage the activations of this k-split (rows >= M are zero) ----
   {
     const int chunks = klen >> 3;
@@ -145,7 +169,19 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
     for (int idx = tid; idx < total; idx += SK_THREADS) {
       const int r = idx / chunks, ch = idx - r * chunks;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (r < p.M) v = __ldcg(reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * lda + ks + ch * 8));
+      if (r < p.M) {
+        v = __ldcg(reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * lda + ks + ch * 8));
+        if (a_norm) {  // HF: weight * (x * rstd).to(dtype)
+          const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(p.a_norm_w + ks + ch * 8));
+          const float rs = s_rstd[r];
+          auto nrm = [rs](uint32_t x, uint32_t gw) {
+            const float2 xf = unpack_bf16x2(x), gf = unpack_bf16x2(gw);
+            const float a = elem_to_float(float_to_elem(xf.x * rs)), b = elem_to_float(float_to_elem(xf.y * rs));
+            return pack_bf16x2(gf.x * a, gf.y * b);
+          };
+          v = make_uint4(nrm(v.x, g4.x), nrm(v.y, g4.y), nrm(v.z, g4.z), nrm(v.w, g4.w));
+        }
+      }
       *reinterpret_cast<uint4*>(xs + static_cast<size_t>(r) * xs_stride + ch * 8) = v;
     }
   }
@@ -214,6 +250,38 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
             skinny_store(p, epi, m, n, acc[mt][2 * h], acc[mt][2 * h + 1]);
           }
         }
+      }
+    }
+    if (partial != nullptr && counters != nullptr) {
+      // ---- in-kernel finish: the warp holding the last ticket of this tile sums the partials of ALL splits in split
+      //      order (its own included, read back like the others: the sum does not depend on who is last) ----
+      __threadfence();
+      __syncwarp();
+      int ticket = 0;
+      if (lane == 0) ticket = atomicAdd(counters + t, 1);
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      if (ticket == splits - 1) {
+        __threadfence();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int m = mt * 16 + g + h * 8;
+            if (m < p.M) {
+              const float* src = partial + static_cast<size_t>(m) * p.N + n;
+              const size_t sstride = static_cast<size_t>(p.M) * p.N;
+              float v0 = 0.f, v1 = 0.f;
+#pragma unroll 4
+              for (int s = 0; s < splits; ++s) {
+                const float2 tt = __ldcg(reinterpret_cast<const float2*>(src + s * sstride));
+                v0 += tt.x;
+                v1 += tt.y;
+              }
+              skinny_store(p, epi, m, n, v0, v1);
+            }
+          }
+        }
+        if (lane == 0) counters[t] = 0;  // zero again for the next launch that uses the array
       }
     }
   }
@@ -361,6 +429,8 @@ SkinnyPlan make_plan(const bf16* A, int lda, const bf16* W, int ldw, const GemmP
                             p.kv_q_cols % 2 != 0 || p.kv_q_cols + 2 * p.kv_dim != p.N))
     return pl;
   const bool fused_norm = p.norm_w != nullptr;
+  if (p.a_norm_w != nullptr && (p.K % 8 != 0 || p.M > 32)) return pl;
+  if (fused_norm && p.tile_counters != nullptr) return pl;  // one or the other
   if (fused_norm && (epi != GEMM_EPI_NONE || p.out == nullptr || p.out_f32 != nullptr || p.norm_out == nullptr ||
                      p.N > 8192 || p.norm_ld % 2 != 0))
     return pl;
@@ -414,7 +484,8 @@ int launch_skinny(const bf16* A, int lda, const bf16* W, int ldw, const GemmPara
   slime_prof_begin(2, static_cast<double>(p.N) * p.K * sizeof(bf16), stream);
   const cudaError_t le = slime_launch_kernel(gemm_skinny_kernel<MT, HALF>, dim3(ctas), dim3(SK_THREADS), smem, stream, true, A, lda,
                                              W, ldw, p, epi, pl.splits, pl.kc, pl.xs_stride,
-                                             pl.use_partial ? p.splitk_ws : static_cast<float*>(nullptr));
+                                             pl.use_partial ? p.splitk_ws : static_cast<float*>(nullptr),
+                                             pl.use_partial ? p.tile_counters : static_cast<int*>(nullptr));
   slime_prof_end(stream);
   SLIME_CHECK_CUDA(le);
   SLIME_AFTER_LAUNCH();
@@ -427,6 +498,8 @@ extern "C" int slime_gemm_set_skinny_mode(int mode) {
   g_skinny_mode = mode < 0 ? -1 : (mode != 0 ? 1 : 0);
   return SLIME_OK;
 }
+
+bool slime_gemm_skinny_enabled() { return skinny_enabled(); }
 
 bool slime_gemm_skinny_applies(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                                int num_sms) {
@@ -450,7 +523,7 @@ int slime_launch_gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, con
   } else {
     SLIME_PROPAGATE((launch_skinny<2, false>(A, lda, W, ldw, p, epi, pl, num_sms, stream)));
   }
-  if (!pl.use_partial) return SLIME_OK;
+  if (!pl.use_partial || p.tile_counters != nullptr) return SLIME_OK;  // finished in the kernel
   const float* part = p.splitk_ws;
   const int pf_ctas = (p.l2_prefetch != nullptr && p.l2_prefetch_bytes > 0) ? num_sms / 2 : 0;
   if (p.norm_w != nullptr) {

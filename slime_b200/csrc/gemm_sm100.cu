@@ -416,6 +416,8 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
   // Decode-step problems (M <= 32): HBM-bound weight streaming instead of 128-row tensor-core tiles.
   if (p.M <= 32 && !norm_fold && slime_gemm_skinny_applies(A, lda, W, ldw, p, epi, num_sms))
     return slime_launch_gemm_skinny(A, lda, W, ldw, p, epi, num_sms, stream);
+  SLIME_REQUIRE(p.a_norm_w == nullptr, "gemm: the RMSNorm of the A rows exists on the weight-streaming path only "
+                "(M=%d N=%d K=%d does not qualify)", p.M, p.N, p.K);
   if (p.norm_w != nullptr) {  // not fusable here: GEMM, then the RMSNorm of its output rows
     GemmParams q = p_in;
     q.norm_w = nullptr;

@@ -25,8 +25,10 @@ def rnd(*shape, scale=1.0):
     return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
 
 
-def skinny(a, w, splits=1, bias=None, residual=None, epi=0, f32=False, out=None, norm_w=None, eps=1e-5, rope=None):
-    """rope = (pos int32 [M], table fp32 [max_pos, half, 2], half, cols)"""
+def skinny(a, w, splits=1, bias=None, residual=None, epi=0, f32=False, out=None, norm_w=None, eps=1e-5, rope=None,
+           counters=None, a_norm_w=None):
+    """rope = (pos int32 [M], table fp32 [max_pos, half, 2], half, cols); counters (int32 [N / 8], zero): split-K sum
+    finished inside the kernel; a_norm_w [K]: RMSNorm(eps) of the rows of a while they are staged"""
     L = _L()
     lib = L.load()
     M, K = a.shape
@@ -37,11 +39,15 @@ def skinny(a, w, splits=1, bias=None, residual=None, epi=0, f32=False, out=None,
     ws = torch.empty(max(1, splits * M * N), device="cuda", dtype=torch.float32)
     norm_out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if norm_w is not None else None
     pos, table, half, rcols = rope if rope is not None else (None, None, 0, 0)
-    rc = lib.slime_op_gemm_skinny(L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), M, N, K, L.ptr(bias), L.ptr(residual),
-                                  residual.stride(0) if residual is not None else 0, epi,
-                                  None if f32 else L.ptr(out), L.ptr(out) if f32 else None, out.stride(0), splits,
-                                  L.ptr(ws), ws.numel(), L.ptr(norm_w), L.ptr(norm_out), eps, L.ptr(pos), L.ptr(table),
-                                  half, rcols, table.shape[0] if table is not None else 0, L.stream_ptr())
+    args = (L.ptr(a), a.stride(0), L.ptr(w), w.stride(0), M, N, K, L.ptr(bias), L.ptr(residual),
+            residual.stride(0) if residual is not None else 0, epi,
+            None if f32 else L.ptr(out), L.ptr(out) if f32 else None, out.stride(0), splits,
+            L.ptr(ws), ws.numel(), L.ptr(norm_w), L.ptr(norm_out), eps, L.ptr(pos), L.ptr(table),
+            half, rcols, table.shape[0] if table is not None else 0)
+    if counters is None and a_norm_w is None:
+        rc = lib.slime_op_gemm_skinny(*args, L.stream_ptr())
+    else:
+        rc = lib.slime_op_gemm_skinny_fused(*args, L.ptr(counters), L.ptr(a_norm_w), eps, L.stream_ptr())
     L.check(rc, "op_gemm_skinny")
     torch.cuda.synchronize()
     return (out, norm_out) if norm_w is not None else out
@@ -170,19 +176,126 @@ def test_skinny_gemm_rope_epilogue(M, splits):
     assert rel_l2(out, ref) < 4e-3
 
 
-def decode_attention(q, kc, vc, lens, heads, kv_heads, splits):
+def decode_attention(q, kc, vc, lens, heads, kv_heads, splits, counters=None):
     L = _L()
     lib = L.load()
     B, cache_len = kc.shape[0], kc.shape[1]
     hd = 128
     out = torch.zeros(B, heads * hd, device="cuda", dtype=torch.bfloat16)
     ws = torch.empty(max(1, B * heads * max(splits, 1) * (hd + 2)), device="cuda", dtype=torch.float32)
-    rc = lib.slime_op_decode_attention(L.ptr(q), q.stride(0), L.ptr(kc), L.ptr(vc), cache_len, L.ptr(lens), B, heads,
-                                       kv_heads, hd, 1.0 / math.sqrt(hd), L.ptr(out), out.stride(0), splits, L.ptr(ws),
-                                       L.stream_ptr())
+    rc = lib.slime_op_decode_attention_fused(L.ptr(q), q.stride(0), L.ptr(kc), L.ptr(vc), cache_len, L.ptr(lens), B, heads,
+                                             kv_heads, hd, 1.0 / math.sqrt(hd), L.ptr(out), out.stride(0), splits,
+                                             L.ptr(ws), L.ptr(counters), L.stream_ptr())
     L.check(rc, "op_decode_attention")
     torch.cuda.synchronize()
     return out
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(1, 4096, 4096, 4), (16, 6144, 4096, 2), (7, 4096, 14336, 8), (24, 4096, 8192, 8),
+                                          (5, 136, 96, 3), (32, 28672, 4096, 2)])
+def test_skinny_gemm_in_kernel_finish(M, N, K, splits):
+    """Split-K finished inside the kernel (atomic ticket per 8-column tile, the last warp adds all partials in split
+    order): bit-identical with the finishing-kernel path for every epilogue, counters back at zero, repeatable."""
+    L = _L()
+    torch.manual_seed(M + N + splits)
+    a, w, bias, res = rnd(M, K), rnd(N, K, scale=0.05), rnd(N), rnd(M, N)
+    cnt = torch.zeros(N // 8, device="cuda", dtype=torch.int32)
+    for kw in (dict(bias=bias), dict(bias=bias, residual=res), dict(f32=True), dict(bias=bias, epi=L.EPI_GELU_ERF)):
+        plain = skinny(a, w, splits=splits, **kw)
+        for _ in range(2):
+            fused = skinny(a, w, splits=splits, counters=cnt, **kw)
+            assert torch.equal(plain, fused), kw.keys()
+            assert int(cnt.abs().sum()) == 0, "tickets must be handed back"
+    if N % 16 == 0:
+        assert torch.equal(skinny(a, w, splits=splits, epi=L.EPI_SWIGLU), skinny(a, w, splits=splits, epi=L.EPI_SWIGLU, counters=cnt))
+    # in-place residual (the decode step's o-/down-projection)
+    h1, h2 = res.clone(), res.clone()
+    skinny(a, w, splits=splits, residual=h1, out=h1)
+    skinny(a, w, splits=splits, residual=h2, out=h2, counters=cnt)
+    assert torch.equal(h1, h2) and int(cnt.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(1, 6144, 4096, 2), (16, 28672, 4096, 1), (9, 6144, 4096, 4), (32, 4096, 4096, 4),
+                                          (3, 7680, 5120, 2)])
+def test_skinny_gemm_rmsnorm_of_the_staged_rows(M, N, K, splits):
+    """a_norm_w: every CTA normalises the rows it stages (1/rms over the FULL row, also when it stages one k-split):
+    equals rmsnorm (HF: w * (x * rstd).to(dtype)) followed by the plain projection."""
+    L = _L()
+    lib = L.load()
+    torch.manual_seed(M + N + K)
+    a, w = rnd(M, K), rnd(N, K, scale=0.05)
+    nw = (1.0 + 0.1 * torch.randn(K, device="cuda")).to(torch.bfloat16)
+    cnt = torch.zeros(N // 8, device="cuda", dtype=torch.int32)
+    normed = torch.empty_like(a)
+    L.check(lib.slime_op_rmsnorm(L.ptr(a), L.ptr(nw), L.ptr(normed), M, K, 1e-5, L.stream_ptr()), "rmsnorm")
+    want = skinny(normed, w, splits=splits)
+    got = skinny(a, w, splits=splits, a_norm_w=nw, counters=cnt if splits > 1 else None)
+    e = rel_l2(got, want)
+    assert e < 1e-3, f"staged RMSNorm vs rmsnorm kernel + projection: rel-L2 {e:.3e}"  # 1/rms may differ in the last bit
+    af = a.float()
+    ref = (nw.float() * (af * torch.rsqrt(af.pow(2).mean(-1, keepdim=True) + 1e-5)).to(torch.bfloat16).float()).to(torch.bfloat16).float() @ w.float().t()
+    assert rel_l2(got, ref) < 4e-3
+    assert torch.equal(got, skinny(a, w, splits=splits, a_norm_w=nw, counters=cnt if splits > 1 else None))
+
+
+@pytest.mark.parametrize("heads,kv_heads", [(32, 8), (8, 8), (16, 2)])
+@pytest.mark.parametrize("splits", [3, 8, 32])
+def test_decode_attention_in_kernel_merge(heads, kv_heads, splits):
+    """kv splits merged by the last CTA of a (sequence, kv head) instead of a merge launch: same result, tickets back at zero."""
+    torch.manual_seed(heads + splits)
+    B, cache_len, hd = 5, 700, 128
+    kc, vc = rnd(B, cache_len, kv_heads * hd), rnd(B, cache_len, kv_heads * hd)
+    qkv = rnd(B, (heads + 2 * kv_heads) * hd)
+    lens = torch.tensor([0, 1, 15, 333, cache_len - 1], device="cuda", dtype=torch.int32)
+    cnt = torch.zeros(B * kv_heads, device="cuda", dtype=torch.int32)
+    plain = decode_attention(qkv, kc, vc, lens, heads, kv_heads, splits)
+    for _ in range(2):
+        fused = decode_attention(qkv, kc, vc, lens, heads, kv_heads, splits, counters=cnt)
+        assert rel_l2(fused, plain) < 1e-6 and (fused.float() - plain.float()).abs().max() <= 2 ** -8 * plain.float().abs().max()
+        assert int(cnt.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("pname,B", [("small", 1), ("small", 18), ("tiny", 32)])
+def test_decode_step_fused_chain_matches_the_finishing_kernels(pname, B):
+    """slime_set_decode_fused: 5 launches per layer (split reductions finished in the producing kernels, RMSNorm in the
+    consumer's staging) against the 9-launch chain with finishing kernels; launch count checked."""
+    from slime_b200.config import preset
+    from slime_b200.engine import SlimeEngine
+    from slime_b200.synth import synth_state_dict
+
+    cfg = preset(pname)
+    eng = SlimeEngine(cfg, 0)
+    eng.load_state_dict(synth_state_dict(cfg))
+    lib = eng.lib
+    torch.manual_seed(B)
+    lens0 = [40 + 3 * (b % 11) for b in range(B)]
+    rows = (torch.randn(sum(lens0), cfg.hidden_size, device="cuda") * 0.5).to(torch.bfloat16)
+    cu = torch.tensor([0] + list(torch.tensor(lens0).cumsum(0)), dtype=torch.int32, device="cuda")
+    pos = torch.cat([torch.arange(n) for n in lens0]).to(device="cuda", dtype=torch.int32)
+    xs = [(torch.randn(B, cfg.hidden_size, device="cuda") * 0.5).to(torch.bfloat16) for _ in range(3)]
+    outs, launches = [], []
+    for fused in (1, 0, 1):
+        lib.slime_set_decode_fused(fused)
+        try:
+            eng.attach_kv_cache(B, 128)
+            eng.decoder_prefill(rows, cu, pos, lens0)
+            lens = torch.tensor(lens0, dtype=torch.int32, device="cuda")
+            step = []
+            n0 = lib.slime_launch_count()
+            for x in xs:
+                step.append(eng.decode_step(x, lens).clone())
+                lens = lens + 1
+            launches.append((lib.slime_launch_count() - n0) / len(xs))
+            outs.append(torch.stack(step))
+        finally:
+            eng.detach_kv_cache()
+            lib.slime_set_decode_fused(-1)
+    e = rel_l2(outs[0], outs[1])
+    print(f"decode step {pname} B={B}: fused vs finishing kernels rel-L2 {e:.3e}; launches per step {launches[0]:.0f} vs {launches[1]:.0f}")
+    assert torch.isfinite(outs[0]).all()
+    assert e < 3e-3
+    assert torch.equal(outs[0], outs[2]), "fused chain must be repeatable bit for bit"
+    assert launches[0] <= 5 * cfg.num_hidden_layers + 2 < launches[1]
 
 
 @pytest.fixture(params=[2, 1], ids=["mma", "cuda_core"])

@@ -89,7 +89,7 @@ def test_end_to_end_against_the_reference_golden(case):
     assert res.lengths == gold["lengths"].tolist()
     e = rel(res.logits_last, gold["logits_last"])
     print(f"[{NAME}] last-token logits rel-L2 vs reference fp32 golden: {e:.3e}")
-    assert e < 1.5e-2
+    assert e < 6.5e-3  # measured 4.9e-3 on B200 (x 1.3)
     # un-forced: the kept count stays within a few tokens of the reference's (near-uniform probabilities: the count is
     # set by top-p, the membership of the last few places by bf16 noise - SURVEY.md 8a row R)
     r2 = eng.prefill(px, ids, mask, grids=grids, want_last=False, run_decoder=False)

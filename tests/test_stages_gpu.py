@@ -6,10 +6,11 @@ Tolerances (north_star: "within 1e-3 relative bf16 tolerance, bit-exact for the 
   * integer results - selected indices given the probabilities, lengths, cu_seqlens, attention_mask,
     position_ids, labels, and the spliced rows as a gather of the stage outputs - are compared EXACTLY;
   * floating-point stages are bf16 pipelines compared with the fp32 oracle: one bf16 rounding is
-    already 1.7e-3 rel-L2, so each stage must stay within STAGE_TOL = 1e-2 after its chain of
-    roundings (measured 3e-3..5e-3), and the end-to-end logits (teacher-forced selection, SURVEY.md 8a
-    row R) within E2E_TOL = 1.5e-2 (measured 5e-3..8e-3) - the unmodified reference's own bf16 run sits at 0.8e-2 on the same case
-    (golden key ref_bf16_rel_err_last).  Measured values are printed (pytest -s) and recorded in DESIGN.md.
+    already 1.7e-3 rel-L2, so the bounds are the values MEASURED on B200 x 1.3 (profiles/r02_stage_errors.txt):
+    stages <= STAGE_TOL = 8e-3 (measured 2.3e-3..6.1e-3), last-token logits (teacher-forced selection, SURVEY.md
+    8a row R) <= LAST_TOL = 8e-3 (measured 4.9e-3..6.1e-3), all-position logits <= E2E_TOL = 1.1e-2 (measured
+    7.2e-3..8.2e-3) - the unmodified reference's own bf16 run sits at 0.8e-2 on the last token of the same case (golden key
+    ref_bf16_rel_err_last); the full-size floor test (test_fullsize_gpu.py) shows these errors are the bf16 floor.
 """
 import os
 
@@ -20,8 +21,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-STAGE_TOL = 1e-2
-E2E_TOL = 1.5e-2
+STAGE_TOL = 8e-3
+LAST_TOL = 8e-3
+E2E_TOL = 1.1e-2
 
 
 def rel(a, b):
@@ -224,7 +226,7 @@ def test_end_to_end_logits(name):
     ref_bf16 = float(gold["ref_bf16_rel_err_last"][0])
     print(f"[{name}] last-token logits rel-L2 vs reference fp32 golden: {e_last:.3e} "
           f"(reference's own bf16 run: {ref_bf16:.3e})")
-    assert e_last < E2E_TOL
+    assert e_last < LAST_TOL
     cu = res.cu_seqlens.cpu().tolist()
     for b in range(px.shape[0]):
         got = res.logits_all[cu[b]:cu[b + 1]]

@@ -36,7 +36,7 @@ def test_config_switches(over):
     last = torch.stack([lg[-1] for lg in ora["logits"]])
     e = rel(res.logits_last, last)
     print(over, "logits rel-L2", e)
-    assert e < 1.5e-2
+    assert e < 8e-3  # measured 4.8e-3..6.0e-3 on B200 (x 1.3)
     if not cfg.use_global_only:
         # un-forced: the device selection obeys the rule on the device probabilities
         r2 = eng.prefill(px, ids, mask, grids=grids, want_probs=True, want_last=False, run_decoder=False)
@@ -76,4 +76,4 @@ def test_mixed_crop_counts_and_missing_placeholder():
     last = torch.stack([lg[-1] for lg in logits])
     e = rel(res.logits_last, last)
     print("mixed batch logits rel-L2", e)
-    assert e < 1.5e-2
+    assert e < 8e-3  # measured 4.8e-3..6.0e-3 on B200 (x 1.3)

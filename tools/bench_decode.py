@@ -77,12 +77,14 @@ def main():
         pos = torch.cat([torch.arange(n) for n in lens0]).to(device=dev, dtype=torch.int32)
         x = (torch.randn(B, H, device=dev) * 0.5).to(torch.bfloat16)
         kv_bytes = cfg.num_hidden_layers * sum(lens0) * 2 * KD * 2
-        for mode, amode, pdl, pf, name in (
-                (1, 2, 1, 0, "weight-streaming GEMM + split-KV attention (mma.sync), PDL"),
-                (1, 1, 1, 0, "weight-streaming GEMM + split-KV attention (CUDA cores), PDL"),
-                (1, 2, 0, 0, "weight-streaming GEMM + split-KV attention (mma.sync), ordinary launches"),
-                (1, 2, 1, 1, "as the first + L2 prefetch of the o-projection by the QKV finishing kernel"),
-                (0, 0, 0, 0, "tcgen05 tile GEMM + one CTA per head"))[:2 if args.quick else None]:
+        for mode, amode, pdl, pf, fused, name in (
+                (1, 2, 1, 0, 1, "fused chain (5 launches / layer): weight-streaming GEMM with in-kernel split-K finish + RMSNorm in the staging, split-KV attention (mma.sync) with in-kernel merge, PDL"),
+                (1, 2, 1, 0, 0, "weight-streaming GEMM + split-KV attention (mma.sync) + finishing kernels, PDL"),
+                (1, 2, 0, 0, 1, "fused chain, ordinary launches"),
+                (1, 1, 1, 0, 0, "weight-streaming GEMM + split-KV attention (CUDA cores) + finishing kernels, PDL"),
+                (1, 2, 0, 0, 0, "weight-streaming GEMM + split-KV attention (mma.sync) + finishing kernels, ordinary launches"),
+                (0, 0, 0, 0, 0, "tcgen05 tile GEMM + one CTA per head"))[:2 if args.quick else None]:
+            lib.slime_set_decode_fused(fused)
             lib.slime_gemm_set_skinny_mode(mode)
             lib.slime_decode_attention_set_mode(amode)
             lib.slime_set_pdl_mode(pdl)
@@ -119,6 +121,7 @@ def main():
                 lib.slime_decode_attention_set_mode(-1)
                 lib.slime_set_pdl_mode(-1)
                 lib.slime_set_decode_prefetch(-1)
+                lib.slime_set_decode_fused(-1)
 
     # ---- isolated projections of one layer at M = 1 / 16 (L2 flushed between launches: weights come from HBM) ----
     gem = []
