@@ -551,8 +551,9 @@ def main():
     crops_per_s = 5 * flat.shape[0] / (e0.elapsed_time(e1) / 1e3) * world
 
     # ---- decode step after this prefill (secondary, HBM-bound): ms per generated token ----
-    def decode_timing(e, c, px, ids, mask, grids, n_dec=16):
+    def decode_timing(e, c, px, ids, mask, grids, n_dec=16, fused_mask=-1):
         try:
+            e.lib.slime_set_decode_fused(fused_mask)
             nb = px.shape[0]
             r0 = e.prefill(px, ids, mask, grids=grids)
             e.attach_kv_cache(nb, max(r0.lengths) + n_dec + 8)
@@ -580,6 +581,7 @@ def main():
         except Exception as ex:  # noqa: BLE001 - never lose the prefill line over a secondary figure
             return {"error": repr(ex)}
         finally:
+            e.lib.slime_set_decode_fused(-1)
             try:
                 e.detach_kv_cache()
             except Exception:  # noqa: BLE001
@@ -587,6 +589,11 @@ def main():
 
     decode = decode_timing(eng, cfg, bench.px_d, bench.ids_d, bench.mask_d, bench.grids)
     decode_b1 = decode_timing(eng, cfg, bench.px_d[:1], bench.ids_d[:1], bench.mask_d[:1], bench.grids[:1])
+    # the 5-launches-per-layer chain (split reductions finished inside the producing kernels; opt-in because it measures
+    # slower than the PDL chain with finishing kernels, profiles/r02_decode_experiments.txt) for the record
+    decode_fused = {f"batch_{nb}": {k: v for k, v in decode_timing(eng, cfg, bench.px_d[:nb], bench.ids_d[:nb], bench.mask_d[:nb],
+                                                                   bench.grids[:nb], fused_mask=7).items()
+                                    if k in ("ms_per_step", "launches_per_step", "error")} for nb in (1, bench.px_d.shape[0])}
 
     # ---- secondary measurements (short step counts; same kernels, other modes / BASELINE.json configurations) ----
     peaks = measured_peaks()
@@ -661,8 +668,9 @@ def main():
         if d is not None and "achieved_gbs" in d:
             d["frac_of_hbm_peak"] = d["achieved_gbs"] / peaks["hbm"]
     if "achieved_gbs" in decode:
-        decode["kernels"] = "weight-streaming mma.sync GEMM (csrc/gemm_skinny.cu) + split-KV mma.sync attention (csrc/decode_attn.cu), PDL"
+        decode["kernels"] = "weight-streaming mma.sync GEMM (csrc/gemm_skinny.cu) + split-KV mma.sync attention (csrc/decode_attn.cu) + finishing kernels, PDL"
         decode["batch_1"] = decode_b1
+        decode["fused_chain_5_launches_per_layer"] = decode_fused
     fl = algorithmic_flops(cfg, args.crops * B, lengths, (args.crops - 1) * B * cfg.mm_resampler_dim)
     gemm_tf = pwork[0] / (pms[0] / 1e3) / 1e12 if pms[0] > 0 else 0.0
     step_ms = ms / args.steps

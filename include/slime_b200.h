@@ -300,11 +300,12 @@ int slime_set_pdl_mode(int mode);
  * QKV weights, 4 / 8 = the attention kernel / the o-projection's finishing kernel pull 32 MB of gate/up each;
  * -1 = back to SLIME_DECODE_PREFETCH / the build default (0: measured slower than no prefetch in every variant). */
 int slime_set_decode_prefetch(int mask);
-/* Decode-step launch chain: 1 (default) = fused - 5 launches per layer, split-K partials and attention kv splits are
- * finished inside the producing kernels (atomic ticket, fixed summation order), RMSNorm applied while the consuming
- * projection stages its rows; 0 = one finishing launch per split reduction (9 per layer); -1 = back to the default /
- * SLIME_DECODE_FUSED. */
-int slime_set_decode_fused(int on);
+/* Decode-step launch chain, bit mask: 1 = split-K partial sums finished inside the projection kernels, 2 = attention kv
+ * splits merged inside the attention kernel (both by atomic ticket, fixed summation order), 4 = RMSNorm applied while the
+ * consuming projection stages its rows instead of in the o-/down-projection's finishing kernel.  7 = 5 launches per layer,
+ * 0 (the default: faster under programmatic dependent launch, profiles/r02_decode_experiments.txt) = 9, one finishing
+ * launch per split reduction; -1 = back to the default / SLIME_DECODE_FUSED. */
+int slime_set_decode_fused(int mask);
 /* ---- multi-GPU: the path's ONE collective - samples are independent, every rank runs the whole prefill on its
  * shard of the batch, and the last-token logits are all-gathered over NCCL (NVLink 5 / NVSwitch).  The reference has no
  * collective (N independent processes, outputs concatenated: scripts/llama/eval/gqa.sh:20-43).  NCCL is bound at run time

@@ -529,19 +529,24 @@ int decode_prefetch_mask() {
 // gemm_skinny.cu for B <= 32, attention on the split-KV kernel of decode_attn.cu; 7-8 launches per layer -
 //   qkv (+RoPE, K/V append) [+ split-K finish] | attention [+ split merge] | o-proj + finish(residual, RMSNorm) |
 //   gate/up (SwiGLU) | down-proj + finish(residual, next layer's RMSNorm).
-// Fused chain (default, SLIME_DECODE_FUSED=0 / slime_set_decode_fused(0) restores the chain above): 5 launches per layer.
+// Fused chain (opt-in: SLIME_DECODE_FUSED=7 / slime_set_decode_fused(7)): 5 launches per layer.
 // The finishing kernels disappear - split-K partials are summed by the warp that delivers a tile's last partial and the
 // kv splits of the attention by the last CTA of a (sequence, kv head), both by atomic ticket and in a fixed order - and
 // the RMSNorms move into the activation staging of the projection that consumes them (every CTA normalises the <= 32
 // rows it stages; the residual stream h is the only activation buffer between layers):
 //   qkv (RMSNorm in, RoPE, K/V append) | attention | o-proj (+residual) | gate/up (RMSNorm in, SwiGLU) | down (+residual).
+// Bit mask (A/B): 1 = split-K sums finished inside the projections, 2 = kv splits merged inside the attention kernel,
+// 4 = RMSNorm in the consumer's staging (else: fused into the o-/down-projection's finishing kernel).  7 = all.
+#ifndef SLIME_DECODE_FUSED_DEFAULT
+#define SLIME_DECODE_FUSED_DEFAULT 0  // measured: every fusion is slower than its PDL finishing launch (profiles/r02_decode_experiments.txt)
+#endif
 int g_decode_fused = -1;
-bool decode_fused_mode() {
+int decode_fused_mask() {
   if (g_decode_fused < 0) {
     const char* e = getenv("SLIME_DECODE_FUSED");
-    g_decode_fused = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_decode_fused = (e != nullptr && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : SLIME_DECODE_FUSED_DEFAULT;
   }
-  return g_decode_fused != 0;
+  return g_decode_fused;
 }
 
 int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B, float* logits, cudaStream_t s) {
@@ -571,16 +576,18 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
   int* counters = a.get<int>(n_cnt);
   ARENA_CHECK(a, "decode");
   if (a.dry || B <= 0) return SLIME_OK;
-  const bool fused = decode_fused_mode() && B <= 32 && asplits >= 1 && H % 32 == 0 && I % 32 == 0 && slime_gemm_skinny_enabled();
+  const int fm = (B <= 32 && asplits >= 1 && H % 32 == 0 && I % 32 == 0 && slime_gemm_skinny_enabled()) ? decode_fused_mask() : 0;
   SLIME_CHECK_CUDA(cudaMemcpyAsync(h, x_in, static_cast<size_t>(B) * H * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
-  if (fused) SLIME_CHECK_CUDA(cudaMemsetAsync(counters, 0, n_cnt * sizeof(int), s));
+  if (fm & 3) SLIME_CHECK_CUDA(cudaMemsetAsync(counters, 0, n_cnt * sizeof(int), s));
   const size_t plane = static_cast<size_t>(c->kv_cache_batch) * c->kv_cache_len * KD;
   GemmExtra ex;
   ex.splitk_ws = skws;
   ex.splitk_ws_floats = sk_floats;
   const int pf = decode_prefetch_mask();
-  if (fused) {
-    ex.tile_counters = counters;
+  int* const tile_cnt = (fm & 1) ? counters : nullptr;
+  int* const attn_cnt = (fm & 2) ? counters + n_tile_cnt : nullptr;
+  if (fm & 4) {  // the residual stream h is the only activation buffer between layers
+    ex.tile_counters = tile_cnt;
     GemmExtra exa = ex;  // projections that read the residual stream through an RMSNorm
     exa.a_norm_eps = d.rms_eps;
     for (int l = 0; l < d.layers; ++l) {
@@ -596,7 +603,7 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
       SLIME_PROPAGATE(qkv_rope(c, h, L.qkv_w, B, lens, qkv, s, &exq));
       SLIME_PROPAGATE(slime_launch_decode_attention(qkv, QKV, kc, vc, c->kv_cache_len, lens, B, d.heads, d.kv_heads, hd,
                                                     1.0f / sqrtf(static_cast<float>(hd)), att, QD, asplits, aws, nullptr, 0, s,
-                                                    counters + n_tile_cnt));
+                                                    attn_cnt));
       SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, B, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s, &ex));
       exa.a_norm_w = L.post_norm_w;
       SLIME_PROPAGATE(gemm(c, h, H, L.gate_up_w, H, B, 2 * I, H, nullptr, nullptr, 0, 0, nullptr, GEMM_EPI_SWIGLU, act,
@@ -625,6 +632,7 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
     exq.kv_v = vc;
     exq.kv_lens = lens;
     exq.kv_cache_len = c->kv_cache_len;
+    exq.tile_counters = tile_cnt;
     if (pf & 1) {
       exq.l2_prefetch = L.o_w;
       exq.l2_prefetch_bytes = static_cast<size_t>(H) * QD * sizeof(bf16);
@@ -633,7 +641,7 @@ int decode_body(slime_ctx* c, Arena& a, const bf16* x_in, const int* lens, int B
     SLIME_PROPAGATE(slime_launch_decode_attention(qkv, QKV, kc, vc, c->kv_cache_len, lens, B, d.heads, d.kv_heads, hd,
                                                   1.0f / sqrtf(static_cast<float>(hd)), att, QD, asplits, aws,
                                                   (pf & 4) ? L.gate_up_w : nullptr,
-                                                  (pf & 4) ? (gu_bytes < PF_PART ? gu_bytes : PF_PART) : 0, s));
+                                                  (pf & 4) ? (gu_bytes < PF_PART ? gu_bytes : PF_PART) : 0, s, attn_cnt));
     GemmExtra exn = ex;  // projection + residual, then the RMSNorm that feeds the next GEMM
     exn.norm_out = t;
     exn.norm_ld = H;
@@ -1186,8 +1194,8 @@ int slime_set_decode_prefetch(int mask) {
   return SLIME_OK;
 }
 
-int slime_set_decode_fused(int on) {
-  g_decode_fused = on < 0 ? -1 : (on != 0 ? 1 : 0);
+int slime_set_decode_fused(int mask) {
+  g_decode_fused = (mask < 0 || mask > 7) ? -1 : mask;
   return SLIME_OK;
 }
 

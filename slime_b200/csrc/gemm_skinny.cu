@@ -115,6 +115,7 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
                    int epi, int splits, int kc, int xs_stride, float* __restrict__ partial, int* __restrict__ counters) {
   extern __shared__ __align__(16) uint8_t sk_smem[];
   __shared__ float s_rstd[32];
+  __shared__ float s_part[32 * SK_WARPS];
   bf16* xs = reinterpret_cast<bf16*>(sk_smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
   const int split = blockIdx.x % splits, cta = blockIdx.x / splits, ctas = gridDim.x / splits;
@@ -139,49 +140,75 @@ gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__
   pdl_trigger();
   pdl_wait();
 
-  // ---- optional RMSNorm of the A rows (a_norm_w): 1/rms of every FULL row (all K columns, not only this k-split),
-  //      one warp per row, every load of a lane issued before the first use ----
   const bool a_norm = p.a_norm_w != nullptr;
   if (a_norm) {
-    const int chunks_k = p.K >> 3;
-    for (int r = warp; r < p.M; r += SK_WARPS) {
-      const uint4* row = reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * lda);
-      float sq = 0.f;
-      for (int c0 = lane; c0 < chunks_k; c0 += 32 * 4) {
-        uint4 v[4];
+    // ---- RMSNorm of the A rows on their way in (a_norm_w): thread t owns the 16-byte chunks t, t + 512, ... of EVERY row, so
+    //      the loads of up to AN_B rows are in flight at once (one L2 round trip per batch of rows); the sum of squares runs
+    //      over the FULL row (all K columns), the chunks of this CTA's k-split are parked raw in shared memory and normalised
+    //      in place by the thread that parked them once 1/rms is known ----
+    constexpr int AN_B = 8;
+    const int chunks_k = p.K >> 3, c_lo = ks >> 3, c_hi = (ks + klen) >> 3;
+    for (int r0 = 0; r0 < p.M; r0 += AN_B) {
+      float sq[AN_B];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (c0 + 32 * j < chunks_k) ? __ldcg(row + c0 + 32 * j) : make_uint4(0u, 0u, 0u, 0u);
+      for (int j = 0; j < AN_B; ++j) sq[j] = 0.f;
+      for (int ch = tid; ch < chunks_k; ch += SK_THREADS) {
+        uint4 v[AN_B];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < AN_B; ++j)
+          v[j] = (r0 + j < p.M) ? __ldcg(reinterpret_cast<const uint4*>(A + static_cast<size_t>(r0 + j) * lda) + ch)
+                                : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < AN_B; ++j) {
           const float2 a = unpack_bf16x2(v[j].x), b = unpack_bf16x2(v[j].y), c2 = unpack_bf16x2(v[j].z), d = unpack_bf16x2(v[j].w);
-          sq += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c2.x * c2.x + c2.y * c2.y + d.x * d.x + d.y * d.y;
+          sq[j] += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c2.x * c2.x + c2.y * c2.y + d.x * d.x + d.y * d.y;
+          if (r0 + j < p.M && ch >= c_lo && ch < c_hi)
+            *reinterpret_cast<uint4*>(xs + static_cast<size_t>(r0 + j) * xs_stride + (ch - c_lo) * 8) = v[j];
         }
       }
-      sq = warp_sum(sq);
-      if (lane == 0) s_rstd[r] = rsqrtf(sq / static_cast<float>(p.K) + p.a_norm_eps);
+#pragma unroll
+      for (int j = 0; j < AN_B; ++j) {
+        const float tsum = warp_sum(sq[j]);
+        if (lane == 0 && r0 + j < p.M) s_part[(r0 + j) * SK_WARPS + warp] = tsum;
+      }
     }
     __syncthreads();
-  }
-  // ---- stage the activations of this k-split (rows >= M are zero) ----
-  {
+    if (tid < p.M) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < SK_WARPS; ++w2) tot += s_part[tid * SK_WARPS + w2];
+      s_rstd[tid] = rsqrtf(tot / static_cast<float>(p.K) + p.a_norm_eps);
+    }
+    __syncthreads();
+    for (int ch = c_lo + tid; ch < c_hi; ch += SK_THREADS) {  // same (thread, chunk) ownership as above
+      const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(p.a_norm_w) + ch);
+      for (int r = 0; r < p.M; ++r) {
+        uint4* px = reinterpret_cast<uint4*>(xs + static_cast<size_t>(r) * xs_stride + (ch - c_lo) * 8);
+        const float rs = s_rstd[r];
+        auto nrm = [rs](uint32_t x, uint32_t gw) {  // HF: weight * (x * rstd).to(dtype)
+          const float2 xf = unpack_bf16x2(x), gf = unpack_bf16x2(gw);
+          const float a = elem_to_float(float_to_elem(xf.x * rs)), b = elem_to_float(float_to_elem(xf.y * rs));
+          return pack_bf16x2(gf.x * a, gf.y * b);
+        };
+        const uint4 v = *px;
+        *px = make_uint4(nrm(v.x, g4.x), nrm(v.y, g4.y), nrm(v.z, g4.z), nrm(v.w, g4.w));
+      }
+    }
+    if (!HALF) {  // fragment rows past M are zero
+      const int chunks = klen >> 3;
+      for (int idx = p.M * chunks + tid; idx < MT * 16 * chunks; idx += SK_THREADS) {
+        const int r = idx / chunks, ch = idx - r * chunks;
+        *reinterpret_cast<uint4*>(xs + static_cast<size_t>(r) * xs_stride + ch * 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  } else {
+    // ---- stage the activations of this k-split (rows >= M are zero) ----
     const int chunks = klen >> 3;
     const int total = (HALF ? p.M : MT * 16) * chunks;  // HALF: exactly the M <= 8 real rows (8 KB at M = 1)
     for (int idx = tid; idx < total; idx += SK_THREADS) {
       const int r = idx / chunks, ch = idx - r * chunks;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (r < p.M) {
-        v = __ldcg(reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * lda + ks + ch * 8));
-        if (a_norm) {  // HF: weight * (x * rstd).to(dtype)
-          const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(p.a_norm_w + ks + ch * 8));
-          const float rs = s_rstd[r];
-          auto nrm = [rs](uint32_t x, uint32_t gw) {
-            const float2 xf = unpack_bf16x2(x), gf = unpack_bf16x2(gw);
-            const float a = elem_to_float(float_to_elem(xf.x * rs)), b = elem_to_float(float_to_elem(xf.y * rs));
-            return pack_bf16x2(gf.x * a, gf.y * b);
-          };
-          v = make_uint4(nrm(v.x, g4.x), nrm(v.y, g4.y), nrm(v.z, g4.z), nrm(v.w, g4.w));
-        }
-      }
+      if (r < p.M) v = __ldcg(reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * lda + ks + ch * 8));
       *reinterpret_cast<uint4*>(xs + static_cast<size_t>(r) * xs_stride + ch * 8) = v;
     }
   }

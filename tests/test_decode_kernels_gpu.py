@@ -257,7 +257,7 @@ def test_decode_attention_in_kernel_merge(heads, kv_heads, splits):
 
 @pytest.mark.parametrize("pname,B", [("small", 1), ("small", 18), ("tiny", 32)])
 def test_decode_step_fused_chain_matches_the_finishing_kernels(pname, B):
-    """slime_set_decode_fused: 5 launches per layer (split reductions finished in the producing kernels, RMSNorm in the
+    """slime_set_decode_fused(7): 5 launches per layer (split reductions finished in the producing kernels, RMSNorm in the
     consumer's staging) against the 9-launch chain with finishing kernels; launch count checked."""
     from slime_b200.config import preset
     from slime_b200.engine import SlimeEngine
@@ -274,7 +274,7 @@ def test_decode_step_fused_chain_matches_the_finishing_kernels(pname, B):
     pos = torch.cat([torch.arange(n) for n in lens0]).to(device="cuda", dtype=torch.int32)
     xs = [(torch.randn(B, cfg.hidden_size, device="cuda") * 0.5).to(torch.bfloat16) for _ in range(3)]
     outs, launches = [], []
-    for fused in (1, 0, 1):
+    for fused in (7, 0, 7, 1, 2, 4):
         lib.slime_set_decode_fused(fused)
         try:
             eng.attach_kv_cache(B, 128)
@@ -296,6 +296,8 @@ def test_decode_step_fused_chain_matches_the_finishing_kernels(pname, B):
     assert e < 3e-3
     assert torch.equal(outs[0], outs[2]), "fused chain must be repeatable bit for bit"
     assert launches[0] <= 5 * cfg.num_hidden_layers + 2 < launches[1]
+    # the partial settings (A/B knobs): in-kernel split-K finish / in-kernel kv merge alone do not change a bit
+    assert torch.equal(outs[3], outs[1]) and rel_l2(outs[4], outs[1]) < 1e-6 and rel_l2(outs[5], outs[0]) < 1e-6
 
 
 @pytest.fixture(params=[2, 1], ids=["mma", "cuda_core"])

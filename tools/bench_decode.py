@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--no-projections", action="store_true", help="skip the isolated projection timings")
     ap.add_argument("--quick", action="store_true", help="only the two PDL configurations (mma / CUDA-core attention)")
+    ap.add_argument("--variants", type=int, default=0, help="only the first N kernel configurations")
     ap.add_argument("--out", default=None, help="write the rows as JSON here (default: print only)")
     args = ap.parse_args()
 
@@ -78,12 +79,17 @@ def main():
         x = (torch.randn(B, H, device=dev) * 0.5).to(torch.bfloat16)
         kv_bytes = cfg.num_hidden_layers * sum(lens0) * 2 * KD * 2
         for mode, amode, pdl, pf, fused, name in (
-                (1, 2, 1, 0, 1, "fused chain (5 launches / layer): weight-streaming GEMM with in-kernel split-K finish + RMSNorm in the staging, split-KV attention (mma.sync) with in-kernel merge, PDL"),
+                (1, 2, 1, 0, 7, "fused chain (5 launches / layer): weight-streaming GEMM with in-kernel split-K finish + RMSNorm in the staging, split-KV attention (mma.sync) with in-kernel merge, PDL"),
                 (1, 2, 1, 0, 0, "weight-streaming GEMM + split-KV attention (mma.sync) + finishing kernels, PDL"),
-                (1, 2, 0, 0, 1, "fused chain, ordinary launches"),
+                (1, 2, 1, 0, 1, "finishing kernels, but the QKV split-K sum in kernel (mask 1), PDL"),
+                (1, 2, 1, 0, 2, "finishing kernels, but the attention kv merge in kernel (mask 2), PDL"),
+                (1, 2, 1, 0, 3, "masks 1 + 2, PDL"),
+                (1, 2, 1, 0, 4, "RMSNorm in the staging, split sums by finishing kernels (mask 4), PDL"),
+                (1, 2, 1, 0, 5, "masks 1 + 4, PDL"),
+                (1, 2, 0, 0, 7, "fused chain, ordinary launches"),
                 (1, 1, 1, 0, 0, "weight-streaming GEMM + split-KV attention (CUDA cores) + finishing kernels, PDL"),
                 (1, 2, 0, 0, 0, "weight-streaming GEMM + split-KV attention (mma.sync) + finishing kernels, ordinary launches"),
-                (0, 0, 0, 0, 0, "tcgen05 tile GEMM + one CTA per head"))[:2 if args.quick else None]:
+                (0, 0, 0, 0, 0, "tcgen05 tile GEMM + one CTA per head"))[:(args.variants or (2 if args.quick else None))]:
             lib.slime_set_decode_fused(fused)
             lib.slime_gemm_set_skinny_mode(mode)
             lib.slime_decode_attention_set_mode(amode)
