@@ -681,7 +681,7 @@ def main():
             tr = json.load(f)["gemm"]
         traffic = tr["dram_bytes_per_launch"]
         traffic_note = (f"static: read from profiles/roofline_traffic.json (ncu --set full capture, {tr['launches']} "
-                        f"launch(es), {tr['source']}), not measured in this run")
+                        f"launch(es), {tr['source']}), not measured in this run" + (f"; {tr['note']}" if tr.get("note") else ""))
     except Exception:
         pass
     roofline = {
