@@ -451,20 +451,21 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
   ARENA_CHECK(a, "decoder");
   if (a.dry || total <= 0) return SLIME_OK;
 
-  SLIME_CHECK_CUDA(cudaMemcpyAsync(h, embeds, static_cast<size_t>(total) * H * sizeof(bf16),
-                                   cudaMemcpyDeviceToDevice, s));
+  // The residual stream starts in the caller's `embeds` (read only) and moves to h with the first o-projection
+  // (residual = embeds, out = h): no copy of the spliced rows.
+  const bf16* hin = embeds;
   // SLIME_FLAG_NORM_FOLDED: the two RMSNorms of a layer live inside the projections that follow them (gamma in the weight
   // columns, 1/rms in the epilogue; gemm.h) - the GEMMs read the residual stream h directly, `t` is not used
   const bool folded = (d.flags & SLIME_FLAG_NORM_FOLDED) != 0 && H % 64 == 0;
   const int parts = H / 64;
-  if (folded) SLIME_PROPAGATE(slime_launch_row_rstd(h, H, rstd, total, H, d.rms_eps, s));
+  if (folded) SLIME_PROPAGATE(slime_launch_row_rstd(hin, H, rstd, total, H, d.rms_eps, s));
   for (int l = 0; l < d.layers; ++l) {
     const LlmLayer& L = c->llm[l];
     GemmExtra exs, exq;  // exs: residual GEMM that also writes the partials; exq: projection scaled by 1/rms
     exs.sumsq_out = folded ? sumsq : nullptr;
     exq.row_scale = folded ? rstd : nullptr;
-    if (!folded) SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, L.in_norm_w, t, H, total, H, d.rms_eps, nullptr, s));
-    SLIME_PROPAGATE(qkv_rope(c, folded ? h : t, L.qkv_w, total, pos_ids, qkv, s, folded ? &exq : nullptr));
+    if (!folded) SLIME_PROPAGATE(slime_launch_rmsnorm(hin, H, L.in_norm_w, t, H, total, H, d.rms_eps, nullptr, s));
+    SLIME_PROPAGATE(qkv_rope(c, folded ? hin : t, L.qkv_w, total, pos_ids, qkv, s, folded ? &exq : nullptr));
     if (c->kv_cache != nullptr) {
       // keep K (post-RoPE) and V of every real token for the decode steps that follow the prefill
       if (l == 0)
@@ -485,8 +486,9 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
     ap.scale = 1.0f / sqrtf(static_cast<float>(hd)); ap.causal = 1;
     ap.total_q_rows = ap.total_k_rows = total;
     SLIME_PROPAGATE(slime_launch_attention(ap, s));
-    SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, total, H, QD, nullptr, h, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s,
+    SLIME_PROPAGATE(gemm(c, att, QD, L.o_w, QD, total, H, QD, nullptr, hin, H, 0, nullptr, GEMM_EPI_NONE, h, nullptr, H, s,
                          folded ? &exs : nullptr));
+    hin = h;
     if (folded) {
       SLIME_PROPAGATE(slime_launch_sumsq_to_rstd(sumsq, parts, rstd, total, H, d.rms_eps, s));
     } else {
@@ -500,13 +502,13 @@ int decoder_body(slime_ctx* c, Arena& a, const bf16* embeds, const int* cu, cons
   }
   if (logits_last != nullptr) {
     SLIME_PROPAGATE(slime_launch_last_rows(cu, B, last_rows, s));
-    SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, c->llm_norm_w, last_h, H, B, H, d.rms_eps, last_rows, s));
+    SLIME_PROPAGATE(slime_launch_rmsnorm(hin, H, c->llm_norm_w, last_h, H, B, H, d.rms_eps, last_rows, s));
     SLIME_PROPAGATE(gemm(c, last_h, H, c->llm_lm_head, H, B, d.vocab, H, nullptr, nullptr, 0, 0, nullptr,
                          GEMM_EPI_NONE, nullptr, logits_last, d.vocab, s));
   }
   if (logits_all != nullptr || hidden_out != nullptr) {
     bf16* hn = hidden_out != nullptr ? hidden_out : t;
-    SLIME_PROPAGATE(slime_launch_rmsnorm(h, H, c->llm_norm_w, hn, H, total, H, d.rms_eps, nullptr, s));
+    SLIME_PROPAGATE(slime_launch_rmsnorm(hin, H, c->llm_norm_w, hn, H, total, H, d.rms_eps, nullptr, s));
     if (logits_all != nullptr) {
       SLIME_PROPAGATE(gemm(c, hn, H, c->llm_lm_head, H, total, d.vocab, H, nullptr, nullptr, 0, 0, nullptr,
                            GEMM_EPI_NONE, logits_all, nullptr, d.vocab, s));
