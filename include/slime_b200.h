@@ -110,6 +110,12 @@ int slime_ctx_finalize_weights(slime_ctx* ctx, void* ws, size_t ws_bytes, void* 
 size_t slime_vision_tower_workspace_bytes(const slime_ctx* ctx, int n_crops);
 int slime_vision_tower_fwd(slime_ctx* ctx, const void* pixels, int n_crops, void* feats, void* ws,
                            size_t ws_bytes, void* stream);
+/* Same for n_images images of crops_per_image crops each (crop 0 of an image = its global view; pixels
+ * [n_images * crops_per_image, 3, S, S]), with the output grouped for the adapter stages: feats[0 .. n_images) = the global
+ * crops, feats[n_images ..) = the local crops in image order - the two slices the reference cuts per sample
+ * (llava/model/llava_arch.py:212-225) are contiguous and need no gather.  Workspace as slime_vision_tower_fwd. */
+int slime_vision_tower_fwd_split(slime_ctx* ctx, const void* pixels, int n_images, int crops_per_image, void* feats,
+                                 void* ws, size_t ws_bytes, void* stream);
 
 /* ---- stage 2: Resampler.forward  (multimodal_resampler/sampler.py:140-170)
  * which = 0: sampler.post_qformer (local compression, 576 -> 144 tokens per crop)

@@ -108,6 +108,7 @@ SIGNATURES = {
     "slime_ctx_finalize_weights": (_i, [_vp, _vp, _sz, _vp]),
     "slime_vision_tower_workspace_bytes": (_sz, [_vp, _i]),
     "slime_vision_tower_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "slime_vision_tower_fwd_split": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "slime_resampler_workspace_bytes": (_sz, [_vp, _i, _i]),
     "slime_resampler_fwd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "slime_projector_workspace_bytes": (_sz, [_vp, _i]),

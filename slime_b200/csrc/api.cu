@@ -234,7 +234,7 @@ int qkv_rope(slime_ctx* c, const bf16* x, const bf16* qkv_w, int rows, const int
 // ------------------------------------------------------------------------------------------
 // stage bodies (dry == true: only account for workspace)
 // ------------------------------------------------------------------------------------------
-int vit_body(slime_ctx* c, Arena& a, const bf16* pixels, int n_crops, bf16* feats, cudaStream_t s) {
+int vit_body(slime_ctx* c, Arena& a, const bf16* pixels, int n_crops, bf16* feats, cudaStream_t s, int per_image = 0) {
   const slime_model_desc& d = c->d;
   const int D = d.vit_hidden, I = d.vit_mlp, P = c->vit_patches, TK = c->vit_tokens, KP = c->vit_kpad;
   const int chunk = n_crops < VIT_CHUNK_CROPS ? n_crops : VIT_CHUNK_CROPS;
@@ -280,7 +280,11 @@ int vit_body(slime_ctx* c, Arena& a, const bf16* pixels, int n_crops, bf16* feat
       SLIME_PROPAGATE(gemm(c, u, I, L.fc2_w, I, rows, D, I, L.fc2_b, h, D, 0, nullptr, GEMM_EPI_NONE, h, nullptr, D, s));
     }
     // feature_select 'patch': drop the CLS row of every crop
-    SLIME_PROPAGATE(slime_launch_copy_rows(h, D, feats + static_cast<size_t>(c0) * P * D, D, nc * P, D, P, TK, 1, s));
+    if (per_image > 0) {  // global crops of all images first, local crops behind them
+      SLIME_PROPAGATE(slime_launch_vit_split_rows(h, feats, nc, D, P, TK, c0, per_image, n_crops / per_image, s));
+    } else {
+      SLIME_PROPAGATE(slime_launch_copy_rows(h, D, feats + static_cast<size_t>(c0) * P * D, D, nc * P, D, P, TK, 1, s));
+    }
   }
   return SLIME_OK;
 }
@@ -924,6 +928,18 @@ int slime_vision_tower_fwd(slime_ctx* ctx, const void* pixels, int n_crops, void
   Arena a(ws, ws_bytes);
   return vit_body(ctx, a, static_cast<const bf16*>(pixels), n_crops, static_cast<bf16*>(feats),
                   static_cast<cudaStream_t>(stream));
+}
+
+int slime_vision_tower_fwd_split(slime_ctx* ctx, const void* pixels, int n_images, int crops_per_image, void* feats,
+                                 void* ws, size_t ws_bytes, void* stream) {
+  SLIME_PROPAGATE(check_ready(ctx, G_VIT));
+  SLIME_REQUIRE(pixels && feats && ws, "vision_tower: null pointer");
+  SLIME_REQUIRE(crops_per_image >= 1, "vision_tower: crops_per_image must be >= 1 (%d given)", crops_per_image);
+  if (n_images <= 0) return SLIME_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Arena a(ws, ws_bytes);
+  return vit_body(ctx, a, static_cast<const bf16*>(pixels), n_images * crops_per_image, static_cast<bf16*>(feats),
+                  static_cast<cudaStream_t>(stream), crops_per_image);
 }
 
 // ---- resampler ----

@@ -274,6 +274,26 @@ __global__ void copy_rows_kernel(const bf16* __restrict__ src, int src_ld, bf16*
   }
 }
 
+// Output rows of the vision tower for a batch of images with `per_image` crops each (crop 0 = the global view):
+// the CLS row of every crop is dropped and crop ci = img * per_image + j lands in slot img (j == 0: all global crops first,
+// [images, P, D]) or images + img * (per_image - 1) + j - 1 (the local crops behind them) - the adapter stages read both
+// groups as contiguous tensors without a gather (reference llava_arch.py:212-225 slices them per sample).
+__global__ void vit_split_rows_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int rows, int D, int P, int TK,
+                                      int crop0, int per_image, int images) {
+  const int nchunks = D >> 3;
+  const long long total = static_cast<long long>(rows) * nchunks;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / nchunks);
+    const int c = static_cast<int>(i % nchunks);
+    const int crop = r / P, pr = r - crop * P;
+    const int ci = crop0 + crop, img = ci / per_image, j = ci - img * per_image;
+    const long long slot = j == 0 ? img : static_cast<long long>(images) + static_cast<long long>(img) * (per_image - 1) + j - 1;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (static_cast<long long>(crop) * TK + 1 + pr) * D + c * 8);
+    *reinterpret_cast<uint4*>(dst + (slot * P + pr) * D + c * 8) = v;
+  }
+}
+
 __global__ void add_rows_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
                                 bf16* __restrict__ y, int rows, int D, int period) {
   const int nchunks = D >> 3;
@@ -506,6 +526,17 @@ int slime_launch_copy_rows(const bf16* src, int src_ld, bf16* dst, int dst_ld, i
   if (rows <= 0) return SLIME_OK;
   copy_rows_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0, stream>>>(
       src, src_ld, dst, dst_ld, rows, D, group, group_stride, offset, nullptr);
+  SLIME_AFTER_LAUNCH();
+  return SLIME_OK;
+}
+
+int slime_launch_vit_split_rows(const bf16* src, bf16* dst, int crops, int D, int P, int TK, int crop0, int per_image,
+                                int images, cudaStream_t stream) {
+  SLIME_REQUIRE(D % 8 == 0 && per_image >= 1 && images >= 1, "vit_split_rows: bad D=%d per_image=%d", D, per_image);
+  if (crops <= 0) return SLIME_OK;
+  const long long rows = static_cast<long long>(crops) * P;
+  vit_split_rows_kernel<<<grid_for(rows * (D / 8), 256), 256, 0, stream>>>(src, dst, static_cast<int>(rows), D, P, TK, crop0,
+                                                                         per_image, images);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

@@ -30,6 +30,9 @@ int slime_launch_clip_embed_ln(const bf16* patch_out, const bf16* cls, const bf1
                                cudaStream_t stream);
 
 // dst[r, :] = src[(r / group) * group_stride + offset + r % group, :]   (row slice / gather copy)
+// vision-tower output with the global crops of all images first, the local crops behind them (elementwise.cu)
+int slime_launch_vit_split_rows(const bf16* src, bf16* dst, int crops, int D, int P, int TK, int crop0, int per_image,
+                                int images, cudaStream_t stream);
 int slime_launch_copy_rows(const bf16* src, int src_ld, bf16* dst, int dst_ld, int rows, int D,
                            int group, int group_stride, int offset, cudaStream_t stream);
 // dst[dst_rows[r], :] = src[r, :]  (row scatter; negative target drops the row)

@@ -181,6 +181,23 @@ class SlimeEngine:
         return feats
 
     @_locked
+    def vision_tower_split(self, pixels: torch.Tensor, crops_per_image: int):
+        """The tower over B images of `crops_per_image` crops each ([B * C, 3, S, S], crop 0 of an image = its global view)
+        with the output grouped for the adapter: returns (global [B,576,D], local [B * (C - 1), 576, D]) as two views of
+        one buffer - the per-sample slices of reference llava_arch.py:212-225 without a gather."""
+        px = pixels.to(device=self.device, dtype=self.dtype).contiguous()
+        n, C = px.shape[0], int(crops_per_image)
+        assert C >= 1 and n % C == 0, (n, C)
+        B = n // C
+        feats = self._bf16(n, self.cfg.vit_patches, self.cfg.vit_hidden)
+        if n == 0:
+            return feats, feats
+        ws = self._workspace(self.lib.slime_vision_tower_workspace_bytes(self._ctx, n))
+        self._check(self.lib.slime_vision_tower_fwd_split(self._ctx, L.ptr(px), B, C, L.ptr(feats), L.ptr(ws), ws.numel(),
+                                                          L.stream_ptr()), "vision_tower_fwd_split")
+        return feats[:B], feats[B:]
+
+    @_locked
     def resampler(self, which: int, x: torch.Tensor) -> torch.Tensor:
         """Resampler.forward (reference multimodal_resampler/sampler.py:140-170); which 0 = local 144-query
         compression (sampler.post_qformer), 1 = the projector's 576-query resampler.  [n,576,D] -> [n,nq,D]."""
@@ -524,17 +541,23 @@ class SlimeEngine:
             mask = None if attention_mask is None else attention_mask.to(device=self.device, non_blocking=True)
             stages = {} if keep_stages else None
 
-            feats = self.vision_tower(px)                                   # [Nc, 576, D]
             starts = [0]
             for c in counts:
                 starts.append(starts[-1] + c)
             uniform = len(set(counts)) == 1
             n_local = [c - 1 for c in counts]
-            if uniform:
+            if uniform and not keep_stages:
+                # every image has the same number of crops: the tower writes the global crops first and the local crops
+                # behind them, so both adapter inputs are contiguous views
+                xg, xl = self.vision_tower_split(px, counts[0])
+                feats = None
+            elif uniform:
+                feats = self.vision_tower(px)                               # [Nc, 576, D]
                 fv = feats.view(B, counts[0], cfg.vit_patches, cfg.vit_hidden)
                 xg = fv[:, 0]
                 xl = fv[:, 1:].reshape(-1, cfg.vit_patches, cfg.vit_hidden)
             else:
+                feats = self.vision_tower(px)
                 gi = torch.tensor(starts[:-1], device=self.device)
                 li = torch.tensor([i for b in range(B) for i in range(starts[b] + 1, starts[b + 1])], device=self.device,
                                   dtype=torch.long)

@@ -77,3 +77,28 @@ def test_mixed_crop_counts_and_missing_placeholder():
     e = rel(res.logits_last, last)
     print("mixed batch logits rel-L2", e)
     assert e < 8e-3  # measured 4.8e-3..6.0e-3 on B200 (x 1.3)
+
+
+@pytest.mark.parametrize("images,per_image", [(3, 5), (4, 1), (2, 3), (27, 5)])
+def test_vision_tower_split_output_is_a_regrouping(images, per_image):
+    """slime_vision_tower_fwd_split: the same features, global crops of all images first and the local crops behind them
+    (the per-sample slices of reference llava_arch.py:212-225 as two contiguous views); 27 x 5 = 135 crops crosses the
+    128-crop pass boundary of the tower.  The prefill that uses it equals the one that gathers (keep_stages path)."""
+    from slime_b200.config import preset
+    from slime_b200.engine import SlimeEngine
+    from slime_b200.synth import synth_inputs, synth_state_dict
+
+    cfg = preset("tiny")
+    eng = SlimeEngine(cfg, 0)
+    eng.load_state_dict(synth_state_dict(cfg))
+    torch.manual_seed(images * 7 + per_image)
+    px = torch.randn(images * per_image, 3, cfg.vit_image, cfg.vit_image, device="cuda").to(torch.bfloat16)
+    feats = eng.vision_tower(px).view(images, per_image, cfg.vit_patches, cfg.vit_hidden)
+    g, l = eng.vision_tower_split(px, per_image)
+    assert torch.equal(g, feats[:, 0])
+    assert torch.equal(l, feats[:, 1:].reshape(-1, cfg.vit_patches, cfg.vit_hidden))
+    if per_image == 5 and images == 3:
+        pxs, ids, mask = synth_inputs(cfg, 3, 5, 20, image_pos=6, ragged=True)
+        a = eng.prefill(pxs, ids, mask, grids=[(2, 2)] * 3)
+        b = eng.prefill(pxs, ids, mask, grids=[(2, 2)] * 3, keep_stages=True)
+        assert a.lengths == b.lengths and torch.equal(a.logits_last, b.logits_last)
