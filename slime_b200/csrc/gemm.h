@@ -36,6 +36,8 @@ struct GemmParams {
   const float* row_scale = nullptr;  // [M] multiplied into the accumulators first (before RoPE / bias / activation)
   float* sumsq_out = nullptr;        // [M][sumsq_parts] partial sums of squares of this GEMM's bf16 output rows (EPI_NONE)
   int sumsq_parts = 0;               // = N / 64
+  int store_hint = 0;  // L2 policy of the epilogue's output stores: 0 default, 1 evict_first (the output streams through L2
+                       // once and would otherwise push the resident A panel out); filled in by slime_launch_gemm
   int epi_mode = 0;    // HBM access pattern of the epilogue (gemm_epilogue.cuh): 0 direct, 1 staged through shared
                        // memory (coalesced stores and residual loads); filled in by slime_launch_gemm
   // ---- decode-step problems (M <= 32 rows; gemm_skinny.cu) ----

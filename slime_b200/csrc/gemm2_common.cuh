@@ -23,7 +23,9 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a sha
 struct TileCoord {
   int m_blk, n_blk;
 };
-SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
+SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m_in) {
+  const bool snake = group_m_in < 0;  // odd groups sweep n downwards: the W tiles still in L2 at a group boundary are reused
+  const int group_m = snake ? -group_m_in : group_m_in;
   const int per_group = group_m * num_n;
   const int group = t / per_group;
   const int first_m = group * group_m;
@@ -32,6 +34,7 @@ SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
   TileCoord c;
   c.m_blk = first_m + in % gsize;
   c.n_blk = in / gsize;
+  if (snake && (group & 1)) c.n_blk = num_n - 1 - c.n_blk;
   return c;
 }
 

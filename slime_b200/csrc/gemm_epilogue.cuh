@@ -177,6 +177,19 @@ SLIME_DEVINL float epi_sumsq8(const uint4& pk) {
   return (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y) + (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
 }
 
+// 16-byte output store with an L2 eviction policy (GemmParams::store_hint)
+SLIME_DEVINL void epi_store16(void* dst, const uint4& v, int hint) {
+  if (hint == 0) {
+    *reinterpret_cast<uint4*>(dst) = v;
+  } else {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol)
+                 : "memory");
+  }
+}
+
 // ---- mode 0: every thread stores its own row ----
 template <int EPI>
 SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, EpiRow& er, int col0, const uint32_t (&r)[32],
@@ -188,8 +201,8 @@ SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, EpiRow& er, int 
     for (int g = 0; g < 2; ++g) {
       const int col = col0 + g * 16;
       if (col >= p.N) break;
-      *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(er.out_row) * p.out_ld + (col >> 1)) =
-          epi_swiglu8(r + g * 16, er.scale);
+      epi_store16(p.out + static_cast<size_t>(er.out_row) * p.out_ld + (col >> 1), epi_swiglu8(r + g * 16, er.scale),
+                  p.store_hint);
     }
   } else {
 #pragma unroll
@@ -204,7 +217,7 @@ SLIME_DEVINL void epi_process_chunk_direct(const GemmParams& p, EpiRow& er, int 
         dst[1] = make_float4(v[4], v[5], v[6], v[7]);
       } else {
         const uint4 pk = epi_pack8(v);
-        *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(er.out_row) * p.out_ld + col) = pk;
+        epi_store16(p.out + static_cast<size_t>(er.out_row) * p.out_ld + col, pk, p.store_hint);
         if (p.sumsq_out != nullptr) er.ssq += epi_sumsq8(pk);
       }
     }
@@ -259,7 +272,7 @@ SLIME_DEVINL void epi_process_chunk_staged(const GemmParams& p, const EpiRow& er
     const int rr = i * (32 / SLOTS) + lane / SLOTS;
     const uint4 v = *reinterpret_cast<const uint4*>(stage_out + epi_stage_off<SLOTS>(rr, q));
     if (col_ok && (ec.ok & (1u << i)))
-      *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(ec.out_row[i]) * p.out_ld + out_col) = v;
+      epi_store16(p.out + static_cast<size_t>(ec.out_row[i]) * p.out_ld + out_col, v, p.store_hint);
   }
   __syncwarp();
 }

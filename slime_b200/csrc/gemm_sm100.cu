@@ -50,7 +50,9 @@ struct TileCoord {
   int m_blk, n_blk;
 };
 
-SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
+SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m_in) {
+  const bool snake = group_m_in < 0;  // odd groups sweep n downwards: the W tiles still in L2 at a group boundary are reused
+  const int group_m = snake ? -group_m_in : group_m_in;
   const int per_group = group_m * num_n;
   const int group = t / per_group;
   const int first_m = group * group_m;
@@ -59,6 +61,7 @@ SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m) {
   TileCoord c;
   c.m_blk = first_m + in % gsize;
   c.n_blk = in / gsize;
+  if (snake && (group & 1)) c.n_blk = num_n - 1 - c.n_blk;
   return c;
 }
 
@@ -335,11 +338,16 @@ int slime_gemm_group_m(int K, int tile_rows) {
     const char* e = getenv("SLIME_GEMM_GROUP_ROWS");
     env_rows = e != nullptr ? atoll(e) : 0;
   }
+  static int snake = -1;
+  if (snake < 0) {
+    const char* e = getenv("SLIME_GEMM_SNAKE");
+    snake = (e != nullptr && e[0] == '0') ? 0 : 1;  // on by default (profiles/r02_gemm_experiments.txt, item 6)
+  }
   long long rows = env_rows > 0 ? env_rows : (32ll << 20) / (2ll * K);
   long long g = rows / tile_rows;
   if (g < 1) g = 1;
   if (g > 64) g = 64;
-  return static_cast<int>(g);
+  return snake ? -static_cast<int>(g) : static_cast<int>(g);
 }
 
 static int g_mode_2cta = -1;  // -1: read SLIME_GEMM_2CTA / the compile-time default on first use
@@ -377,6 +385,14 @@ int slime_launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, const Gemm
   int mode = g_epi_mode;
   if (mode == 2) mode = (p_in.M >= 16384 && (p_in.K <= 1024 || p_in.N <= 1024)) ? 1 : 0;
   p.epi_mode = p.out_f32 != nullptr ? 0 : mode;  // fp32 outputs always go direct
+  {
+    static int store_hint = -1;
+    if (store_hint < 0) {
+      const char* e = getenv("SLIME_GEMM_STORE_HINT");
+      store_hint = (e != nullptr && e[0] == '0') ? 0 : 1;  // on by default (profiles/r02_gemm_experiments.txt, item 6)
+    }
+    p.store_hint = (p.out_f32 == nullptr && static_cast<double>(p.M) * p.N * 2 > 64e6) ? store_hint : 0;
+  }
   SLIME_REQUIRE(A != nullptr && W != nullptr, "gemm: null operand");
   SLIME_REQUIRE(p.out != nullptr || p.out_f32 != nullptr, "gemm: no output pointer");
   SLIME_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
