@@ -24,7 +24,9 @@ struct TileCoord {
   int m_blk, n_blk;
 };
 SLIME_DEVINL TileCoord tile_coord(int t, int num_m, int num_n, int group_m_in) {
-  const bool snake = group_m_in < 0;  // odd groups sweep n downwards: the W tiles still in L2 at a group boundary are reused
+  // group_m_in < 0: serpentine - odd groups sweep the n-tiles downwards, so the W tiles still in L2 at a group boundary
+  // are used again
+  const bool snake = group_m_in < 0;
   const int group_m = snake ? -group_m_in : group_m_in;
   const int per_group = group_m * num_n;
   const int group = t / per_group;
