@@ -345,8 +345,18 @@ int slime_gemm_group_m(int K, int tile_rows) {
     const char* e = getenv("SLIME_GEMM_SNAKE");
     snake = (e != nullptr && e[0] == '0') ? 0 : 1;  // on by default (profiles/r02_gemm_experiments.txt, item 6)
   }
+  static int g_min = -1;
+  if (g_min < 0) {
+    const char* e = getenv("SLIME_GEMM_GROUP_MIN");
+    g_min = e != nullptr ? atoi(e) : 8;
+    if (g_min < 1 || g_min > 64) g_min = 8;
+  }
   long long rows = env_rows > 0 ? env_rows : (32ll << 20) / (2ll * K);
   long long g = rows / tile_rows;
+  // long reductions (K = 14336: 7 MB per 256-row tile) fit no panel; what is left is the sharing between the ~74 clusters of
+  // one wave, best for a near-square patch of tiles: at least 8 m-tiles per group (down-projection: 6.4 -> 5.3 GB of DRAM
+  // reads per launch, +1.9 %; profiles/r02_gemm_experiments.txt item 10)
+  if (env_rows <= 0 && g < g_min) g = g_min;
   if (g < 1) g = 1;
   if (g > 64) g = 64;
   return snake ? -static_cast<int>(g) : static_cast<int>(g);
