@@ -306,6 +306,10 @@ int slime_set_pdl_mode(int mode);
  * QKV weights, 4 / 8 = the attention kernel / the o-projection's finishing kernel pull 32 MB of gate/up each;
  * -1 = back to SLIME_DECODE_PREFETCH / the build default (0: measured slower than no prefetch in every variant). */
 int slime_set_decode_prefetch(int mask);
+/* Programmatic dependent launch for the prefill chain (tcgen05 GEMMs, attention, norm kernels): 1 (default) = the next kernel's
+ * prologue overlaps the tail of the previous one (each such kernel waits for its predecessor before its first global
+ * access), 0 = ordinary launches, -1 = back to the default / SLIME_PREFILL_PDL. */
+int slime_set_prefill_pdl(int mode);
 /* Decode-step launch chain, bit mask: 1 = split-K partial sums finished inside the projection kernels, 2 = attention kv
  * splits merged inside the attention kernel (both by atomic ticket, fixed summation order), 4 = RMSNorm applied while the
  * consuming projection stages its rows instead of in the o-/down-projection's finishing kernel.  7 = 5 launches per layer,

@@ -348,6 +348,8 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_trigger();
+  pdl_wait();  // the prologue above overlaps the previous kernel's tail when launched with the programmatic attribute
 
   if (warp_idx == 0) {
     // ================================ TMA producer ================================
@@ -830,8 +832,10 @@ int launch2q_var(const AttnParams& p, int num_sms, cudaStream_t stream) {
   if (p.cu_q == nullptr)
     flops = 4.0 * p.seqlen_q * static_cast<double>(p.seqlen_k) * HD * p.num_heads * p.batch * (CAUSAL ? 0.5 : 1.0);
   slime_prof_begin(1, flops, stream);
-  kern<<<grid, NT, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, p, units, hsel_count, pair_heads, total, per_cta);
+  const cudaError_t le = slime_launch_prefill(kern, dim3(grid), dim3(NT), Cfg::SMEM_BYTES, stream, tq, tk, tv, p, units,
+                                              hsel_count, pair_heads, total, per_cta);
   slime_prof_end(stream);
+  SLIME_CHECK_CUDA(le);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

