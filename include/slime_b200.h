@@ -306,6 +306,10 @@ int slime_set_pdl_mode(int mode);
  * QKV weights, 4 / 8 = the attention kernel / the o-projection's finishing kernel pull 32 MB of gate/up each;
  * -1 = back to SLIME_DECODE_PREFETCH / the build default (0: measured slower than no prefetch in every variant). */
 int slime_set_decode_prefetch(int mask);
+/* Column width of the cta_group::2 GEMM's cluster tiles: 0 (default) = 256 unless 192-column tiles finish the problem in
+ * fewer width-weighted waves (small problems only, e.g. the N = 4096 projections of a batch-1 prefill), 256 / 192 = forced
+ * (tests, A/B), -1 = back to the default / SLIME_GEMM2_BN.  Results do not depend on it (same k order per element). */
+int slime_gemm_set_tile_n(int bn);
 /* Programmatic dependent launch for the prefill chain (tcgen05 GEMMs, attention, norm kernels): 1 (default) = the next kernel's
  * prologue overlaps the tail of the previous one (each such kernel waits for its predecessor before its first global
  * access), 0 = ordinary launches, -1 = back to the default / SLIME_PREFILL_PDL. */

@@ -152,6 +152,7 @@ SIGNATURES = {
     "slime_decode_attention_set_mode": (_i, [_i]),
     "slime_set_pdl_mode": (_i, [_i]),
     "slime_set_decode_prefetch": (_i, [_i]),
+    "slime_gemm_set_tile_n": (_i, [_i]),
     "slime_set_prefill_pdl": (_i, [_i]),
     "slime_set_decode_fused": (_i, [_i]),
     "slime_attention_set_trace": (_i, [_vp]),

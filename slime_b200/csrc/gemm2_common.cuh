@@ -4,18 +4,28 @@
 #pragma once
 
 constexpr int BLOCK_M = 128;      // rows per CTA (256 per cluster tile)
-constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
-constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // 16 KB: this CTA's half of the W tile
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 2 * BLOCK_N;
-constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;  // barriers + TMEM holder live in the 256 bytes before it
-constexpr int SMEM_BYTES = 1024 + EPI_OFF + NUM_EPI_WARPS * 4096;  // + the epilogue staging tiles
+// Cluster tile 256 x BLOCK_N.  256 columns is the throughput shape (UMMA 256 x 256 x 16; 96 B/clk of shared-memory operand
+// reads per SM).  192 columns (UMMA 256 x 192 x 16, 108 B/clk - still under the 128 B/clk limit that made a 128-wide tile
+// slow) exists for problems whose 256-wide tiles leave the last wave nearly empty: a batch-1 prefill has M = 1379 rows, and
+// N = 4096 is 96 tiles for 74 clusters - two waves, the second 30 % full; as 132 tiles of 192 columns it is two waves of
+// three quarters the length.  Same k order per output element: results do not depend on the tile width.
+template <int BLOCK_N>
+struct Gemm2Cfg {
+  static_assert(BLOCK_N == 256 || BLOCK_N == 192, "cluster tile width");
+  static constexpr int STAGES = 6;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;  // this CTA's half of the W tile (16 / 12 KB)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 512;                // two accumulators of BLOCK_N columns (allocation: a power of two)
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;  // barriers + TMEM holder live in the 256 bytes before it
+  static constexpr int SMEM_BYTES = 1024 + EPI_OFF + NUM_EPI_WARPS * 4096;  // + the epilogue staging tiles
+  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0
 
 #include "gemm_epilogue.cuh"

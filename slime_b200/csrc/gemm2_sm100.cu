@@ -10,6 +10,8 @@
 //   warp 1 (leader)   : issues tcgen05.mma.cta_group::2; commits multicast to both CTAs' barriers
 //   warps 2..9 (both) : epilogue of the CTA's own 128 rows (gemm_epilogue.cuh), arriving on the leader's
 //                       tmem_empty barrier
+#include <cstdlib>
+
 #include "errors.h"
 #include "gemm.h"
 
@@ -17,10 +19,13 @@ namespace {
 
 #include "gemm2_common.cuh"
 
-template <int EPI, bool STAGED>
+template <int BLOCK_N, int EPI, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p, const int group_m) {
+  using Cfg = Gemm2Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES, TMEM_COLS = Cfg::TMEM_COLS,
+                EPI_OFF = Cfg::EPI_OFF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
@@ -31,7 +36,6 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint8_t* epi_stage = smem + EPI_OFF;  // [NUM_EPI_WARPS][EPI_STAGE_BYTES]
-  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block");
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,9 +161,10 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
-template <int EPI, bool STAGED>
+template <int BLOCK_N, int EPI, bool STAGED>
 int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_tn_2cta_kernel<EPI, STAGED>;
+  constexpr int SMEM_BYTES = Gemm2Cfg<BLOCK_N>::SMEM_BYTES;
+  auto kern = gemm_bf16_tn_2cta_kernel<BLOCK_N, EPI, STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
     SLIME_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -179,32 +184,66 @@ int launch2s(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, 
   return SLIME_OK;
 }
 
-template <int EPI>
+template <int BLOCK_N, int EPI>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  if (p.epi_mode != 0 && p.out_f32 == nullptr) return launch2s<EPI, true>(ta, tb, p, num_sms, stream);
-  return launch2s<EPI, false>(ta, tb, p, num_sms, stream);
+  if (p.epi_mode != 0 && p.out_f32 == nullptr) return launch2s<BLOCK_N, EPI, true>(ta, tb, p, num_sms, stream);
+  return launch2s<BLOCK_N, EPI, false>(ta, tb, p, num_sms, stream);
 }
 
-}  // namespace
-
-int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms,
-                           cudaStream_t stream) {
+template <int BLOCK_N>
+int launch2n(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms, cudaStream_t stream) {
   CUtensorMap ta, tb;
   SLIME_PROPAGATE(slime_get_tmap(A, p.M, p.K, lda, BLOCK_M, &ta));
   SLIME_PROPAGATE(slime_get_tmap(W, p.N, p.K, ldw, BLOCK_N / 2, &tb));
   switch (epi) {
     case GEMM_EPI_NONE:
-      return launch2<GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
+      return launch2<BLOCK_N, GEMM_EPI_NONE>(ta, tb, p, num_sms, stream);
     case GEMM_EPI_QUICK_GELU:
-      return launch2<GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
+      return launch2<BLOCK_N, GEMM_EPI_QUICK_GELU>(ta, tb, p, num_sms, stream);
     case GEMM_EPI_GELU_ERF:
-      return launch2<GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
+      return launch2<BLOCK_N, GEMM_EPI_GELU_ERF>(ta, tb, p, num_sms, stream);
     case GEMM_EPI_SWIGLU:
-      return launch2<GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
+      return launch2<BLOCK_N, GEMM_EPI_SWIGLU>(ta, tb, p, num_sms, stream);
     case GEMM_EPI_ROPE:
-      return launch2<GEMM_EPI_ROPE>(ta, tb, p, num_sms, stream);
+      return launch2<BLOCK_N, GEMM_EPI_ROPE>(ta, tb, p, num_sms, stream);
     default:
       slime_set_error("unknown GEMM epilogue %d", epi);
       return SLIME_EINVAL;
   }
+}
+
+}  // namespace
+
+// Tile width: 256 columns unless 192-column tiles finish the problem in fewer (width-weighted) waves - only small problems
+// qualify (batch-1 prefill: o- / down-projection), anything of many waves stays on the throughput shape.  SLIME_GEMM2_BN=256 /
+// 192 forces one (A/B, tests).
+static int g_force_bn = -1;  // -1: read SLIME_GEMM2_BN on first use; 0 = by shape; 256 / 192 = forced
+extern "C" int slime_gemm_set_tile_n(int bn) {
+  if (bn != -1 && bn != 0 && bn != 192 && bn != 256) {
+    slime_set_error("gemm tile width %d not in {-1 (default), 0 (by shape), 192, 256}", bn);
+    return SLIME_EINVAL;
+  }
+  g_force_bn = bn;
+  return SLIME_OK;
+}
+int slime_gemm2_block_n(int M, int N, int num_sms) {
+  if (g_force_bn < 0) {
+    const char* e = getenv("SLIME_GEMM2_BN");
+    g_force_bn = e != nullptr ? atoi(e) : 0;
+    if (g_force_bn != 192 && g_force_bn != 256) g_force_bn = 0;
+  }
+  const int force_bn = g_force_bn;
+  if (force_bn == 256 || force_bn == 192) return N >= 192 ? force_bn : 256;
+  const int clusters = num_sms / 2;
+  const long long m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const long long t256 = m_tiles * ((N + 255) / 256), t192 = m_tiles * ((N + 191) / 192);
+  const double w256 = static_cast<double>((t256 + clusters - 1) / clusters);              // in units of a 256-wide tile
+  const double w192 = static_cast<double>((t192 + clusters - 1) / clusters) * 0.75 * 1.04;  // (slightly less efficient per FLOP)
+  return (N >= 192 && w192 < w256) ? 192 : 256;
+}
+
+int slime_launch_gemm_2cta(const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, int num_sms,
+                           cudaStream_t stream) {
+  if (slime_gemm2_block_n(p.M, p.N, num_sms) == 192) return launch2n<192>(A, lda, W, ldw, p, epi, num_sms, stream);
+  return launch2n<256>(A, lda, W, ldw, p, epi, num_sms, stream);
 }

@@ -283,7 +283,11 @@ SLIME_DEVINL void epi_process_chunk_staged(const GemmParams& p, const EpiRow& er
 template <int BLOCK_N, int EPI, bool STAGED>
 SLIME_DEVINL void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m0, int n0, int quad, int half, int lane,
                                 uint8_t* stage) {
-  constexpr int NCH = BLOCK_N / 64;  // 32-column chunks per warp (half of the tile's columns)
+  // 32-column chunks per warp: the two warps of a lane quadrant split the tile's columns in halves; a 192-wide tile is split
+  // 128 + 64 so that every warp owns whole 64-column groups (the sum-of-squares partials are per 64 columns)
+  constexpr int NCH = BLOCK_N == 192 ? 4 : BLOCK_N / 64;
+  const int nch = (BLOCK_N == 192 && half == 1) ? 2 : NCH;
+  const int col_off = BLOCK_N == 192 ? half * 128 : half * (BLOCK_N / 2);
   constexpr int SLOTS = EPI == GEMM_EPI_SWIGLU ? 2 : 4;
   EpiRow er;
   const int row = m0 + quad * 32 + lane;
@@ -301,8 +305,8 @@ SLIME_DEVINL void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m0, 
   EpiCoal ec = {};
   if constexpr (STAGED) ec = epi_make_coal<SLOTS>(er, lane);
 
-  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + half * (BLOCK_N / 2);
-  const int col_begin = n0 + half * (BLOCK_N / 2);
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + col_off;
+  const int col_begin = n0 + col_off;
 
   uint32_t acc[2][32];
   uint4 res[2][4];
@@ -313,7 +317,8 @@ SLIME_DEVINL void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m0, 
   tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    if (i + 1 < NCH) {
+    if (i >= nch) break;
+    if (i + 1 < nch) {
       tmem_ld_32x32b_x32(taddr + (i + 1) * 32, acc[(i + 1) & 1]);
       if constexpr (EPI != GEMM_EPI_SWIGLU) epi_issue_bias(p, col_begin + (i + 1) * 32, bia[(i + 1) & 1]);
       epi_issue_residual<EPI, STAGED>(p, er, ec, lane, col_begin + (i + 1) * 32, res[(i + 1) & 1]);
@@ -331,6 +336,6 @@ SLIME_DEVINL void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m0, 
         }
       }
     }
-    if (i + 1 < NCH) tmem_ld_wait();
+    if (i + 1 < nch) tmem_ld_wait();
   }
 }

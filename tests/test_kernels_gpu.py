@@ -357,6 +357,47 @@ def test_gemm_2cta_epilogues(force_2cta):
     assert_close_bf16(out, ref, "gemm 2cta + swiglu")
 
 
+@pytest.mark.parametrize("epi_mode", [0, 1])
+def test_gemm_2cta_tile_width_bit_identical(epi_mode):
+    """192-column cluster tiles (small problems: fewer width-weighted waves) against the 256-column throughput shape: every
+    output element accumulates over k in the same order, so all epilogues must give the same bits - ragged M, N not a
+    multiple of either width, row map, periodic residual, fp32 out, SwiGLU; also against fp32 math."""
+    L = _lib()
+    lib = L.load()
+    torch.manual_seed(9)
+    M, N, K = 1379, 4096, 512
+    a, w, bias, h = rnd(M, K), rnd(N, K, scale=0.05), rnd(N), rnd(M, N)
+    a2, w2, b2 = rnd(1000, 256), rnd(1064, 256, scale=0.05), rnd(1064)
+    table = rnd(37, 1064)
+    row_map = torch.randperm(1000, device="cuda").to(torch.int32)
+    row_map[::7] = -1
+    gu = rnd(2048, 256, scale=0.05)
+    res = {}
+    lib.slime_gemm_set_2cta_mode(1)
+    L.check(lib.slime_gemm_set_epi_mode(epi_mode), "set_epi_mode")
+    try:
+        for bn in (256, 192):
+            L.check(lib.slime_gemm_set_tile_n(bn), "set_tile_n")
+            res[bn] = [
+                gemm(a, w, bias=bias),
+                gemm(a, w, bias=bias, residual=h),
+                gemm(a2, w2, residual=table, res_period=37),
+                gemm(a2, w2, bias=b2, epi=L.EPI_QUICK_GELU),
+                gemm(a2, w2, bias=b2, epi=L.EPI_GELU_ERF),
+                gemm(a2, w2, bias=b2, row_map=row_map),
+                gemm(a2, gu, epi=L.EPI_SWIGLU),
+                gemm(a2, w2, bias=b2, f32=True),
+            ]
+    finally:
+        lib.slime_gemm_set_tile_n(-1)
+        lib.slime_gemm_set_epi_mode(-1)
+        lib.slime_gemm_set_2cta_mode(-1)
+    for i, (x, y) in enumerate(zip(res[256], res[192])):
+        assert torch.equal(x, y), f"192-wide tiles differ from 256-wide in case {i} (epi_mode={epi_mode})"
+    assert_close_bf16(res[192][1], a.float() @ w.float().t() + bias.float() + h.float(), "gemm 192-wide + residual")
+    assert lib.slime_gemm_set_tile_n(7) < 0  # only -1, 0, 192, 256
+
+
 # ------------------------------------------------------------------------------------------------
 # opt-in / alternative code paths: staged GEMM epilogue, softmax variants, RoPE in the QKV epilogue
 # ------------------------------------------------------------------------------------------------
