@@ -608,8 +608,26 @@ def main():
 
         def lat(e, c, crops, T):
             r = short_run(torch, None, e, c, 1, crops, T, rank, 1, dev, steps=20)
-            return {"ms": r["ms_per_step"], "tokens_per_s": r["tokens_per_s"],
-                    "whole_step_frac": r["whole_step_tflops_per_gpu"] / peaks["tf_sustained"], "mean_len": r["mean_len"]}
+            out = {"ms": r["ms_per_step"], "tokens_per_s": r["tokens_per_s"],
+                   "whole_step_frac": r["whole_step_tflops_per_gpu"] / peaks["tf_sustained"], "mean_len": r["mean_len"]}
+            try:  # the same step captured in a CUDA graph (slime_b200.engine.GraphedPrefill: no host sync, one graph launch)
+                from slime_b200.engine import GraphedPrefill
+                b1 = Bench(torch, None, e, c, 1, crops, T, rank, 1, dev)
+                g = GraphedPrefill(e, 1, crops, T, grids=b1.grids)
+                for _ in range(3):
+                    g(b1.px_d, b1.ids_d, b1.mask_d)
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                t0.record()
+                for _ in range(20):
+                    g(b1.px_d, b1.ids_d, b1.mask_d)
+                t1.record()
+                torch.cuda.synchronize()
+                out["ms_graph"] = t0.elapsed_time(t1) / 20
+                del g
+            except Exception as ex:  # noqa: BLE001
+                out["ms_graph_error"] = repr(ex)
+            return out
 
         # batch-1 latency (the reference's eval loop is batch 1, llava/eval/model_vqa_loader.py:103-119)
         guarded("latency_b1", lambda: {"headline_llama3_8b_T256": lat(eng, cfg, args.crops, args.prompt_len)})
